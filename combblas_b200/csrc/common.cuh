@@ -1,0 +1,135 @@
+// Shared internals of libcbgpu.so (sm_100a). Not part of the public ABI (include/cbgpu.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/cbgpu.h"
+
+namespace cbgpu {
+
+constexpr int kSMs = 148; // B200: 2 dies x 74 SMs; grids are sized in multiples of this where it matters
+constexpr unsigned kEmptyKey = 0xFFFFFFFFu;
+
+struct Options {
+  // symbolic (keys only) hash limits, in products per task
+  int64_t sym_warp_small = 32;   // warp table 64
+  int64_t sym_warp_max = 256;    // warp table 512
+  int64_t sym_cta_small = 2048;  // CTA(256) table 4096
+  int64_t sym_cta_max = 16384;   // CTA(512) table 32768
+  // numeric (key+value) hash limits, in output entries per task
+  int64_t num_warp_small = 32;   // warp table 64
+  int64_t num_warp_max = 256;    // warp table 512
+  int64_t num_cta_max = 2048;    // CTA(256) table 4096
+  // bitmap path
+  int64_t bitmap_window_log2 = 19; // rows per window (2^19 rows = 64 KiB bitmap + 32 KiB rank index)
+  int64_t bitmap_min_nnz = 0;      // 0 = automatic: clamp(window_rows/2048, 32, num_cta_max)
+  int64_t bitmap_smem_acc = 12288; // accumulators kept in shared memory up to this many outputs per task
+  int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only
+};
+
+} // namespace cbgpu
+
+// the opaque handles of include/cbgpu.h
+struct cbgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string last_error;
+  cbgpu::Options opt;
+  int64_t launches = 0;
+  int sm_count = cbgpu::kSMs;
+  int max_smem_optin = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct cbgpu_mat {
+  int64_t m = 0, n = 0, nnz = 0, nzc = 0;
+  int dtype = CBGPU_F64;
+  int64_t *jc = nullptr;     // [nzc]
+  int64_t *cp = nullptr;     // [nzc+1]
+  int32_t *ir = nullptr;     // [nnz]
+  void *numx = nullptr;      // [nnz]
+  int64_t *colptr = nullptr; // [n+1] dense column index, built on demand (replaces Dcsc::ConstructAux/FillColInds)
+  int device = 0;
+};
+
+namespace cbgpu {
+typedef ::cbgpu_ctx cbgpu_ctx_impl;
+typedef ::cbgpu_mat cbgpu_mat_impl;
+
+inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case CBGPU_F64: return 8;
+    case CBGPU_F32: return 4;
+    case CBGPU_I64: return 8;
+    case CBGPU_I32: return 4;
+    case CBGPU_BOOL: return 1;
+  }
+  return 0;
+}
+
+int set_error(cbgpu_ctx_impl *ctx, int code, const char *fmt, ...);
+
+#define CB_CUDA(ctx, expr)                                                                                             \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess) {                                                                                           \
+      return ::cbgpu::set_error((ctx), _e == cudaErrorMemoryAllocation ? CBGPU_ERR_NOMEM : CBGPU_ERR_CUDA,             \
+                                "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e));           \
+    }                                                                                                                  \
+  } while (0)
+
+#define CB_TRY(expr)                                                                                                   \
+  do {                                                                                                                 \
+    int _rc = (expr);                                                                                                  \
+    if (_rc != CBGPU_OK) return _rc;                                                                                   \
+  } while (0)
+
+#define CB_LAUNCH_CHECK(ctx)                                                                                           \
+  do {                                                                                                                 \
+    (ctx)->launches++;                                                                                                 \
+    CB_CUDA(ctx, cudaGetLastError());                                                                                  \
+  } while (0)
+
+// stream-ordered allocation helpers (cudaMallocAsync pool; no implicit device sync)
+int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes);
+int dev_free(cbgpu_ctx_impl *ctx, void *p);
+template <class T>
+inline int dev_alloc_t(cbgpu_ctx_impl *ctx, T **p, size_t count) {
+  return dev_alloc(ctx, reinterpret_cast<void **>(p), count * sizeof(T));
+}
+
+// device-wide primitives (util.cu)
+int exclusive_scan_i64(cbgpu_ctx_impl *ctx, const int64_t *in, int64_t *out, int64_t n); // out has n+1 entries
+int fill_i64(cbgpu_ctx_impl *ctx, int64_t *p, int64_t n, int64_t v);
+int ensure_dense_colptr(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M);
+int mat_alloc(cbgpu_ctx_impl *ctx, int64_t m, int64_t n, int64_t nnz, int64_t nzc, int dtype, cbgpu_mat_impl **out);
+int mat_release(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M);
+// builds DCSC (jc, cp) of the non-empty columns from per-column counts over `ncols_in` candidate columns
+int compact_columns(cbgpu_ctx_impl *ctx, const int64_t *cand_ids /*may be null: identity*/, const int64_t *cand_ptr,
+                    int64_t ncand, int64_t **jc, int64_t **cp, int64_t *nzc);
+
+// per-semiring entry points generated from accumulate.cuh (one translation unit per semiring)
+struct SpgemmArgs {
+  cbgpu_ctx_impl *ctx;
+  cbgpu_mat_impl *A, *B;
+  cbgpu_mat_impl **C; // null: symbolic only
+  cbgpu_stats *stats;
+  int64_t *flops_out, *nnz_out;
+};
+struct MergeArgs {
+  cbgpu_ctx_impl *ctx;
+  int k;
+  cbgpu_mat_impl *const *lists;
+  cbgpu_mat_impl **out;
+  cbgpu_stats *stats;
+};
+typedef int (*spgemm_fn)(const SpgemmArgs &);
+typedef int (*merge_fn)(const MergeArgs &);
+spgemm_fn spgemm_entry(int semiring);
+merge_fn merge_entry(int semiring);
+int semiring_types(int semiring, int *a, int *b, int *c);
+
+} // namespace cbgpu

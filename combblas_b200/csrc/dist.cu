@@ -1,0 +1,459 @@
+// Distributed semiring SpGEMM: process-grid arithmetic (host only) and the 2D / 3D Sparse SUMMA drivers with
+// NCCL collectives on device-resident DCSC blocks.
+//
+//   Mult_AnXBn_Synch      ParFriends.h:1447-1556  -> cbgpu_summa2d
+//   Mult_AnXBn_SUMMA3D    ParFriends.h:3374-3667  -> cbgpu_summa3d
+//   GetSetSizes/BCastMatrix SpParHelper.cpp:798,:583 -> one ncclAllGather of the essentials + grouped ncclBroadcast
+//   fiber Alltoallv       ParFriends.h:3578-3612  -> grouped ncclSend/ncclRecv of column slabs
+//   CommGrid / CommGrid3D rank maps: src/CommGrid.cpp:57-58, CommGrid3D.h:75-93
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2 -- inside a torch process this is torch's own copy), so
+// the library loads on machines without NCCL and single-GPU use never touches it.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include "common.cuh"
+#include "util.cuh"
+
+namespace cbgpu {
+int mat_colslice(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *M, int64_t c0, int64_t c1, cbgpu_mat_impl **out);
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static NcclApi &nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+#define LOAD(field, sym)                                                                                               \
+  *(void **)(&api.field) = dlsym(api.handle, sym);                                                                     \
+  if (!api.field) return api;
+  LOAD(GetUniqueId, "ncclGetUniqueId")
+  LOAD(CommInitRank, "ncclCommInitRank")
+  LOAD(CommSplit, "ncclCommSplit")
+  LOAD(CommDestroy, "ncclCommDestroy")
+  LOAD(Broadcast, "ncclBroadcast")
+  LOAD(AllGather, "ncclAllGather")
+  LOAD(Send, "ncclSend")
+  LOAD(Recv, "ncclRecv")
+  LOAD(GroupStart, "ncclGroupStart")
+  LOAD(GroupEnd, "ncclGroupEnd")
+  LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+  api.ok = true;
+  return api;
+}
+
+#define CB_NCCL(ctx, expr)                                                                                             \
+  do {                                                                                                                 \
+    ncclResult_t _r = (expr);                                                                                          \
+    if (_r != ncclSuccess)                                                                                             \
+      return set_error((ctx), CBGPU_ERR_NCCL, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                     \
+                       nccl().GetErrorString ? nccl().GetErrorString(_r) : "?");                                       \
+  } while (0)
+
+} // namespace cbgpu
+
+using namespace cbgpu;
+
+struct cbgpu_comm {
+  cbgpu_grid grid;
+  ncclComm_t world = nullptr, row = nullptr, col = nullptr, fiber = nullptr;
+};
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------- grid arithmetic
+int cbgpu_grid_make(int world, int rank, int layers, cbgpu_grid *g) {
+  if (!g || world < 1 || rank < 0 || rank >= world || layers < 1 || world % layers != 0) return CBGPU_ERR_GRID;
+  int per_layer = world / layers;
+  int pr = (int)floor(sqrt((double)per_layer) + 0.5);
+  if (pr * pr != per_layer) return CBGPU_ERR_GRID; // NOTSQUARE (src/CommGrid.cpp:44-54, CommGrid3D.h:51-58)
+  g->world = world;
+  g->rank = rank;
+  g->layers = layers;
+  g->grid_rows = pr;
+  g->grid_cols = pr;
+  g->my_layer = rank / per_layer;       // CommGrid3D.h:75
+  int in_layer = rank % per_layer;      // CommGrid3D.h:76
+  g->my_row = in_layer / pr;            // src/CommGrid.cpp:57
+  g->my_col = in_layer % pr;            // src/CommGrid.cpp:58
+  return CBGPU_OK;
+}
+
+int cbgpu_block_range(int64_t dim, int parts, int index, int64_t *begin, int64_t *end) {
+  if (parts < 1 || index < 0 || index >= parts || dim < 0) return CBGPU_ERR_INVALID;
+  int64_t per = dim / parts;
+  *begin = per * index;
+  *end = (index == parts - 1) ? dim : per * (index + 1);
+  return CBGPU_OK;
+}
+
+int cbgpu_block_owner(int64_t dim, int parts, int64_t gi) {
+  if (parts < 1 || gi < 0 || gi >= dim) return -1;
+  int64_t per = dim / parts;
+  if (per == 0) return parts - 1;
+  int64_t o = gi / per;
+  return (int)(o < parts - 1 ? o : parts - 1);
+}
+
+int cbgpu_grid_local_range(const cbgpu_grid *g, int64_t m, int64_t n, int split_cols, int64_t *r0, int64_t *r1,
+                           int64_t *c0, int64_t *c1) {
+  if (!g) return CBGPU_ERR_INVALID;
+  int64_t rb, re, cb, ce;
+  cbgpu_block_range(m, g->grid_rows, g->my_row, &rb, &re);
+  cbgpu_block_range(n, g->grid_cols, g->my_col, &cb, &ce);
+  if (g->layers > 1) {
+    int64_t s0, s1;
+    if (split_cols) { // A and C: columns of the 2D block cut into `layers` contiguous chunks (SpParMat3D.cpp:337-402)
+      cbgpu_block_range(ce - cb, g->layers, g->my_layer, &s0, &s1);
+      ce = cb + s1;
+      cb = cb + s0;
+    } else { // B: rows of the 2D block
+      cbgpu_block_range(re - rb, g->layers, g->my_layer, &s0, &s1);
+      re = rb + s1;
+      rb = rb + s0;
+    }
+  }
+  *r0 = rb; *r1 = re; *c0 = cb; *c1 = ce;
+  return CBGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- communicators
+int cbgpu_nccl_unique_id(void *id128) {
+  if (!id128) return CBGPU_ERR_INVALID;
+  if (!nccl().ok) return CBGPU_ERR_NCCL;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return CBGPU_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return CBGPU_OK;
+}
+
+int cbgpu_comm_create(cbgpu_ctx *ctx, const cbgpu_grid *grid, const void *id128, cbgpu_comm **out) {
+  if (!ctx || !grid || !id128 || !out) return CBGPU_ERR_INVALID;
+  if (!nccl().ok) return set_error(ctx, CBGPU_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cbgpu_comm *c = new cbgpu_comm();
+  c->grid = *grid;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  CB_NCCL(ctx, nccl().CommInitRank(&c->world, grid->world, id, grid->rank));
+  const int pr = grid->grid_rows, pc = grid->grid_cols;
+  // row world: same layer, same grid row, ordered by column  (src/CommGrid.cpp:66)
+  CB_NCCL(ctx, nccl().CommSplit(c->world, grid->my_layer * pr + grid->my_row, grid->my_col, &c->row, nullptr));
+  // column world: same layer, same grid column, ordered by row (src/CommGrid.cpp:67)
+  CB_NCCL(ctx, nccl().CommSplit(c->world, grid->my_layer * pc + grid->my_col, grid->my_row, &c->col, nullptr));
+  // fiber world: same position in every layer, ordered by layer (CommGrid3D.h:77-78)
+  CB_NCCL(ctx, nccl().CommSplit(c->world, grid->my_row * pc + grid->my_col, grid->my_layer, &c->fiber, nullptr));
+  *out = c;
+  return CBGPU_OK;
+}
+
+int cbgpu_comm_destroy(cbgpu_comm *c) {
+  if (!c) return CBGPU_OK;
+  if (nccl().ok) {
+    if (c->row) nccl().CommDestroy(c->row);
+    if (c->col) nccl().CommDestroy(c->col);
+    if (c->fiber) nccl().CommDestroy(c->fiber);
+    if (c->world) nccl().CommDestroy(c->world);
+  }
+  delete c;
+  return CBGPU_OK;
+}
+
+} // extern "C"
+
+namespace cbgpu {
+
+static ncclDataType_t nccl_bytes() { return ncclUint8; }
+
+// essentials {nnz, nzc, m, n} of every block in a communicator (GetSetSizes, SpParHelper.cpp:798-809)
+static int gather_essentials(cbgpu_ctx *ctx, ncclComm_t comm, int nranks, const cbgpu_mat *M, std::vector<int64_t> &ess) {
+  int64_t mine[4] = {M->nnz, M->nzc, M->m, M->n};
+  int64_t *d = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &d, (size_t)4 * (nranks + 1)));
+  CB_CUDA(ctx, cudaMemcpyAsync(d, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  CB_NCCL(ctx, nccl().AllGather(d, d + 4, 4, ncclInt64, comm, ctx->stream));
+  ess.resize((size_t)4 * nranks);
+  CB_CUDA(ctx, cudaMemcpyAsync(ess.data(), d + 4, sizeof(int64_t) * 4 * nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CB_TRY(dev_free(ctx, d));
+  return CBGPU_OK;
+}
+
+// BCastMatrix (SpParHelper.cpp:583-603): the four DCSC arrays of the root's block, device to device
+static int bcast_block(cbgpu_ctx *ctx, ncclComm_t comm, int root, int me, const cbgpu_mat *own, const int64_t *ess,
+                       int dtype, cbgpu_mat **recv, int64_t *bytes) {
+  const int64_t nnz = ess[0], nzc = ess[1], m = ess[2], n = ess[3];
+  cbgpu_mat *R = nullptr;
+  const cbgpu_mat *src = own;
+  if (me != root) {
+    CB_TRY(mat_alloc(ctx, m, n, nnz, nzc, dtype, &R));
+    src = R;
+  }
+  const size_t vb = dtype_size(dtype);
+  if (nnz > 0) {
+    CB_NCCL(ctx, nccl().GroupStart());
+    CB_NCCL(ctx, nccl().Broadcast(src->jc, src->jc, (size_t)nzc * 8, nccl_bytes(), root, comm, ctx->stream));
+    CB_NCCL(ctx, nccl().Broadcast(src->cp, src->cp, (size_t)(nzc + 1) * 8, nccl_bytes(), root, comm, ctx->stream));
+    CB_NCCL(ctx, nccl().Broadcast(src->ir, src->ir, (size_t)nnz * 4, nccl_bytes(), root, comm, ctx->stream));
+    CB_NCCL(ctx, nccl().Broadcast(src->numx, src->numx, (size_t)nnz * vb, nccl_bytes(), root, comm, ctx->stream));
+    CB_NCCL(ctx, nccl().GroupEnd());
+    *bytes += nzc * 16 + 8 + nnz * (4 + (int64_t)vb);
+  } else if (R) {
+    CB_CUDA(ctx, cudaMemsetAsync(R->cp, 0, 8, ctx->stream));
+  }
+  *recv = R;
+  return CBGPU_OK;
+}
+
+static void add_stats(cbgpu_stats &acc, const cbgpu_stats &s) {
+  acc.flops += s.flops; acc.tasks += s.tasks; acc.kernel_launches += s.kernel_launches;
+  acc.ms_setup += s.ms_setup; acc.ms_symbolic += s.ms_symbolic; acc.ms_numeric += s.ms_numeric; acc.ms_total += s.ms_total;
+  acc.tasks_hash_warp += s.tasks_hash_warp; acc.tasks_hash_cta += s.tasks_hash_cta;
+  acc.tasks_bitmap_smem += s.tasks_bitmap_smem; acc.tasks_bitmap_gmem += s.tasks_bitmap_gmem;
+  acc.flops_hash_warp += s.flops_hash_warp; acc.flops_hash_cta += s.flops_hash_cta;
+  acc.flops_bitmap_smem += s.flops_bitmap_smem; acc.flops_bitmap_gmem += s.flops_bitmap_gmem;
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  cudaStream_t s;
+  Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, s); }
+  float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+// the SUMMA loop of one layer (ParFriends.h:1482-1532): stage i multiplies A(:, i-th block) by B(i-th block, :)
+static int summa_layer(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, cbgpu_mat **C,
+                       cbgpu_dist_stats *ds) {
+  const cbgpu_grid &g = comm->grid;
+  const int stages = g.grid_cols;
+  int ta, tb, tc;
+  CB_TRY(semiring_types(semiring, &ta, &tb, &tc));
+  if (A->dtype != ta || B->dtype != tb) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "operand types do not match the semiring");
+  std::vector<int64_t> essA, essB;
+  Timer tm(ctx->stream);
+  tm.start();
+  if (stages > 1) {
+    CB_TRY(gather_essentials(ctx, comm->row, stages, A, essA));
+    CB_TRY(gather_essentials(ctx, comm->col, stages, B, essB));
+  } else {
+    essA = {A->nnz, A->nzc, A->m, A->n};
+    essB = {B->nnz, B->nzc, B->m, B->n};
+  }
+  ds->ms_bcast += tm.stop();
+  std::vector<cbgpu_mat *> partial;
+  int rc = CBGPU_OK;
+  for (int i = 0; i < stages && rc == CBGPU_OK; ++i) {
+    cbgpu_mat *Ar = nullptr, *Br = nullptr;
+    const cbgpu_mat *Ause = A, *Buse = B;
+    tm.start();
+    if (stages > 1) {
+      rc = bcast_block(ctx, comm->row, i, g.my_col, A, &essA[4 * i], ta, &Ar, &ds->bytes_bcast);
+      if (rc == CBGPU_OK) rc = bcast_block(ctx, comm->col, i, g.my_row, B, &essB[4 * i], tb, &Br, &ds->bytes_bcast);
+      if (Ar) Ause = Ar;
+      if (Br) Buse = Br;
+    }
+    ds->ms_bcast += tm.stop();
+    if (rc == CBGPU_OK) {
+      if (Ause->n != Buse->m) rc = set_error(ctx, CBGPU_ERR_DIMMISMATCH, "stage %d: inner block dimensions differ (%lld vs %lld)", i, (long long)Ause->n, (long long)Buse->m);
+    }
+    if (rc == CBGPU_OK && Ause->nnz > 0 && Buse->nnz > 0) {
+      cbgpu_mat *Ci = nullptr;
+      cbgpu_stats st;
+      memset(&st, 0, sizeof(st));
+      tm.start();
+      rc = cbgpu_spgemm_local(ctx, semiring, Ause, Buse, &Ci, &st);
+      ds->ms_multiply += tm.stop();
+      if (rc == CBGPU_OK) {
+        add_stats(ds->local, st);
+        if (Ci->nnz > 0) partial.push_back(Ci); // empty stage results are not merged (ParFriends.h:1524)
+        else mat_release(ctx, Ci);
+      }
+    }
+    mat_release(ctx, Ar);
+    mat_release(ctx, Br);
+    ds->stages++;
+  }
+  if (rc == CBGPU_OK) {
+    tm.start();
+    if (partial.empty()) {
+      cbgpu_mat *E = nullptr;
+      rc = mat_alloc(ctx, A->m, B->n, 0, 0, tc, &E);
+      if (rc == CBGPU_OK) {
+        cudaMemsetAsync(E->cp, 0, 8, ctx->stream);
+        *C = E;
+      }
+    } else if (partial.size() == 1) {
+      *C = partial[0]; // MultiwayMerge steals a single list (MultiwayMerge.h:437-442)
+      partial.clear();
+    } else {
+      cbgpu_stats st;
+      memset(&st, 0, sizeof(st));
+      rc = cbgpu_merge(ctx, semiring, (int)partial.size(), partial.data(), C, &st);
+      ds->local.kernel_launches += st.kernel_launches;
+    }
+    ds->ms_merge += tm.stop();
+  }
+  for (cbgpu_mat *p : partial) mat_release(ctx, p);
+  return rc;
+}
+
+} // namespace cbgpu
+
+extern "C" {
+
+int cbgpu_summa2d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, cbgpu_mat **C,
+                  cbgpu_dist_stats *stats) {
+  if (!ctx || !comm || !A || !B || !C) return CBGPU_ERR_INVALID;
+  if (comm->grid.layers != 1) return set_error(ctx, CBGPU_ERR_GRID, "cbgpu_summa2d needs a single-layer grid");
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cbgpu_dist_stats ds;
+  memset(&ds, 0, sizeof(ds));
+  Timer all(ctx->stream);
+  all.start();
+  int rc = summa_layer(ctx, comm, semiring, A, B, C, &ds);
+  ds.ms_total = all.stop();
+  if (stats) *stats = ds;
+  return rc;
+}
+
+int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, cbgpu_mat **C,
+                  cbgpu_dist_stats *stats) {
+  if (!ctx || !comm || !A || !B || !C) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const cbgpu_grid &g = comm->grid;
+  const int L = g.layers;
+  cbgpu_dist_stats ds;
+  memset(&ds, 0, sizeof(ds));
+  Timer all(ctx->stream), tm(ctx->stream);
+  all.start();
+  cbgpu_mat *Cl = nullptr; // this layer's partial product: full block shape
+  CB_TRY(summa_layer(ctx, comm, semiring, A, B, &Cl, &ds));
+  if (L == 1) {
+    *C = Cl;
+    ds.ms_total = all.stop();
+    if (stats) *stats = ds;
+    return CBGPU_OK;
+  }
+  // ---- cut the layer result into L column slabs (CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576-609;
+  //      send ranges ParFriends.h:3578-3600); slab l belongs to fiber rank l
+  int rc = CBGPU_OK;
+  tm.start();
+  std::vector<cbgpu_mat *> slab(L, nullptr), recv(L, nullptr);
+  for (int l = 0; l < L && rc == CBGPU_OK; ++l) {
+    int64_t c0, c1;
+    cbgpu_block_range(Cl->n, L, l, &c0, &c1);
+    rc = mat_colslice(ctx, Cl, c0, c1, &slab[l]);
+  }
+  mat_release(ctx, Cl);
+  // ---- sizes: every rank tells every fiber peer {nnz, nzc} of the slab it will send (ParFriends.h:3602)
+  std::vector<int64_t> sizes((size_t)2 * L * L, 0);
+  if (rc == CBGPU_OK) {
+    std::vector<int64_t> mine((size_t)2 * L);
+    for (int l = 0; l < L; ++l) { mine[2 * l] = slab[l]->nnz; mine[2 * l + 1] = slab[l]->nzc; }
+    int64_t *d = nullptr;
+    rc = dev_alloc_t(ctx, &d, (size_t)2 * L * (L + 1));
+    if (rc == CBGPU_OK) {
+      cudaMemcpyAsync(d, mine.data(), sizeof(int64_t) * 2 * L, cudaMemcpyHostToDevice, ctx->stream);
+      ncclResult_t r = nccl().AllGather(d, d + 2 * L, (size_t)2 * L, ncclInt64, comm->fiber, ctx->stream);
+      if (r != ncclSuccess) rc = set_error(ctx, CBGPU_ERR_NCCL, "fiber allgather failed: %s", nccl().GetErrorString(r));
+      cudaMemcpyAsync(sizes.data(), d + 2 * L, sizeof(int64_t) * 2 * L * L, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      dev_free(ctx, d);
+    }
+  }
+  // ---- exchange (ParFriends.h:3612): grouped send/recv of the four arrays per peer
+  const int me = g.my_layer;
+  int tc = slab[0] ? slab[0]->dtype : CBGPU_F64;
+  const size_t vb = dtype_size(tc);
+  if (rc == CBGPU_OK) {
+    for (int p = 0; p < L && rc == CBGPU_OK; ++p) {
+      if (p == me) continue;
+      int64_t nnz = sizes[(size_t)2 * L * p + 2 * me], nzc = sizes[(size_t)2 * L * p + 2 * me + 1];
+      rc = mat_alloc(ctx, slab[me]->m, slab[me]->n, nnz, nzc, tc, &recv[p]);
+      if (rc == CBGPU_OK && nzc == 0) cudaMemsetAsync(recv[p]->cp, 0, 8, ctx->stream);
+    }
+  }
+  if (rc == CBGPU_OK) {
+    ncclResult_t r = nccl().GroupStart();
+    for (int p = 0; p < L && r == ncclSuccess; ++p) {
+      if (p == me) continue;
+      cbgpu_mat *S = slab[p], *R = recv[p];
+      if (S->nnz > 0) {
+        r = nccl().Send(S->jc, (size_t)S->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Send(S->cp, (size_t)(S->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Send(S->ir, (size_t)S->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Send(S->numx, (size_t)S->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+        ds.bytes_fiber += S->nzc * 16 + 8 + S->nnz * (4 + (int64_t)vb);
+      }
+      if (r == ncclSuccess && R->nnz > 0) {
+        r = nccl().Recv(R->jc, (size_t)R->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Recv(R->cp, (size_t)(R->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Recv(R->ir, (size_t)R->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Recv(R->numx, (size_t)R->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+      }
+    }
+    ncclResult_t r2 = nccl().GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess)
+      rc = set_error(ctx, CBGPU_ERR_NCCL, "fiber exchange failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
+  }
+  ds.ms_fiber_exchange = tm.stop();
+  // ---- merge what arrived with my own slab (ParFriends.h:3642)
+  if (rc == CBGPU_OK) {
+    tm.start();
+    std::vector<cbgpu_mat *> lists;
+    for (int p = 0; p < L; ++p) {
+      cbgpu_mat *M = (p == me) ? slab[me] : recv[p];
+      if (M && M->nnz > 0) lists.push_back(M);
+    }
+    if (lists.empty()) {
+      *C = slab[me];
+      slab[me] = nullptr;
+    } else if (lists.size() == 1) {
+      *C = lists[0];
+      for (int p = 0; p < L; ++p) {
+        if (slab[p] == lists[0]) slab[p] = nullptr;
+        if (recv[p] == lists[0]) recv[p] = nullptr;
+      }
+    } else {
+      cbgpu_stats st;
+      memset(&st, 0, sizeof(st));
+      rc = cbgpu_merge(ctx, semiring, (int)lists.size(), lists.data(), C, &st);
+      ds.local.kernel_launches += st.kernel_launches;
+    }
+    ds.ms_fiber_merge = tm.stop();
+  }
+  for (int p = 0; p < L; ++p) {
+    mat_release(ctx, slab[p]);
+    mat_release(ctx, recv[p]);
+  }
+  ds.ms_total = all.stop();
+  if (stats) *stats = ds;
+  return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,538 @@
+// Column-accumulation engine: the sm_100a replacement for the reference's per-column loops
+//   estimateFLOP (mtSpGEMM.h:1058), estimateNNZ_Hash (:807), the numeric hash column of
+//   LocalHybridSpGEMM / LocalSpGEMMHash (:362-440, :552-634) and the merge column of
+//   MultiwayMerge[Hash] (MultiwayMerge.h:194-248, :338-422).
+//
+// One engine serves both the multiply and the k-way merge: a TASK is (output column, row window) and a
+// task's input is a list of SEGMENTS -- contiguous runs of (row, value) in one array pair:
+//   multiply: one segment per nonzero B(k,j): the part of A(:,k) inside the row window, scaled by B(k,j)
+//   merge   : one segment per input list: the part of L_s(:,j) inside the row window
+// Segment bounds come from a monotone table T[col*nwin + w] (for one window this is the dense column
+// pointer array itself; it replaces Dcsc::ConstructAux/FillColInds, dcsc.cpp:1043,:1363).
+//
+// Per task the engine runs a symbolic pass (count distinct rows) and, after an exclusive scan over the
+// counts, a numeric pass that writes the column's rows ASCENDING together with the accumulated values:
+//   hash path   (small tasks) : shared-memory open addressing per warp or per CTA + bitonic sort of the hits
+//   bitmap path (large tasks) : shared-memory presence bitmap of the row window; popcount ranks give every row
+//                               its sorted output slot directly, so there is no sort and no probing;
+//                               values accumulate in shared memory, or straight into C in HBM (L2 atomics)
+//                               when the task has more outputs than fit.
+// No tensor cores: the work is irregular integer/atomic traffic; the levers are coalesced segment reads,
+// shared-memory atomics, and keeping every SM busy with size-ordered tasks.
+#pragma once
+#include "common.cuh"
+#include "semiring.cuh"
+
+namespace cbgpu {
+
+constexpr int kWarpLong = 48;    // segments at least this long are walked by a whole warp
+constexpr int kCtaLong = 1536;   // ... and at least this long by the whole CTA (via a small queue)
+constexpr int kQueueCap = 96;
+constexpr int kBitmapThreads = 512;
+constexpr int kLightMax = 2048;  // with several row windows, columns up to this many products stay one task
+
+// ------------------------------------------------------------------------------------------------ source
+template <class SR, bool MERGE>
+struct Source {
+  typedef typename std::conditional<MERGE, typename SR::out_t, typename SR::a_t>::type aval_t;
+  typedef typename SR::b_t mult_t;
+  const int64_t *T;   // segment table, stride nwin
+  int nwin;
+  int wlog2;
+  const int32_t *Air;
+  const aval_t *Aval;
+  // multiply
+  const int64_t *Bcp;
+  const int32_t *Bir;
+  const mult_t *Bval;
+  // merge
+  int k;
+  int64_t n;
+  // tasks (null task_col: task t is column t over all windows)
+  const int32_t *task_col;
+  const uint32_t *task_win;
+};
+
+struct Task {
+  int col;      // multiply: index into B's non-empty columns; merge: column id
+  int wlo, whi; // row windows [wlo, whi)
+  int64_t seg_begin, seg_end;
+};
+
+template <class Src>
+__device__ __forceinline__ Task load_task(const Src &s, int t) {
+  Task k;
+  if (s.task_col) {
+    k.col = s.task_col[t];
+    unsigned w = s.task_win[t];
+    k.wlo = (int)(w & 0xFFFFu);
+    k.whi = (int)(w >> 16);
+  } else {
+    k.col = t;
+    k.wlo = 0;
+    k.whi = s.nwin;
+  }
+  return k;
+}
+
+template <class SR, bool MERGE>
+__device__ __forceinline__ void task_segments(const Source<SR, MERGE> &s, Task &k) {
+  if (MERGE) {
+    k.seg_begin = 0;
+    k.seg_end = s.k;
+  } else {
+    k.seg_begin = s.Bcp[k.col];
+    k.seg_end = s.Bcp[k.col + 1];
+  }
+}
+
+// segment p of task k: [beg, beg+len) in Air/Aval, with its multiplier
+template <class SR, bool MERGE, bool NEED_MULT>
+__device__ __forceinline__ void load_segment(const Source<SR, MERGE> &s, const Task &k, int64_t p, int64_t &beg, int &len,
+                                             typename SR::b_t &mult) {
+  int64_t col;
+  if (MERGE) {
+    col = p * s.n + k.col;
+  } else {
+    col = s.Bir[p];
+    if (NEED_MULT) mult = s.Bval[p];
+  }
+  const int64_t *t = s.T + col * s.nwin;
+  beg = t[k.wlo];
+  len = (int)(t[k.whi] - beg);
+}
+
+// ------------------------------------------------------------------------------------------------ product walk
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+template <class M>
+__device__ __forceinline__ M shfl_mult(M v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+template <>
+__device__ __forceinline__ uint8_t shfl_mult<uint8_t>(uint8_t v, int src) {
+  return (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)v, src);
+}
+
+struct CtaQueue {
+  int n;
+  int len[kQueueCap];
+  long long beg[kQueueCap];
+  unsigned long long mult[kQueueCap]; // raw bits of the multiplier
+};
+
+template <class M>
+__device__ __forceinline__ unsigned long long mult_bits(M v) {
+  unsigned long long r = 0;
+  memcpy(&r, &v, sizeof(M));
+  return r;
+}
+template <class M>
+__device__ __forceinline__ M bits_mult(unsigned long long r) {
+  M v;
+  memcpy(&v, &r, sizeof(M));
+  return v;
+}
+
+// One warp walks the segments [first + 32*chunk...] assigned to it. f(pos, mult) is invoked once per product by
+// exactly one lane. Long segments are strided by the whole warp (coalesced), the rest are flattened so that
+// all 32 lanes stay busy on short A-columns. Segments >= kCtaLong are deferred to `q` when given.
+template <class SR, bool MERGE, bool NEED_MULT, class F>
+__device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task &k, int warp_in_group, int group_warps,
+                                          CtaQueue *q, F &&f) {
+  typedef typename SR::b_t mult_t;
+  const int lane = lane_id();
+  for (int64_t base = k.seg_begin + (int64_t)warp_in_group * 32; base < k.seg_end; base += (int64_t)group_warps * 32) {
+    int64_t p = base + lane;
+    int64_t beg = 0;
+    int len = 0;
+    mult_t mult = mult_t();
+    if (p < k.seg_end) load_segment<SR, MERGE, NEED_MULT>(s, k, p, beg, len, mult);
+    if (q != nullptr && len >= kCtaLong) {
+      int qi = atomicAdd(&q->n, 1);
+      if (qi < kQueueCap) {
+        q->len[qi] = len;
+        q->beg[qi] = beg;
+        if (NEED_MULT) q->mult[qi] = mult_bits<mult_t>(mult);
+        len = 0;
+      }
+    }
+    // long segments: whole warp, coalesced
+    unsigned longmask = __ballot_sync(0xFFFFFFFFu, len >= kWarpLong);
+    while (longmask) {
+      int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      int64_t b = __shfl_sync(0xFFFFFFFFu, beg, src);
+      int l = __shfl_sync(0xFFFFFFFFu, len, src);
+      mult_t mu = mult_t();
+      if (NEED_MULT) mu = shfl_mult<mult_t>(mult, src);
+      for (int i = lane; i < l; i += 32) f(b + i, mu);
+    }
+    // short segments: flatten over the warp
+    int slen = (len >= kWarpLong) ? 0 : len;
+    int incl = slen;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int excl = incl - slen;
+    int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      int t = t0 + lane;
+      int idx = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        int e = __shfl_sync(0xFFFFFFFFu, excl, idx + step);
+        if (e <= t) idx += step;
+      }
+      int e0 = __shfl_sync(0xFFFFFFFFu, excl, idx);
+      int64_t b = __shfl_sync(0xFFFFFFFFu, beg, idx);
+      mult_t mu = mult_t();
+      if (NEED_MULT) mu = shfl_mult<mult_t>(mult, idx);
+      if (t < total) f(b + (t - e0), mu);
+    }
+  }
+}
+
+// whole-CTA walk = per-warp walk + cooperative pass over the queued very long segments. All threads must call.
+template <class SR, bool MERGE, bool NEED_MULT, class F>
+__device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueue *q, F &&f) {
+  typedef typename SR::b_t mult_t;
+  if (threadIdx.x == 0) q->n = 0;
+  __syncthreads();
+  warp_walk<SR, MERGE, NEED_MULT>(s, k, threadIdx.x >> 5, blockDim.x >> 5, q, f);
+  __syncthreads();
+  int nq = min(q->n, kQueueCap);
+  for (int e = 0; e < nq; ++e) {
+    int64_t b = q->beg[e];
+    int l = q->len[e];
+    mult_t mu = mult_t();
+    if (NEED_MULT) mu = bits_mult<mult_t>(q->mult[e]);
+    for (int i = threadIdx.x; i < l; i += blockDim.x) f(b + i, mu);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ K1: products per task
+template <class SR, bool MERGE>
+__global__ void __launch_bounds__(256) task_flop_kernel(Source<SR, MERGE> s, int64_t ntask, int64_t *flop) {
+  int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= ntask) return; // whole warp exits together
+  Task k = load_task(s, (int)t);
+  task_segments(s, k);
+  int64_t sum = 0;
+  typename SR::b_t dummy;
+  for (int64_t p = k.seg_begin + lane_id(); p < k.seg_end; p += 32) {
+    int64_t beg;
+    int len;
+    load_segment<SR, MERGE, false>(s, k, p, beg, len, dummy);
+    sum += len;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+  if (lane_id() == 0) flop[t] = sum;
+}
+
+// ------------------------------------------------------------------------------------------------ hash tables
+template <int LOG2T>
+__device__ __forceinline__ int hash_row(unsigned row) { return (int)((row * 2654435761u) >> (32 - LOG2T)); }
+
+// returns the slot of `row`; `fresh` is set when this call inserted it
+template <int LOG2T>
+__device__ __forceinline__ int table_insert(unsigned *keys, unsigned row, bool &fresh) {
+  constexpr int MASK = (1 << LOG2T) - 1;
+  int h = hash_row<LOG2T>(row);
+  fresh = false;
+  while (true) {
+    unsigned cur = ((volatile unsigned *)keys)[h];
+    if (cur == row) return h;
+    if (cur == kEmptyKey) {
+      unsigned old = atomicCAS(&keys[h], kEmptyKey, row);
+      if (old == kEmptyKey) {
+        fresh = true;
+        return h;
+      }
+      if (old == row) return h;
+    }
+    h = (h + 1) & MASK;
+  }
+}
+
+template <int GROUP_WARPS>
+__device__ __forceinline__ void group_sync() {
+  if (GROUP_WARPS == 1) __syncwarp();
+  else __syncthreads();
+}
+
+// K2 (hash): distinct rows per task. GROUP_WARPS == 1: one task per warp, 8 tasks per CTA;
+// otherwise one task per CTA of GROUP_WARPS warps.
+template <class SR, bool MERGE, int GROUP_WARPS, int LOG2T>
+__global__ void __launch_bounds__(GROUP_WARPS == 1 ? 256 : GROUP_WARPS * 32)
+sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t *tasknnz) {
+  constexpr int T = 1 << LOG2T;
+  constexpr int GROUPS = GROUP_WARPS == 1 ? 8 : 1;
+  constexpr int GT = GROUP_WARPS * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned *keys_all = reinterpret_cast<unsigned *>(smem_raw);
+  __shared__ CtaQueue queue;
+  __shared__ int cta_count;
+  const int group = GROUP_WARPS == 1 ? (threadIdx.x >> 5) : 0;
+  const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
+  int64_t ti = (int64_t)blockIdx.x * GROUPS + group;
+  const bool valid = ti < count; // uniform per group
+  if (GROUP_WARPS == 1 && !valid) return;
+  unsigned *keys = keys_all + group * T;
+  for (int i = gtid; i < T; i += GT) keys[i] = kEmptyKey;
+  if (GROUP_WARPS > 1 && threadIdx.x == 0) cta_count = 0;
+  group_sync<GROUP_WARPS>();
+  int t = order[ti];
+  Task k = load_task(s, t);
+  task_segments(s, k);
+  int mine = 0;
+  auto f = [&](int64_t pos, typename SR::b_t) {
+    bool fresh;
+    table_insert<LOG2T>(keys, (unsigned)s.Air[pos], fresh);
+    mine += fresh ? 1 : 0;
+  };
+  if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, 0, 1, nullptr, f);
+  else cta_walk<SR, MERGE, false>(s, k, &queue, f);
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+  if (GROUP_WARPS == 1) {
+    if (lane_id() == 0) tasknnz[t] = mine;
+  } else {
+    if (lane_id() == 0 && mine) atomicAdd(&cta_count, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tasknnz[t] = cta_count;
+  }
+}
+
+// bitonic sort of P (power of two) 64-bit keys in shared memory by one group
+template <int GROUP_WARPS>
+__device__ __forceinline__ void group_bitonic(unsigned long long *a, int P, int gtid, int GT) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = gtid; i < P; i += GT) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long x = a[i], y = a[ixj];
+          bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      group_sync<GROUP_WARPS>();
+    }
+  }
+}
+
+// K4 (hash): accumulate, compact, sort by row, emit.
+template <class SR, bool MERGE, int GROUP_WARPS, int LOG2T>
+__global__ void __launch_bounds__(GROUP_WARPS == 1 ? 256 : GROUP_WARPS * 32)
+num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const int64_t *taskptr, int32_t *Cir,
+                typename SR::out_t *Cval) {
+  typedef typename SR::acc_t acc_t;
+  constexpr int T = 1 << LOG2T;
+  constexpr int GROUPS = GROUP_WARPS == 1 ? 8 : 1;
+  constexpr int GT = GROUP_WARPS * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout per CTA: sortbuf[GROUPS*T] u64 | acc[GROUPS*T] acc_t | keys[GROUPS*T] u32 | counters[GROUPS]
+  unsigned long long *sort_all = reinterpret_cast<unsigned long long *>(smem_raw);
+  acc_t *acc_all = reinterpret_cast<acc_t *>(sort_all + GROUPS * T);
+  unsigned *keys_all = reinterpret_cast<unsigned *>(acc_all + GROUPS * T);
+  int *cnt_all = reinterpret_cast<int *>(keys_all + GROUPS * T);
+  __shared__ CtaQueue queue;
+  const int group = GROUP_WARPS == 1 ? (threadIdx.x >> 5) : 0;
+  const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
+  int64_t ti = (int64_t)blockIdx.x * GROUPS + group;
+  if (GROUP_WARPS == 1 && ti >= count) return;
+  unsigned long long *sortbuf = sort_all + group * T;
+  acc_t *acc = acc_all + group * T;
+  unsigned *keys = keys_all + group * T;
+  int *cnt = cnt_all + group;
+  for (int i = gtid; i < T; i += GT) {
+    keys[i] = kEmptyKey;
+    acc[i] = SR::identity();
+  }
+  if (gtid == 0) *cnt = 0;
+  group_sync<GROUP_WARPS>();
+  int t = order[ti];
+  Task k = load_task(s, t);
+  task_segments(s, k);
+  auto f = [&](int64_t pos, typename SR::b_t mu) {
+    bool fresh;
+    int slot = table_insert<LOG2T>(keys, (unsigned)s.Air[pos], fresh);
+    acc_t v;
+    if (MERGE) v = SR::from_out((typename SR::out_t)s.Aval[pos]);
+    else v = SR::mul((typename SR::a_t)s.Aval[pos], mu);
+    SR::accumulate(&acc[slot], v);
+  };
+  if (GROUP_WARPS == 1) {
+    warp_walk<SR, MERGE, true>(s, k, 0, 1, nullptr, f);
+    __syncwarp();
+  } else {
+    cta_walk<SR, MERGE, true>(s, k, &queue, f);
+  }
+  // compact the occupied slots
+  for (int i = gtid; i < T; i += GT) {
+    unsigned key = keys[i];
+    if (key != kEmptyKey) {
+      int pos = atomicAdd(cnt, 1);
+      sortbuf[pos] = ((unsigned long long)key << 32) | (unsigned)i;
+    }
+  }
+  group_sync<GROUP_WARPS>();
+  const int n = *cnt;
+  int P = 2;
+  while (P < n) P <<= 1;
+  for (int i = n + gtid; i < P; i += GT) sortbuf[i] = ~0ull;
+  group_sync<GROUP_WARPS>();
+  group_bitonic<GROUP_WARPS>(sortbuf, P, gtid, GT);
+  const int64_t obase = taskptr[t];
+  for (int i = gtid; i < n; i += GT) {
+    unsigned long long e = sortbuf[i];
+    Cir[obase + i] = (int32_t)(e >> 32);
+    Cval[obase + i] = SR::to_out(acc[(unsigned)e]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bitmap path
+// block-wide exclusive scan of one int per thread (blockDim <= 1024); returns exclusive prefix, total in *total
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /*[32]*/, int *total) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += x;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarp ? warp_sums[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int x = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+      if (lane >= d) wi += x;
+    }
+    warp_sums[lane] = wi - w; // exclusive warp offsets
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  return warp_sums[warp] + incl - v;
+}
+
+template <class SR, bool MERGE>
+__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, CtaQueue *q, unsigned *bm,
+                                            int ncell, int rbase) {
+  uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
+  const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) bm4[i] = make_uint4(0, 0, 0, 0);
+  auto f = [&](int64_t pos, typename SR::b_t) {
+    unsigned r = (unsigned)(s.Air[pos] - rbase);
+    atomicOr(&bm[r >> 5], 1u << (r & 31));
+  };
+  cta_walk<SR, MERGE, false>(s, k, q, f); // starts and ends with __syncthreads
+}
+
+// K2 (bitmap): rows of the window present in the task
+template <class SR, bool MERGE>
+__global__ void __launch_bounds__(kBitmapThreads)
+sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int64_t *tasknnz) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned *bm = reinterpret_cast<unsigned *>(smem_raw);
+  __shared__ CtaQueue queue;
+  __shared__ int warp_sums[32];
+  __shared__ int total;
+  int t = order[blockIdx.x];
+  Task k = load_task(s, t);
+  task_segments(s, k);
+  const int64_t rbase64 = (int64_t)k.wlo << s.wlog2;
+  int64_t rend = (k.whi == s.nwin) ? m : ((int64_t)k.whi << s.wlog2);
+  const int wrows = (int)(rend - rbase64);
+  const int ncell = (wrows + 63) >> 6;
+  bitmap_mark(s, k, &queue, bm, ncell, (int)rbase64);
+  int c = 0;
+  for (int i = threadIdx.x; i < ncell * 2; i += blockDim.x) c += __popc(bm[i]);
+  block_exclusive_scan(c, warp_sums, &total);
+  if (threadIdx.x == 0) tasknnz[t] = total;
+}
+
+// K4 (bitmap): rank every present row by popcount, accumulate values at their final sorted position.
+// GMEM_ACC == false: accumulators in shared memory, copied out at the end;
+// GMEM_ACC == true : accumulators are C's value array itself (atomics resolve in L2).
+template <class SR, bool MERGE, bool GMEM_ACC>
+__global__ void __launch_bounds__(kBitmapThreads)
+num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int max_cells,
+                  const int64_t *taskptr, int32_t *Cir, typename SR::out_t *Cval) {
+  typedef typename SR::acc_t acc_t;
+  typedef typename SR::out_t out_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: bm[2*max_cells] u32 | pre[max_cells] u32 | acc[...] acc_t
+  unsigned *bm = reinterpret_cast<unsigned *>(smem_raw);
+  unsigned *pre = bm + 2 * (size_t)max_cells;
+  acc_t *acc = reinterpret_cast<acc_t *>(pre + max_cells + (max_cells & 1));
+  __shared__ CtaQueue queue;
+  __shared__ int warp_sums[32];
+  __shared__ int total;
+  int t = order[blockIdx.x];
+  Task k = load_task(s, t);
+  task_segments(s, k);
+  const int64_t rbase64 = (int64_t)k.wlo << s.wlog2;
+  int64_t rend = (k.whi == s.nwin) ? m : ((int64_t)k.whi << s.wlog2);
+  const int rbase = (int)rbase64;
+  const int wrows = (int)(rend - rbase64);
+  const int ncell = (wrows + 63) >> 6;
+  bitmap_mark(s, k, &queue, bm, ncell, rbase);
+  // rank index + sorted row ids
+  const int64_t obase = taskptr[t];
+  const int cpt = (ncell + blockDim.x - 1) / blockDim.x;
+  const int c0 = min(ncell, (int)threadIdx.x * cpt), c1 = min(ncell, c0 + cpt);
+  int mine = 0;
+  for (int c = c0; c < c1; ++c) mine += __popc(bm[2 * c]) + __popc(bm[2 * c + 1]);
+  int run = block_exclusive_scan(mine, warp_sums, &total);
+  const int nnz = total;
+  for (int c = c0; c < c1; ++c) {
+    pre[c] = (unsigned)run;
+    unsigned lo = bm[2 * c], hi = bm[2 * c + 1];
+    int rowbase = rbase + (c << 6);
+    while (lo) {
+      int b = __ffs(lo) - 1;
+      lo &= lo - 1;
+      Cir[obase + run++] = rowbase + b;
+    }
+    rowbase += 32;
+    while (hi) {
+      int b = __ffs(hi) - 1;
+      hi &= hi - 1;
+      Cir[obase + run++] = rowbase + b;
+    }
+  }
+  if (GMEM_ACC) {
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(SR::identity());
+  } else {
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) acc[i] = SR::identity();
+  }
+  __syncthreads();
+  auto f = [&](int64_t pos, typename SR::b_t mu) {
+    unsigned r = (unsigned)(s.Air[pos] - rbase);
+    unsigned cell = r >> 6, bit = r & 63;
+    uint2 w = reinterpret_cast<const uint2 *>(bm)[cell];
+    unsigned rank = pre[cell];
+    if (bit >= 32) rank += __popc(w.x) + __popc(w.y & ((1u << (bit - 32)) - 1u));
+    else rank += __popc(w.x & ((1u << bit) - 1u));
+    acc_t v;
+    if (MERGE) v = SR::from_out((out_t)s.Aval[pos]);
+    else v = SR::mul((typename SR::a_t)s.Aval[pos], mu);
+    if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
+    else SR::accumulate(&acc[rank], v);
+  };
+  cta_walk<SR, MERGE, true>(s, k, &queue, f);
+  if (!GMEM_ACC) {
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(acc[i]);
+  }
+}
+
+} // namespace cbgpu

@@ -1,0 +1,346 @@
+// Host-side orchestration of the accumulation engine (engine.cuh): task construction, size binning,
+// symbolic pass, scan, numeric pass, DCSC assembly. Instantiated once per semiring (sr_instance.cu).
+#pragma once
+#include <algorithm>
+#include "engine.cuh"
+#include "util.cuh"
+
+namespace cbgpu {
+
+__device__ __forceinline__ int size_bucket(int64_t v) {
+  if (v <= 0) return 0;
+  if (v == 1) return 1;
+  int b = 1 + (64 - __clzll((unsigned long long)(v - 1)));
+  return b > 39 ? 39 : b;
+}
+
+static __global__ void sym_bucket_kernel(const int64_t *flop, int64_t ntask, uint8_t *bucket) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ntask) bucket[i] = (uint8_t)size_bucket(flop[i]);
+}
+
+// numeric path choice per task: bucket = size bucket (+0 hash, +40 bitmap/shared accumulators, +80 bitmap/HBM accumulators)
+static __global__ void num_bucket_kernel(const int64_t *nnz, const uint32_t *task_win, int nwin, int64_t ntask,
+                                  int64_t bitmap_min_nnz, int64_t hash_max_nnz, int64_t smem_acc_max, int force_path,
+                                  uint8_t *bucket) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntask) return;
+  int64_t v = nnz[i];
+  int sb = size_bucket(v);
+  if (sb == 0) {
+    bucket[i] = 0;
+    return;
+  }
+  bool can_bitmap = true;
+  if (nwin > 1 && task_win) {
+    unsigned w = task_win[i];
+    can_bitmap = ((w >> 16) - (w & 0xFFFFu)) == 1;
+  }
+  bool use_bitmap = can_bitmap && (v >= bitmap_min_nnz || v > hash_max_nnz);
+  if (force_path == 1 && v <= hash_max_nnz) use_bitmap = false;
+  if (force_path == 2 && can_bitmap) use_bitmap = true;
+  if (!use_bitmap) bucket[i] = (uint8_t)sb;
+  else bucket[i] = (uint8_t)(sb + (v <= smem_acc_max ? 40 : 80));
+}
+
+static __global__ void col_task_count_kernel(const int64_t *colflop, int64_t ncol, int nwin, int64_t lightmax, int64_t *cnt) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ncol) cnt[j] = colflop[j] <= lightmax ? 1 : nwin;
+}
+
+static __global__ void fill_tasks_kernel(const int64_t *first, int64_t ncol, int nwin, int32_t *task_col, uint32_t *task_win) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncol) return;
+  int64_t b = first[j], e = first[j + 1];
+  if (e - b == 1) {
+    task_col[b] = (int32_t)j;
+    task_win[b] = ((unsigned)nwin << 16);
+  } else {
+    for (int w = 0; w < nwin; ++w) {
+      task_col[b + w] = (int32_t)j;
+      task_win[b + w] = ((unsigned)(w + 1) << 16) | (unsigned)w;
+    }
+  }
+}
+
+static __global__ void gather_ptr_kernel(const int64_t *taskptr, const int64_t *first, int64_t ncol, int64_t *colptr_out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j <= ncol) colptr_out[j] = taskptr[first[j]];
+}
+
+template <class K>
+inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CBGPU_OK;
+}
+
+struct EngineIO {
+  // A side (or the concatenated merge lists)
+  const int64_t *Acolptr;
+  int64_t ncolA;
+  int64_t m;
+  // task space
+  int64_t ncol;               // multiply: nzc(B); merge: n
+  const int64_t *out_col_ids; // multiply: B.jc; merge: null (identity)
+  int64_t n_out;              // columns of C
+  int out_dtype;
+  // results
+  cbgpu_mat_impl **C; // null: symbolic only
+  cbgpu_stats *stats;
+  int64_t *flops_out, *nnz_out;
+};
+
+template <class SR, bool MERGE>
+int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
+  typedef typename SR::acc_t acc_t;
+  typedef typename SR::out_t out_t;
+  cudaStream_t st = ctx->stream;
+  const Options &opt = ctx->opt;
+  const int64_t launches0 = ctx->launches;
+  cbgpu_stats stats;
+  memset(&stats, 0, sizeof(stats));
+  CB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+
+  const int64_t ncol = io.ncol;
+  if (ncol >= (int64_t)1 << 31 || io.m >= ((int64_t)1 << 31) - 1)
+    return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "local dimensions must stay below 2^31 (m=%lld, columns=%lld)",
+                     (long long)io.m, (long long)ncol);
+
+  // ---- row windows
+  int wlog2 = (int)opt.bitmap_window_log2;
+  if (wlog2 < 10) wlog2 = 10;
+  if (wlog2 > 19) wlog2 = 19;
+  const int64_t W = (int64_t)1 << wlog2;
+  const int nwin = (int)std::max<int64_t>(1, (io.m + W - 1) / W);
+  if (nwin > 65535) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many row windows (%d)", nwin);
+  int64_t *Ttab = nullptr;
+  if (nwin == 1) {
+    src.T = io.Acolptr;
+  } else {
+    CB_TRY(build_window_table(ctx, io.Acolptr, src.Air, io.ncolA, nwin, wlog2, &Ttab));
+    src.T = Ttab;
+  }
+  src.nwin = nwin;
+  src.wlog2 = wlog2;
+  src.task_col = nullptr;
+  src.task_win = nullptr;
+
+  // ---- K1: products per column, then tasks
+  int64_t *colflop = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &colflop, (size_t)ncol + 1));
+  if (ncol > 0) {
+    task_flop_kernel<SR, MERGE><<<(unsigned)((ncol + 7) / 8), 256, 0, st>>>(src, ncol, colflop);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  int64_t ntask = ncol;
+  int64_t *taskflop = colflop;
+  int64_t *first = nullptr; // first task of every column (nwin > 1)
+  int32_t *task_col = nullptr;
+  uint32_t *task_win = nullptr;
+  if (nwin > 1 && ncol > 0) {
+    int64_t *cnt = nullptr;
+    CB_TRY(dev_alloc_t(ctx, &cnt, (size_t)ncol));
+    CB_TRY(dev_alloc_t(ctx, &first, (size_t)ncol + 1));
+    col_task_count_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(colflop, ncol, nwin, kLightMax, cnt);
+    CB_LAUNCH_CHECK(ctx);
+    CB_TRY(exclusive_scan_i64(ctx, cnt, first, ncol));
+    CB_CUDA(ctx, cudaMemcpyAsync(&ntask, first + ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    CB_TRY(dev_free(ctx, cnt));
+    if (ntask >= (int64_t)1 << 31) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many tasks");
+    CB_TRY(dev_alloc_t(ctx, &task_col, (size_t)ntask));
+    CB_TRY(dev_alloc_t(ctx, &task_win, (size_t)ntask));
+    fill_tasks_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(first, ncol, nwin, task_col, task_win);
+    CB_LAUNCH_CHECK(ctx);
+    src.task_col = task_col;
+    src.task_win = task_win;
+    CB_TRY(dev_alloc_t(ctx, &taskflop, (size_t)ntask + 1));
+    task_flop_kernel<SR, MERGE><<<(unsigned)((ntask + 7) / 8), 256, 0, st>>>(src, ntask, taskflop);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  stats.tasks = ntask;
+
+  // ---- symbolic binning
+  uint8_t *bucket = nullptr;
+  int32_t *order = nullptr;
+  int64_t *tasknnz = nullptr, *taskptr = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &bucket, (size_t)ntask + 1));
+  CB_TRY(dev_alloc_t(ctx, &order, (size_t)ntask + 1));
+  CB_TRY(dev_alloc_t(ctx, &tasknnz, (size_t)ntask + 1));
+  CB_TRY(dev_alloc_t(ctx, &taskptr, (size_t)ntask + 2));
+  BinResult bins;
+  memset(&bins, 0, sizeof(bins));
+  if (ntask > 0) {
+    CB_CUDA(ctx, cudaMemsetAsync(tasknnz, 0, sizeof(int64_t) * (size_t)ntask, st));
+    sym_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(taskflop, ntask, bucket);
+    CB_LAUNCH_CHECK(ctx);
+    CB_TRY(bin_tasks(ctx, bucket, taskflop, ntask, order, &bins));
+  }
+  for (int b = 1; b < 256; ++b) stats.flops += bins.weight[b];
+  CB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+
+  // ---- K2: symbolic kernels, largest tasks first
+  const int max_cells = (int)((std::min<int64_t>(io.m, W) + 63) / 64 + 1) & ~1; // even, covers the uint4 clear
+  const size_t bm_bytes = (size_t)max_cells * 8;
+  {
+    int64_t beg, cnt;
+    bucket_range(bins, 16, 39, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = sym_bitmap_kernel<SR, MERGE>;
+      CB_TRY(optin_smem(ctx, kern, bm_bytes));
+      kern<<<(unsigned)cnt, kBitmapThreads, bm_bytes, st>>>(src, order + beg, cnt, io.m, tasknnz);
+      CB_LAUNCH_CHECK(ctx);
+    }
+    bucket_range(bins, 13, 15, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = sym_hash_kernel<SR, MERGE, 16, 15>;
+      size_t sm = sizeof(unsigned) << 15;
+      CB_TRY(optin_smem(ctx, kern, sm));
+      kern<<<(unsigned)cnt, 512, sm, st>>>(src, order + beg, cnt, tasknnz);
+      CB_LAUNCH_CHECK(ctx);
+    }
+    bucket_range(bins, 10, 12, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = sym_hash_kernel<SR, MERGE, 8, 12>;
+      size_t sm = sizeof(unsigned) << 12;
+      kern<<<(unsigned)cnt, 256, sm, st>>>(src, order + beg, cnt, tasknnz);
+      CB_LAUNCH_CHECK(ctx);
+    }
+    bucket_range(bins, 7, 9, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = sym_hash_kernel<SR, MERGE, 1, 9>;
+      size_t sm = 8 * (sizeof(unsigned) << 9);
+      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, tasknnz);
+      CB_LAUNCH_CHECK(ctx);
+    }
+    bucket_range(bins, 1, 6, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = sym_hash_kernel<SR, MERGE, 1, 6>;
+      size_t sm = 8 * (sizeof(unsigned) << 6);
+      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, tasknnz);
+      CB_LAUNCH_CHECK(ctx);
+    }
+  }
+  // ---- K3: scan -> output offsets
+  CB_TRY(exclusive_scan_i64(ctx, tasknnz, taskptr, ntask));
+  int64_t nnzC = 0;
+  CB_CUDA(ctx, cudaMemcpyAsync(&nnzC, taskptr + ntask, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  CB_CUDA(ctx, cudaStreamSynchronize(st));
+  stats.nnz_out = nnzC;
+  if (io.flops_out) *io.flops_out = stats.flops;
+  if (io.nnz_out) *io.nnz_out = nnzC;
+
+  int rc = CBGPU_OK;
+  cbgpu_mat_impl *Cm = nullptr;
+  if (io.C) {
+    // ---- output block
+    CB_TRY(mat_alloc(ctx, io.m, io.n_out, nnzC, -1, io.out_dtype, &Cm));
+    // ---- numeric binning by exact output size
+    BinResult nb;
+    memset(&nb, 0, sizeof(nb));
+    if (ntask > 0) {
+      int64_t auto_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 2048, 32), 2048);
+      int64_t bmin = opt.bitmap_min_nnz > 0 ? opt.bitmap_min_nnz : auto_min;
+      num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048,
+                                                                        opt.bitmap_smem_acc, (int)opt.force_path, bucket);
+      CB_LAUNCH_CHECK(ctx);
+      CB_TRY(bin_tasks(ctx, bucket, taskflop, ntask, order, &nb));
+    }
+    out_t *Cval = reinterpret_cast<out_t *>(Cm->numx);
+    int64_t beg, cnt;
+    // bitmap, accumulators in HBM (largest tasks)
+    bucket_range(nb, 81, 119, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = num_bitmap_kernel<SR, MERGE, true>;
+      size_t sm = bm_bytes + (size_t)max_cells * 4 + 16;
+      CB_TRY(optin_smem(ctx, kern, sm));
+      kern<<<(unsigned)cnt, kBitmapThreads, sm, st>>>(src, order + beg, cnt, io.m, max_cells, taskptr, Cm->ir, Cval);
+      CB_LAUNCH_CHECK(ctx);
+      stats.tasks_bitmap_gmem = cnt;
+      for (int b = 81; b <= 119; ++b) stats.flops_bitmap_gmem += nb.weight[b];
+    }
+    // bitmap, accumulators in shared memory
+    bucket_range(nb, 41, 79, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = num_bitmap_kernel<SR, MERGE, false>;
+      size_t sm = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)opt.bitmap_smem_acc * sizeof(acc_t);
+      CB_TRY(optin_smem(ctx, kern, sm));
+      kern<<<(unsigned)cnt, kBitmapThreads, sm, st>>>(src, order + beg, cnt, io.m, max_cells, taskptr, Cm->ir, Cval);
+      CB_LAUNCH_CHECK(ctx);
+      stats.tasks_bitmap_smem = cnt;
+      for (int b = 41; b <= 79; ++b) stats.flops_bitmap_smem += nb.weight[b];
+    }
+    // hash per CTA: 257..2048 outputs
+    bucket_range(nb, 10, 39, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = num_hash_kernel<SR, MERGE, 8, 12>;
+      size_t sm = ((size_t)1 << 12) * (8 + sizeof(acc_t) + 4) + 16;
+      CB_TRY(optin_smem(ctx, kern, sm));
+      kern<<<(unsigned)cnt, 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
+      CB_LAUNCH_CHECK(ctx);
+      stats.tasks_hash_cta = cnt;
+      for (int b = 10; b <= 39; ++b) stats.flops_hash_cta += nb.weight[b];
+    }
+    // hash per warp: 33..256 outputs
+    bucket_range(nb, 7, 9, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = num_hash_kernel<SR, MERGE, 1, 9>;
+      size_t sm = 8 * ((size_t)1 << 9) * (8 + sizeof(acc_t) + 4) + 64;
+      CB_TRY(optin_smem(ctx, kern, sm));
+      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
+      CB_LAUNCH_CHECK(ctx);
+      stats.tasks_hash_warp += cnt;
+      for (int b = 7; b <= 9; ++b) stats.flops_hash_warp += nb.weight[b];
+    }
+    // hash per warp: <= 32 outputs
+    bucket_range(nb, 1, 6, &beg, &cnt);
+    if (cnt > 0) {
+      auto kern = num_hash_kernel<SR, MERGE, 1, 6>;
+      size_t sm = 8 * ((size_t)1 << 6) * (8 + sizeof(acc_t) + 4) + 64;
+      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
+      CB_LAUNCH_CHECK(ctx);
+      stats.tasks_hash_warp += cnt;
+      for (int b = 1; b <= 6; ++b) stats.flops_hash_warp += nb.weight[b];
+    }
+    // ---- DCSC assembly: column pointers of the candidate columns, then drop the empty ones
+    const int64_t *cand_ptr = taskptr;
+    int64_t *colptr_out = nullptr;
+    if (first) {
+      CB_TRY(dev_alloc_t(ctx, &colptr_out, (size_t)ncol + 1));
+      gather_ptr_kernel<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(taskptr, first, ncol, colptr_out);
+      CB_LAUNCH_CHECK(ctx);
+      cand_ptr = colptr_out;
+    }
+    rc = compact_columns(ctx, io.out_col_ids, cand_ptr, ncol, &Cm->jc, &Cm->cp, &Cm->nzc);
+    dev_free(ctx, colptr_out);
+    stats.nzc_out = Cm->nzc;
+  }
+  CB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+
+  if (taskflop != colflop) dev_free(ctx, taskflop);
+  dev_free(ctx, colflop);
+  dev_free(ctx, first);
+  dev_free(ctx, task_col);
+  dev_free(ctx, task_win);
+  dev_free(ctx, bucket);
+  dev_free(ctx, order);
+  dev_free(ctx, tasknnz);
+  dev_free(ctx, taskptr);
+  dev_free(ctx, Ttab);
+  if (rc != CBGPU_OK) {
+    mat_release(ctx, Cm);
+    return rc;
+  }
+  CB_CUDA(ctx, cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&stats.ms_symbolic, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&stats.ms_numeric, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&stats.ms_total, ctx->ev[0], ctx->ev[3]);
+  stats.kernel_launches = ctx->launches - launches0;
+  if (io.stats) *io.stats = stats;
+  if (io.C) *io.C = Cm;
+  return CBGPU_OK;
+}
+
+} // namespace cbgpu

@@ -1,0 +1,374 @@
+// Device-wide helper kernels: scan, task binning, dense column index, row-window table, column compaction.
+// Hand-written (no CUB/Thrust) so every launch on the hot path is ours and counted.
+#include <stdarg.h>
+#include "common.cuh"
+#include "util.cuh"
+
+namespace cbgpu {
+
+int set_error(cbgpu_ctx_impl *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->last_error = buf;
+  else fprintf(stderr, "[cbgpu] %s\n", buf);
+  return code;
+}
+
+int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(ctx, e == cudaErrorMemoryAllocation ? CBGPU_ERR_NOMEM : CBGPU_ERR_CUDA,
+                     "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return CBGPU_OK;
+}
+
+int dev_free(cbgpu_ctx_impl *ctx, void *p) {
+  if (!p) return CBGPU_OK;
+  CB_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+  return CBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+// three-phase exclusive scan of int64: per-tile sums, scan of the sums by one block, per-tile scan + offset
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int64_t block_scan_i64(int64_t v, int64_t *warp_sums, int64_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  int64_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int64_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += x;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < nwarp ? warp_sums[lane] : 0;
+    int64_t wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t x = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+      if (lane >= d) wi += x;
+    }
+    warp_sums[lane] = wi - w;
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  int64_t r = warp_sums[warp] + incl - v;
+  __syncthreads(); // warp_sums is reused by the caller's next round
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int64_t *in, int64_t n, int64_t *tile_sums) {
+  __shared__ int64_t ws[32];
+  __shared__ int64_t tot;
+  int64_t base = (int64_t)blockIdx.x * kScanTile;
+  int64_t s = 0;
+  for (int i = 0; i < kScanItems; ++i) {
+    int64_t idx = base + (int64_t)i * kScanThreads + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  block_scan_i64(s, ws, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan in place over ntiles entries; writes the grand total to sums[ntiles]
+__global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t *sums, int64_t ntiles) {
+  __shared__ int64_t ws[32];
+  __shared__ int64_t tot;
+  int64_t carry = 0;
+  for (int64_t base = 0; base < ntiles; base += blockDim.x) {
+    int64_t idx = base + threadIdx.x;
+    int64_t v = idx < ntiles ? sums[idx] : 0;
+    int64_t ex = block_scan_i64(v, ws, &tot);
+    if (idx < ntiles) sums[idx] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[ntiles] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply(const int64_t *in, int64_t n, const int64_t *tile_offsets, int64_t *out) {
+  __shared__ int64_t ws[32];
+  __shared__ int64_t tot;
+  // each thread owns kScanItems consecutive items so that the scan order equals the index order
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int64_t v[kScanItems];
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    int64_t idx = base + i;
+    v[i] = idx < n ? in[idx] : 0;
+    s += v[i];
+  }
+  int64_t ex = block_scan_i64(s, ws, &tot) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    int64_t idx = base + i;
+    if (idx < n) out[idx] = ex;
+    ex += v[i];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_offsets[gridDim.x];
+}
+
+__global__ void set_one_i64(int64_t *p, int64_t v) { *p = v; }
+
+int exclusive_scan_i64(cbgpu_ctx_impl *ctx, const int64_t *in, int64_t *out, int64_t n) {
+  if (n <= 0) {
+    set_one_i64<<<1, 1, 0, ctx->stream>>>(out, 0);
+    CB_LAUNCH_CHECK(ctx);
+    return CBGPU_OK;
+  }
+  int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  int64_t *sums = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &sums, (size_t)ntiles + 1));
+  scan_tile_sums<<<(unsigned)ntiles, kScanThreads, 0, ctx->stream>>>(in, n, sums);
+  CB_LAUNCH_CHECK(ctx);
+  scan_sums_inplace<<<1, 1024, 0, ctx->stream>>>(sums, ntiles);
+  CB_LAUNCH_CHECK(ctx);
+  scan_apply<<<(unsigned)ntiles, kScanThreads, 0, ctx->stream>>>(in, n, sums, out);
+  CB_LAUNCH_CHECK(ctx);
+  CB_TRY(dev_free(ctx, sums));
+  return CBGPU_OK;
+}
+
+__global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill_i64(cbgpu_ctx_impl *ctx, int64_t *p, int64_t n, int64_t v) {
+  if (n <= 0) return CBGPU_OK;
+  fill_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, n, v);
+  CB_LAUNCH_CHECK(ctx);
+  return CBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ dense column index
+__global__ void scatter_col_counts(const int64_t *jc, const int64_t *cp, int64_t nzc, int64_t *counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nzc) counts[jc[i]] = cp[i + 1] - cp[i];
+}
+
+int ensure_dense_colptr(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M) {
+  if (M->colptr) return CBGPU_OK;
+  int64_t *counts = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &counts, (size_t)M->n + 1));
+  CB_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int64_t) * ((size_t)M->n + 1), ctx->stream));
+  if (M->nzc > 0) {
+    scatter_col_counts<<<(unsigned)((M->nzc + 255) / 256), 256, 0, ctx->stream>>>(M->jc, M->cp, M->nzc, counts);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  CB_TRY(dev_alloc_t(ctx, &M->colptr, (size_t)M->n + 1));
+  CB_TRY(exclusive_scan_i64(ctx, counts, M->colptr, M->n));
+  CB_TRY(dev_free(ctx, counts));
+  return CBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ row-window table
+// T[c*nwin + w] = first position in column c whose row >= w << wlog2 ; T[ncols*nwin] = colptr[ncols]
+__global__ void window_table_kernel(const int64_t *colptr, const int32_t *rows, int64_t ncols, int nwin, int wlog2,
+                                    int64_t *T) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncols) return;
+  if (c == ncols) {
+    T[ncols * nwin] = colptr[ncols];
+    return;
+  }
+  int64_t lo = colptr[c], end = colptr[c + 1];
+  T[c * nwin] = lo;
+  for (int w = 1; w < nwin; ++w) {
+    int64_t bound = (int64_t)w << wlog2;
+    int64_t a = lo, b = end;
+    while (a < b) {
+      int64_t mid = (a + b) >> 1;
+      if ((int64_t)rows[mid] < bound) a = mid + 1;
+      else b = mid;
+    }
+    lo = a;
+    T[c * nwin + w] = lo;
+  }
+}
+
+int build_window_table(cbgpu_ctx_impl *ctx, const int64_t *colptr, const int32_t *rows, int64_t ncols, int nwin,
+                       int wlog2, int64_t **T) {
+  CB_TRY(dev_alloc_t(ctx, T, (size_t)ncols * nwin + 1));
+  window_table_kernel<<<(unsigned)((ncols + 1 + 255) / 256), 256, 0, ctx->stream>>>(colptr, rows, ncols, nwin, wlog2, *T);
+  CB_LAUNCH_CHECK(ctx);
+  return CBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ binning
+__global__ void __launch_bounds__(256)
+bucket_hist_kernel(const uint8_t *bucket, const int64_t *weight, int64_t n, unsigned long long *hist,
+                   unsigned long long *whist) {
+  __shared__ unsigned int h[256];
+  __shared__ unsigned long long wh[256];
+  h[threadIdx.x] = 0;
+  wh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * 4096;
+  for (int i = 0; i < 16; ++i) {
+    int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
+    if (idx < n) {
+      int b = bucket[idx];
+      atomicAdd(&h[b], 1u);
+      if (weight) atomicAdd(&wh[b], (unsigned long long)weight[idx]);
+    }
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) {
+    atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+    if (weight) atomicAdd(&whist[threadIdx.x], wh[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(const uint8_t *bucket, int64_t n, unsigned long long *cursor, int32_t *order) {
+  __shared__ unsigned int h[256];
+  __shared__ unsigned long long base_of[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * 4096;
+  for (int i = 0; i < 16; ++i) {
+    int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
+    if (idx < n) atomicAdd(&h[bucket[idx]], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) base_of[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+  __syncthreads();
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = 0; i < 16; ++i) {
+    int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
+    if (idx < n) {
+      int b = bucket[idx];
+      if (b != 0) { // bucket 0 = nothing to do; not listed
+        unsigned int off = atomicAdd(&h[b], 1u);
+        order[base_of[b] + off] = (int32_t)idx;
+      }
+    }
+  }
+}
+
+int bin_tasks(cbgpu_ctx_impl *ctx, const uint8_t *bucket, const int64_t *weight, int64_t n, int32_t *order, BinResult *res) {
+  memset(res, 0, sizeof(*res));
+  if (n <= 0) return CBGPU_OK;
+  unsigned long long *dh = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &dh, 768));
+  CB_CUDA(ctx, cudaMemsetAsync(dh, 0, 768 * sizeof(unsigned long long), ctx->stream));
+  unsigned nblk = (unsigned)((n + 4095) / 4096);
+  bucket_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, weight, n, dh, dh + 256);
+  CB_LAUNCH_CHECK(ctx);
+  unsigned long long hh[512];
+  CB_CUDA(ctx, cudaMemcpyAsync(hh, dh, sizeof(hh), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // descending bucket order: larger work first
+  unsigned long long cur[256];
+  int64_t off = 0;
+  for (int b = 255; b >= 1; --b) {
+    res->count[b] = (int64_t)hh[b];
+    res->weight[b] = (int64_t)hh[256 + b];
+    res->offset[b] = off;
+    cur[b] = (unsigned long long)off;
+    off += (int64_t)hh[b];
+  }
+  res->count[0] = (int64_t)hh[0];
+  res->offset[0] = off;
+  cur[0] = (unsigned long long)off;
+  res->listed = off;
+  CB_CUDA(ctx, cudaMemcpyAsync(dh + 512, cur, sizeof(cur), cudaMemcpyHostToDevice, ctx->stream));
+  bucket_scatter_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, n, dh + 512, order);
+  CB_LAUNCH_CHECK(ctx);
+  // `cur` lives on this stack frame: make sure the copy has been consumed before returning
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CB_TRY(dev_free(ctx, dh));
+  return CBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ column compaction
+__global__ void nonempty_flags(const int64_t *ptr, int64_t n, int64_t *flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = ptr[i + 1] > ptr[i] ? 1 : 0;
+}
+__global__ void compact_cols_kernel(const int64_t *ids, const int64_t *ptr, const int64_t *pos, int64_t n, int64_t *jc,
+                                    int64_t *cp) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ptr[i + 1] > ptr[i]) {
+    int64_t o = pos[i];
+    jc[o] = ids ? ids[i] : i;
+    cp[o] = ptr[i];
+  }
+  if (i == n) cp[pos[n]] = ptr[n];
+}
+
+int compact_columns(cbgpu_ctx_impl *ctx, const int64_t *cand_ids, const int64_t *cand_ptr, int64_t ncand, int64_t **jc,
+                    int64_t **cp, int64_t *nzc) {
+  *jc = nullptr;
+  *cp = nullptr;
+  *nzc = 0;
+  if (ncand <= 0) {
+    CB_TRY(dev_alloc_t(ctx, jc, 1));
+    CB_TRY(dev_alloc_t(ctx, cp, 1));
+    CB_CUDA(ctx, cudaMemsetAsync(*cp, 0, sizeof(int64_t), ctx->stream));
+    return CBGPU_OK;
+  }
+  int64_t *flags = nullptr, *pos = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &flags, (size_t)ncand));
+  CB_TRY(dev_alloc_t(ctx, &pos, (size_t)ncand + 1));
+  unsigned nblk = (unsigned)((ncand + 1 + 255) / 256);
+  nonempty_flags<<<nblk, 256, 0, ctx->stream>>>(cand_ptr, ncand, flags);
+  CB_LAUNCH_CHECK(ctx);
+  CB_TRY(exclusive_scan_i64(ctx, flags, pos, ncand));
+  int64_t cnt = 0;
+  CB_CUDA(ctx, cudaMemcpyAsync(&cnt, pos + ncand, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CB_TRY(dev_alloc_t(ctx, jc, (size_t)cnt));
+  CB_TRY(dev_alloc_t(ctx, cp, (size_t)cnt + 1));
+  compact_cols_kernel<<<nblk, 256, 0, ctx->stream>>>(cand_ids, cand_ptr, pos, ncand, *jc, *cp);
+  CB_LAUNCH_CHECK(ctx);
+  *nzc = cnt;
+  CB_TRY(dev_free(ctx, flags));
+  CB_TRY(dev_free(ctx, pos));
+  return CBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ matrices
+int mat_alloc(cbgpu_ctx_impl *ctx, int64_t m, int64_t n, int64_t nnz, int64_t nzc, int dtype, cbgpu_mat_impl **out) {
+  cbgpu_mat_impl *M = new cbgpu_mat_impl();
+  M->m = m; M->n = n; M->nnz = nnz; M->nzc = nzc; M->dtype = dtype; M->device = ctx->device;
+  int rc = CBGPU_OK;
+  if (nzc >= 0) {
+    if ((rc = dev_alloc_t(ctx, &M->jc, (size_t)nzc)) != CBGPU_OK) goto fail;
+    if ((rc = dev_alloc_t(ctx, &M->cp, (size_t)nzc + 1)) != CBGPU_OK) goto fail;
+  }
+  if ((rc = dev_alloc_t(ctx, &M->ir, (size_t)nnz)) != CBGPU_OK) goto fail;
+  if ((rc = dev_alloc(ctx, &M->numx, (size_t)nnz * dtype_size(dtype))) != CBGPU_OK) goto fail;
+  *out = M;
+  return CBGPU_OK;
+fail:
+  mat_release(ctx, M);
+  return rc;
+}
+
+int mat_release(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M) {
+  if (!M) return CBGPU_OK;
+  dev_free(ctx, M->jc);
+  dev_free(ctx, M->cp);
+  dev_free(ctx, M->ir);
+  dev_free(ctx, M->numx);
+  dev_free(ctx, M->colptr);
+  delete M;
+  return CBGPU_OK;
+}
+
+} // namespace cbgpu

@@ -1,0 +1,362 @@
+"""ctypes binding of libcbgpu.so (include/cbgpu.h). Plumbing only; every compute call goes to the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+F64, F32, I64, I32, BOOL = 0, 1, 2, 3, 4
+DTYPE_TO_NUMPY = {F64: np.float64, F32: np.float32, I64: np.int64, I32: np.int32, BOOL: np.uint8}
+NUMPY_TO_DTYPE = {np.dtype(np.float64): F64, np.dtype(np.float32): F32, np.dtype(np.int64): I64,
+                  np.dtype(np.int32): I32, np.dtype(np.uint8): BOOL, np.dtype(np.bool_): BOOL}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libcbgpu.so")
+
+
+class CbgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cbgpu error {code}: {msg}")
+        self.code = code
+
+
+class _DcscView(C.Structure):
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("nnz", C.c_int64), ("nzc", C.c_int64), ("cp", C.c_void_p),
+                ("jc", C.c_void_p), ("ir", C.c_void_p), ("numx", C.c_void_p), ("idx_bytes", C.c_int), ("dtype", C.c_int)]
+
+
+class _DcscOut(C.Structure):
+    _fields_ = [("cp", C.c_void_p), ("jc", C.c_void_p), ("ir", C.c_void_p), ("numx", C.c_void_p), ("idx_bytes", C.c_int)]
+
+
+class _MatInfo(C.Structure):
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("nnz", C.c_int64), ("nzc", C.c_int64), ("dtype", C.c_int),
+                ("device_bytes", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("flops", C.c_int64), ("nnz_out", C.c_int64), ("nzc_out", C.c_int64), ("tasks", C.c_int64),
+                ("kernel_launches", C.c_int64), ("ms_setup", C.c_float), ("ms_symbolic", C.c_float),
+                ("ms_numeric", C.c_float), ("ms_total", C.c_float),
+                ("tasks_hash_warp", C.c_int64), ("tasks_hash_cta", C.c_int64), ("tasks_bitmap_smem", C.c_int64),
+                ("tasks_bitmap_gmem", C.c_int64), ("flops_hash_warp", C.c_int64), ("flops_hash_cta", C.c_int64),
+                ("flops_bitmap_smem", C.c_int64), ("flops_bitmap_gmem", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DistStats(C.Structure):
+    _fields_ = [("local", Stats), ("ms_bcast", C.c_float), ("ms_multiply", C.c_float), ("ms_merge", C.c_float),
+                ("ms_fiber_exchange", C.c_float), ("ms_fiber_merge", C.c_float), ("ms_total", C.c_float),
+                ("bytes_bcast", C.c_int64), ("bytes_fiber", C.c_int64), ("stages", C.c_int)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "local"}
+        d["local"] = self.local.as_dict()
+        return d
+
+
+class Grid(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("layers", C.c_int), ("grid_rows", C.c_int),
+                ("grid_cols", C.c_int), ("my_layer", C.c_int), ("my_row", C.c_int), ("my_col", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/cbgpu.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "cbgpu_version": (C.c_int, []),
+    "cbgpu_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cbgpu_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "cbgpu_destroy": (C.c_int, [_P]),
+    "cbgpu_last_error": (C.c_char_p, [_P]),
+    "cbgpu_sync": (C.c_int, [_P]),
+    "cbgpu_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "cbgpu_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
+    "cbgpu_launch_count": (C.c_int64, [_P]),
+    "cbgpu_mat_upload": (C.c_int, [_P, C.POINTER(_DcscView), C.POINTER(_P)]),
+    "cbgpu_mat_from_device_csc": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_int, C.POINTER(_P)]),
+    "cbgpu_mat_info": (C.c_int, [_P, C.POINTER(_MatInfo)]),
+    "cbgpu_mat_download": (C.c_int, [_P, _P, C.POINTER(_DcscOut)]),
+    "cbgpu_mat_download_coo": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
+    "cbgpu_mat_device_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "cbgpu_mat_free": (C.c_int, [_P, _P]),
+    "cbgpu_mat_checksum": (C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cbgpu_mat_colsplit": (C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
+    "cbgpu_mat_colslice": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "cbgpu_mat_colconcat": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "cbgpu_spgemm_local": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(Stats)]),
+    "cbgpu_spgemm_symbolic": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cbgpu_spgemm_local_host": (C.c_int, [_P, C.c_int, C.POINTER(_DcscView), C.POINTER(_DcscView), C.POINTER(_P), C.POINTER(Stats)]),
+    "cbgpu_merge": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(Stats)]),
+    "cbgpu_grid_make": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(Grid)]),
+    "cbgpu_block_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cbgpu_block_owner": (C.c_int, [C.c_int64, C.c_int, C.c_int64]),
+    "cbgpu_grid_local_range": (C.c_int, [C.POINTER(Grid), C.c_int64, C.c_int64, C.c_int] + [C.POINTER(C.c_int64)] * 4),
+    "cbgpu_nccl_unique_id": (C.c_int, [_P]),
+    "cbgpu_comm_create": (C.c_int, [_P, C.POINTER(Grid), _P, C.POINTER(_P)]),
+    "cbgpu_comm_destroy": (C.c_int, [_P]),
+    "cbgpu_summa2d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
+    "cbgpu_summa3d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
+    "cbgpu_rmat_edges_host": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, _P, _P]),
+    "cbgpu_gen_rmat": (C.c_int, [_P, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                 C.c_int, C.POINTER(_P)]),
+}
+
+
+def load_library():
+    """Load libcbgpu.so. Raises (never falls back) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise CbgpuError(-100, f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class DeviceMatrix:
+    """A DCSC block resident in HBM (opaque cbgpu_mat handle)."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    def info(self):
+        inf = _MatInfo()
+        self.ctx._check(self.ctx.lib.cbgpu_mat_info(self.handle, C.byref(inf)))
+        return inf
+
+    @property
+    def shape(self):
+        i = self.info()
+        return (i.m, i.n)
+
+    @property
+    def nnz(self):
+        return self.info().nnz
+
+    @property
+    def nzc(self):
+        return self.info().nzc
+
+    @property
+    def dtype(self):
+        return self.info().dtype
+
+    def free(self):
+        if self.handle is not None and self.ctx.handle is not None:
+            self.ctx.lib.cbgpu_mat_free(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per (process, GPU). Raises if no CUDA device is usable."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.lib = load_library()
+        h = _P()
+        rc = self.lib.cbgpu_create(device, stream, C.byref(h))
+        if rc != 0:
+            raise CbgpuError(rc, f"cbgpu_create(device={device}) failed: no usable CUDA device; there is no CPU fallback")
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.cbgpu_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CbgpuError(rc, self.lib.cbgpu_last_error(self.handle).decode(errors="replace"))
+
+    def sync(self):
+        self._check(self.lib.cbgpu_sync(self.handle))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.cbgpu_set_option(self.handle, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int64()
+        self._check(self.lib.cbgpu_get_option(self.handle, name.encode(), C.byref(v)))
+        return v.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.cbgpu_launch_count(self.handle))
+
+    # ---- staging
+    @staticmethod
+    def _view(m, n, jc, cp, ir, numx):
+        idx_bytes = ir.dtype.itemsize if len(ir) else jc.dtype.itemsize if len(jc) else 8
+        jc = np.ascontiguousarray(jc)
+        cp = np.ascontiguousarray(cp)
+        ir = np.ascontiguousarray(ir)
+        numx = np.ascontiguousarray(numx)
+        for a in (jc, cp, ir):
+            if len(a) and a.dtype.itemsize != idx_bytes:
+                raise ValueError("index arrays must share one integer width")
+        v = _DcscView(m, n, len(ir), len(jc), cp.ctypes.data, jc.ctypes.data, ir.ctypes.data, numx.ctypes.data, idx_bytes,
+                      NUMPY_TO_DTYPE[numx.dtype])
+        return v, (jc, cp, ir, numx)
+
+    def upload(self, M) -> DeviceMatrix:
+        """M: host SpDCCols (combblas_b200.host)."""
+        v, keep = self._view(M.m, M.n, M.jc, M.cp, M.ir, M.numx)
+        h = _P()
+        self._check(self.lib.cbgpu_mat_upload(self.handle, C.byref(v), C.byref(h)))
+        del keep
+        return DeviceMatrix(self, h)
+
+    def from_device_csc(self, m, n, nnz, colptr_ptr, rows_ptr, vals_ptr, dtype) -> DeviceMatrix:
+        h = _P()
+        self._check(self.lib.cbgpu_mat_from_device_csc(self.handle, m, n, nnz, colptr_ptr, rows_ptr, vals_ptr, dtype, C.byref(h)))
+        return DeviceMatrix(self, h)
+
+    def download(self, D: DeviceMatrix, idx_dtype=np.int64):
+        """-> (m, n, jc, cp, ir, numx) numpy arrays (DCSC, Dcsc layout of dcsc.h:125-132)."""
+        inf = D.info()
+        idx_dtype = np.dtype(idx_dtype)
+        jc = np.empty(inf.nzc, dtype=idx_dtype)
+        cp = np.zeros(inf.nzc + 1, dtype=idx_dtype)
+        ir = np.empty(inf.nnz, dtype=idx_dtype)
+        numx = np.empty(inf.nnz, dtype=DTYPE_TO_NUMPY[inf.dtype])
+        o = _DcscOut(cp.ctypes.data, jc.ctypes.data, ir.ctypes.data, numx.ctypes.data, idx_dtype.itemsize)
+        self._check(self.lib.cbgpu_mat_download(self.handle, D.handle, C.byref(o)))
+        return inf.m, inf.n, jc, cp, ir, numx
+
+    def download_coo(self, D: DeviceMatrix, idx_dtype=np.int64):
+        inf = D.info()
+        idx_dtype = np.dtype(idx_dtype)
+        rows = np.empty(inf.nnz, dtype=idx_dtype)
+        cols = np.empty(inf.nnz, dtype=idx_dtype)
+        vals = np.empty(inf.nnz, dtype=DTYPE_TO_NUMPY[inf.dtype])
+        self._check(self.lib.cbgpu_mat_download_coo(self.handle, D.handle, rows.ctypes.data, cols.ctypes.data,
+                                                    vals.ctypes.data, idx_dtype.itemsize))
+        return rows, cols, vals
+
+    def checksum(self, D: DeviceMatrix):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.cbgpu_mat_checksum(self.handle, D.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def colslice(self, D: DeviceMatrix, c0: int, c1: int) -> DeviceMatrix:
+        h = _P()
+        self._check(self.lib.cbgpu_mat_colslice(self.handle, D.handle, c0, c1, C.byref(h)))
+        return DeviceMatrix(self, h)
+
+    def colsplit(self, D: DeviceMatrix, parts: int):
+        arr = (_P * parts)()
+        self._check(self.lib.cbgpu_mat_colsplit(self.handle, D.handle, parts, arr))
+        return [DeviceMatrix(self, _P(arr[i])) for i in range(parts)]
+
+    def colconcat(self, mats):
+        arr = (_P * len(mats))(*[m.handle for m in mats])
+        h = _P()
+        self._check(self.lib.cbgpu_mat_colconcat(self.handle, len(mats), arr, C.byref(h)))
+        return DeviceMatrix(self, h)
+
+    # ---- compute
+    def spgemm(self, sr: int, A: DeviceMatrix, B: DeviceMatrix, want_stats=False):
+        h = _P()
+        st = Stats()
+        self._check(self.lib.cbgpu_spgemm_local(self.handle, sr, A.handle, B.handle, C.byref(h), C.byref(st)))
+        out = DeviceMatrix(self, h)
+        return (out, st) if want_stats else out
+
+    def spgemm_host(self, sr: int, A, B, want_stats=False):
+        va, ka = self._view(A.m, A.n, A.jc, A.cp, A.ir, A.numx)
+        vb, kb = self._view(B.m, B.n, B.jc, B.cp, B.ir, B.numx)
+        h = _P()
+        st = Stats()
+        self._check(self.lib.cbgpu_spgemm_local_host(self.handle, sr, C.byref(va), C.byref(vb), C.byref(h), C.byref(st)))
+        out = DeviceMatrix(self, h)
+        return (out, st) if want_stats else out
+
+    def symbolic(self, A: DeviceMatrix, B: DeviceMatrix):
+        f, z = C.c_int64(), C.c_int64()
+        self._check(self.lib.cbgpu_spgemm_symbolic(self.handle, A.handle, B.handle, C.byref(f), C.byref(z)))
+        return f.value, z.value
+
+    def merge(self, sr: int, mats, want_stats=False):
+        arr = (_P * len(mats))(*[m.handle for m in mats])
+        h = _P()
+        st = Stats()
+        self._check(self.lib.cbgpu_merge(self.handle, sr, len(mats), arr, C.byref(h), C.byref(st)))
+        out = DeviceMatrix(self, h)
+        return (out, st) if want_stats else out
+
+    def gen_rmat(self, scale, nedges, seed, a=0.57, b=0.19, c=0.19, scramble=True, dtype=F64, value_mode=0):
+        h = _P()
+        self._check(self.lib.cbgpu_gen_rmat(self.handle, scale, nedges, seed, a, b, c, int(scramble), dtype, value_mode, C.byref(h)))
+        return DeviceMatrix(self, h)
+
+
+def make_grid(world: int, rank: int, layers: int = 1) -> Grid:
+    g = Grid()
+    rc = load_library().cbgpu_grid_make(world, rank, layers, C.byref(g))
+    if rc != 0:
+        raise CbgpuError(rc, f"no {layers}-layer square grid over {world} ranks (reference: NOTSQUARE / GRIDMISMATCH)")
+    return g
+
+
+class Comm:
+    """NCCL communicators (world, row, column, fiber) of this rank; bootstrap via torch.distributed (plumbing)."""
+
+    def __init__(self, ctx: Context, grid: Grid, unique_id: bytes):
+        self.ctx = ctx
+        self.grid = grid
+        buf = C.create_string_buffer(unique_id, 128)
+        h = _P()
+        ctx._check(ctx.lib.cbgpu_comm_create(ctx.handle, C.byref(grid), buf, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().cbgpu_nccl_unique_id(buf)
+        if rc != 0:
+            raise CbgpuError(rc, "ncclGetUniqueId failed (NCCL not loadable?)")
+        return buf.raw
+
+    def summa2d(self, sr, A: DeviceMatrix, B: DeviceMatrix):
+        h = _P()
+        st = DistStats()
+        self.ctx._check(self.ctx.lib.cbgpu_summa2d(self.ctx.handle, self.handle, sr, A.handle, B.handle, C.byref(h), C.byref(st)))
+        return DeviceMatrix(self.ctx, h), st
+
+    def summa3d(self, sr, A: DeviceMatrix, B: DeviceMatrix):
+        h = _P()
+        st = DistStats()
+        self.ctx._check(self.ctx.lib.cbgpu_summa3d(self.ctx.handle, self.handle, sr, A.handle, B.handle, C.byref(h), C.byref(st)))
+        return DeviceMatrix(self.ctx, h), st
+
+    def destroy(self):
+        if self.handle is not None:
+            self.ctx.lib.cbgpu_comm_destroy(self.handle)
+            self.handle = None

@@ -1,0 +1,213 @@
+/*
+ * cbgpu.h -- C ABI of libcbgpu.so: B200-native (sm_100a) semiring SpGEMM hot path behind the
+ * CombBLAS SpDCCols / SpTuples / semiring interface.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary. Every entry point returns
+ * CBGPU_OK (0) or a negative cbgpu_status and never aborts the process; the C++ overlay
+ * (include/combblas_b200/overlay) maps failures onto the reference's MPI_Abort codes (SpDefs.h:72-78).
+ *
+ * Each entry cites the reference interface (path:line under the CombBLAS tree) that it replaces.
+ * The reference has no FFI of its own -- its seam is C++ templates -- so INTEGRATION.md shows the
+ * constrained-overload binding a maintainer adds on the reference side.
+ *
+ * Threading: one host thread per context at a time. All work of a context is ordered on its stream.
+ */
+#ifndef CBGPU_H
+#define CBGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBGPU_VERSION 100
+
+typedef enum {
+  CBGPU_OK = 0,
+  CBGPU_ERR_INVALID = -1,     /* bad argument */
+  CBGPU_ERR_CUDA = -2,        /* CUDA runtime failure; text in cbgpu_last_error */
+  CBGPU_ERR_NOMEM = -3,       /* device allocation failed */
+  CBGPU_ERR_UNSUPPORTED = -4, /* type/semiring/size combination outside the device path */
+  CBGPU_ERR_DIMMISMATCH = -5, /* inner dimensions differ (reference: DIMMISMATCH 3002, SpDefs.h:73) */
+  CBGPU_ERR_NCCL = -6,        /* NCCL failure or NCCL not loadable */
+  CBGPU_ERR_GRID = -7         /* process grid not usable (reference: GRIDMISMATCH 3001 / NOTSQUARE 3003) */
+} cbgpu_status;
+
+/* value types of matrix entries; bool travels as one byte (C++ bool) */
+typedef enum { CBGPU_F64 = 0, CBGPU_F32 = 1, CBGPU_I64 = 2, CBGPU_I32 = 3, CBGPU_BOOL = 4 } cbgpu_dtype;
+
+/*
+ * Library semirings (Semirings.h:143-255; OR-AND as in ReleaseTests/KTipsTest.cpp:12-20).
+ * Each fixes the operand types (A, B) and the output type.
+ */
+typedef enum {
+  CBGPU_SR_PLUS_TIMES_F64 = 0,      /* PlusTimesSRing<double,double>   f64 x f64 -> f64 */
+  CBGPU_SR_PLUS_TIMES_F32 = 1,      /* PlusTimesSRing<float,float>     f32 x f32 -> f32 */
+  CBGPU_SR_PLUS_TIMES_I64 = 2,      /* PlusTimesSRing<int64,int64>     i64 x i64 -> i64 */
+  CBGPU_SR_SELECT_MAX_BOOL_I64 = 3, /* SelectMaxSRing<bool,int64_t>    bool x i64 -> i64 */
+  CBGPU_SR_MIN_PLUS_F64 = 4,        /* MinPlusSRing<double,double>     f64 x f64 -> f64 */
+  CBGPU_SR_OR_AND_BOOL = 5,         /* user OR-AND semiring on bool    bool x bool -> bool */
+  CBGPU_SR_PLUS_TIMES_BOOL_F64 = 6, /* PlusTimesSRing<bool,double>     bool x f64 -> f64 */
+  CBGPU_SR_PLUS_TIMES_I32 = 7,      /* PlusTimesSRing<int32,int32>     i32 x i32 -> i32 */
+  CBGPU_SR_SELECT_MAX_I64 = 8,      /* SelectMaxSRing<int64,int64>     i64 x i64 -> i64 */
+  CBGPU_SR_COUNT = 9
+} cbgpu_semiring;
+
+typedef struct cbgpu_ctx cbgpu_ctx; /* one per (process, GPU): stream, workspace, tunables */
+typedef struct cbgpu_mat cbgpu_mat; /* device-resident DCSC block (dcsc.h:125-132), rows ascending per column */
+
+/*
+ * Host- or device-side view of an SpDCCols<IT,NT> block: the four arrays of Dcsc (dcsc.h:125-132)
+ * plus the "essentials" {nnz, m, n, nzc} (SpDCCols.cpp:788 GetEssentials). idx_bytes is sizeof(IT), 4 or 8.
+ * A zero matrix has nnz == nzc == 0 and may pass NULL arrays (SpDCCols keeps dcsc == NULL then).
+ */
+typedef struct {
+  int64_t m, n, nnz, nzc;
+  const void *cp;   /* nzc+1 column pointers      (IT) */
+  const void *jc;   /* nzc   non-empty column ids (IT) */
+  const void *ir;   /* nnz   row ids              (IT) */
+  const void *numx; /* nnz   values               (dtype) */
+  int idx_bytes;
+  int dtype; /* cbgpu_dtype */
+} cbgpu_dcsc_view;
+
+/* writable counterpart used for downloads: caller allocates arrays sized from cbgpu_mat_info */
+typedef struct {
+  void *cp, *jc, *ir, *numx;
+  int idx_bytes;
+} cbgpu_dcsc_out;
+
+typedef struct {
+  int64_t m, n, nnz, nzc;
+  int dtype;
+  int64_t device_bytes;
+} cbgpu_mat_info_t;
+
+/* counters and stream-timed phases of the last multiply / merge (milliseconds, CUDA events) */
+typedef struct {
+  int64_t flops;     /* products = sum_j sum_{k in B(:,j)} nnz(A(:,k)); reference: estimateFLOP mtSpGEMM.h:1058 */
+  int64_t nnz_out;   /* nnz(C) */
+  int64_t nzc_out;   /* non-empty columns of C */
+  int64_t tasks;     /* (column, row-window) work items */
+  int64_t kernel_launches;
+  float ms_setup;    /* dense column index, row windows, flop count, binning */
+  float ms_symbolic; /* distinct-row counting (estimateNNZ_Hash mtSpGEMM.h:807) + scan */
+  float ms_numeric;  /* accumulation + sorted emission */
+  float ms_total;
+  int64_t tasks_hash_warp, tasks_hash_cta, tasks_bitmap_smem, tasks_bitmap_gmem; /* numeric path census */
+  int64_t flops_hash_warp, flops_hash_cta, flops_bitmap_smem, flops_bitmap_gmem;
+} cbgpu_stats;
+
+/* ---------------------------------------------------------------- lifecycle */
+int cbgpu_version(void);
+int cbgpu_device_count(int *count);
+/* stream may be NULL (the context creates its own non-blocking stream) or a cudaStream_t to adopt */
+int cbgpu_create(int device, void *stream, cbgpu_ctx **ctx);
+int cbgpu_destroy(cbgpu_ctx *ctx);
+const char *cbgpu_last_error(const cbgpu_ctx *ctx);
+int cbgpu_sync(cbgpu_ctx *ctx);
+/* tunables: "hash_warp_max", "hash_cta_max", "bitmap_window_log2", "bitmap_min_nnz", "sort_output" ... */
+int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value);
+int cbgpu_get_option(cbgpu_ctx *ctx, const char *name, int64_t *value);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t cbgpu_launch_count(const cbgpu_ctx *ctx);
+
+/* ---------------------------------------------------------------- DCSC staging in HBM
+ * replaces: SpDCCols::CreateImpl / GetArrays (SpDCCols.cpp:735,:827) as the thing BCastMatrix moves,
+ * and the tuples->DCSC constructor SpDCCols(const SpTuples&, bool) (SpDCCols.cpp:110-189). */
+int cbgpu_mat_upload(cbgpu_ctx *ctx, const cbgpu_dcsc_view *host, cbgpu_mat **out);
+/* adopt DEVICE arrays laid out as plain CSC: colptr int64[n+1], rows int32[nnz] ascending per column,
+ * vals dtype[nnz]. Arrays are copied into library-owned storage (the caller keeps its buffers). */
+int cbgpu_mat_from_device_csc(cbgpu_ctx *ctx, int64_t m, int64_t n, int64_t nnz, const int64_t *colptr,
+                              const int32_t *rows, const void *vals, int dtype, cbgpu_mat **out);
+int cbgpu_mat_info(const cbgpu_mat *mat, cbgpu_mat_info_t *info);
+int cbgpu_mat_download(cbgpu_ctx *ctx, const cbgpu_mat *mat, const cbgpu_dcsc_out *host);
+/* column-major COO (rows ascending per column) as three separate host arrays; idx_bytes 4 or 8.
+ * This is what the overlay turns into SpTuples (SpTuples.h:64; std::tuple layout is the overlay's business). */
+int cbgpu_mat_download_coo(cbgpu_ctx *ctx, const cbgpu_mat *mat, void *rows, void *cols, void *vals, int idx_bytes);
+/* raw device pointers of a resident block (jc int64[nzc], cp int64[nzc+1], ir int32[nnz], numx dtype[nnz]) */
+int cbgpu_mat_device_arrays(const cbgpu_mat *mat, const int64_t **jc, const int64_t **cp, const int32_t **ir,
+                            const void **numx);
+int cbgpu_mat_free(cbgpu_ctx *ctx, cbgpu_mat *mat);
+/* order-independent 64-bit checksum of (row, col, value bits) over all entries; used for slab-wise parity */
+int cbgpu_mat_checksum(cbgpu_ctx *ctx, const cbgpu_mat *mat, uint64_t *pattern_sum, uint64_t *value_sum);
+/* ColSplit / ColConcatenate of B and C slabs (dcsc.cpp:1202-1277, :1317-1360; SpDCCols.cpp:1054-1263) */
+int cbgpu_mat_colsplit(cbgpu_ctx *ctx, const cbgpu_mat *mat, int parts, cbgpu_mat **out /* parts */);
+int cbgpu_mat_colslice(cbgpu_ctx *ctx, const cbgpu_mat *mat, int64_t col_begin, int64_t col_end, cbgpu_mat **out);
+int cbgpu_mat_colconcat(cbgpu_ctx *ctx, int parts, cbgpu_mat *const *in, cbgpu_mat **out);
+
+/* ---------------------------------------------------------------- local multiply (K1-K4)
+ * replaces: LocalHybridSpGEMM (mtSpGEMM.h:213-460), LocalSpGEMMHash (:463-656), LocalSpGEMM (:74-202)
+ * and, fused in, estimateFLOP (:1058), estimateNNZ_Hash (:807), prefixsum (:24) and the
+ * tuples->DCSC conversion the SUMMA drivers do afterwards (ParFriends.h:1549).
+ * C = A (x) B; output block is DCSC with rows ascending inside every column. */
+int cbgpu_spgemm_local(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, cbgpu_mat **C,
+                       cbgpu_stats *stats);
+/* symbolic only: total products and nnz(C) (EstimateFLOP ParFriends.h:357; estimateNNZ_Hash) */
+int cbgpu_spgemm_symbolic(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops, int64_t *nnz_out);
+/* host-buffers-in, host-buffers-out form of the same call (what a LocalHybridSpGEMM overlay invokes):
+ * uploads both operands, multiplies, and hands back a resident result to download. */
+int cbgpu_spgemm_local_host(cbgpu_ctx *ctx, int semiring, const cbgpu_dcsc_view *A, const cbgpu_dcsc_view *B,
+                            cbgpu_mat **C, cbgpu_stats *stats);
+
+/* ---------------------------------------------------------------- k-way merge (K7/K8)
+ * replaces: MultiwayMerge (MultiwayMerge.h:428-543) and MultiwayMergeHash (:553-701): column-wise union of k
+ * blocks of identical shape with SR::add on equal (row, col). k == 1 returns a copy. */
+int cbgpu_merge(cbgpu_ctx *ctx, int semiring, int k, const cbgpu_mat *const *lists, cbgpu_mat **out,
+                cbgpu_stats *stats);
+
+/* ---------------------------------------------------------------- process grids and distributed SpGEMM
+ * Host-side arithmetic of the reference's distributions (no GPU needed):
+ * 2D owner rule SpParMat::Owner (SpParMat.cpp:5081-5107), 3D split SpParMat3D::Owner/LocalDim
+ * (SpParMat3D.cpp:337-436), layer column split CalculateColSplitDistributionOfLayer (:576-609),
+ * rank maps CommGrid (CommGrid.h:106, src/CommGrid.cpp:57-58) and CommGrid3D (CommGrid3D.h:75-93). */
+typedef struct {
+  int world, rank;
+  int layers;    /* c; 1 for a plain 2D grid */
+  int grid_rows; /* pr == pc inside a layer */
+  int grid_cols;
+  int my_layer, my_row, my_col; /* position of `rank` */
+} cbgpu_grid;
+int cbgpu_grid_make(int world, int rank, int layers, cbgpu_grid *grid);
+/* half-open range [begin,end) of the global dimension `dim` owned by block `index` of `parts` (last takes remainder) */
+int cbgpu_block_range(int64_t dim, int parts, int index, int64_t *begin, int64_t *end);
+int cbgpu_block_owner(int64_t dim, int parts, int64_t global_index);
+/* local ranges of the A (column-split) / B (row-split) / C (column-split) block of `grid`'s rank for an m x n matrix */
+int cbgpu_grid_local_range(const cbgpu_grid *grid, int64_t m, int64_t n, int split_cols /*1: A,C  0: B*/,
+                           int64_t *row_begin, int64_t *row_end, int64_t *col_begin, int64_t *col_end);
+
+typedef struct cbgpu_comm cbgpu_comm; /* NCCL communicators of one rank: world, row, column, fiber */
+int cbgpu_nccl_unique_id(void *id128 /* 128 bytes out */);
+int cbgpu_comm_create(cbgpu_ctx *ctx, const cbgpu_grid *grid, const void *id128, cbgpu_comm **comm);
+int cbgpu_comm_destroy(cbgpu_comm *comm);
+
+typedef struct {
+  cbgpu_stats local; /* summed over stages */
+  float ms_bcast, ms_multiply, ms_merge, ms_fiber_exchange, ms_fiber_merge, ms_total;
+  int64_t bytes_bcast, bytes_fiber;
+  int stages;
+} cbgpu_dist_stats;
+
+/* 2D Sparse SUMMA: replaces Mult_AnXBn_Synch (ParFriends.h:1447-1556) incl. GetSetSizes/BCastMatrix
+ * (SpParHelper.cpp:798,:583) and the final MultiwayMerge. A, B, C are this rank's blocks. */
+int cbgpu_summa2d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B,
+                  cbgpu_mat **C, cbgpu_dist_stats *stats);
+/* 3D SUMMA: replaces Mult_AnXBn_SUMMA3D (ParFriends.h:3374-3667): per-layer 2D SUMMA, fiber all-to-all of
+ * column slabs (:3578-3612), fiber merge (:3642). A column-split, B row-split, C column-split across layers. */
+int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B,
+                  cbgpu_mat **C, cbgpu_dist_stats *stats);
+
+/* ---------------------------------------------------------------- synthetic inputs (own seeded generators)
+ * R-MAT (Graph500 initiator a,b,c,d as in 3DSpGEMM/mpipspgemm.cpp:126-133), duplicates summed into the value
+ * (SpTuples.cpp:70-124 semantics), vertex scramble by a seeded bijection. Device generation; the identical
+ * arithmetic is available on the host for parity inputs (cbgpu_rmat_edges_host). Not part of the timed path. */
+int cbgpu_rmat_edges_host(int scale, int64_t nedges, uint64_t seed, double a, double b, double c, int scramble,
+                          int64_t *rows, int64_t *cols);
+/* value_mode: 0 = multiplicity of the edge (duplicates summed), 1 = one (duplicates collapsed), 2 = 1 + row id */
+int cbgpu_gen_rmat(cbgpu_ctx *ctx, int scale, int64_t nedges, uint64_t seed, double a, double b, double c,
+                   int scramble, int dtype, int value_mode, cbgpu_mat **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBGPU_H */

@@ -1,0 +1,297 @@
+"""ctypes front-ends for the two CPU parity oracles.
+
+TEST INFRASTRUCTURE ONLY. May be imported by tests/, by ``__graft_entry__.smoke()`` and by
+``bench.py``'s cpu_baseline / ``--impl reference`` legs -- never by the product package
+``combblas_b200`` (a test asserts this).
+
+* ``RefOracle``  -- oracle/_ref/libref_oracle.so: the UNMODIFIED reference (CombBLAS v2.0.1) compiled
+  from /root/reference in the build container against a single-rank mpi.h stand-in (oracle/Makefile).
+* ``PortOracle`` -- oracle/libspgemm_oracle.so: plain-C restatement of the same algorithm
+  (oracle/spgemm_oracle.c, each function cites the reference file:line it follows).
+
+Matrices are (m, n, colptr[int64 n+1], rows[int64 nnz], vals[typed nnz]) CSC triples ("Csc").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# semiring ids -- identical numbering to include/cbgpu.h (cbgpu_semiring)
+SR_PLUS_TIMES_F64 = 0
+SR_PLUS_TIMES_F32 = 1
+SR_PLUS_TIMES_I64 = 2
+SR_SELECT_MAX_BOOL_I64 = 3
+SR_MIN_PLUS_F64 = 4
+SR_OR_AND_BOOL = 5
+SR_PLUS_TIMES_BOOL_F64 = 6
+SR_PLUS_TIMES_I32 = 7
+SR_SELECT_MAX_I64 = 8
+
+# (A dtype, B dtype, C dtype) per semiring; bool travels as uint8
+SR_DTYPES = {
+    0: (np.float64, np.float64, np.float64),
+    1: (np.float32, np.float32, np.float32),
+    2: (np.int64, np.int64, np.int64),
+    3: (np.uint8, np.int64, np.int64),
+    4: (np.float64, np.float64, np.float64),
+    5: (np.uint8, np.uint8, np.uint8),
+    6: (np.uint8, np.float64, np.float64),
+    7: (np.int32, np.int32, np.int32),
+    8: (np.int64, np.int64, np.int64),
+}
+SR_NAMES = {
+    0: "PlusTimes<f64>", 1: "PlusTimes<f32>", 2: "PlusTimes<i64>", 3: "SelectMax<bool,i64>", 4: "MinPlus<f64>",
+    5: "OrAnd<bool>", 6: "PlusTimes<bool,f64>", 7: "PlusTimes<i32>", 8: "SelectMax<i64>",
+}
+
+# reference routines (oracle/ref_oracle.h)
+REF_LOCAL_HYBRID, REF_LOCAL_HASH_SORTED, REF_LOCAL_HASH_UNSORTED, REF_LOCAL_HEAP = 0, 1, 2, 3
+REF_DIST_SYNCH, REF_DIST_DOUBLEBUFF, REF_DIST_MEMEFF_HASH, REF_DIST_MEMEFF_HEAP, REF_DIST_SUMMA3D = 10, 11, 12, 13, 14
+
+
+@dataclass
+class Csc:
+    m: int
+    n: int
+    colptr: np.ndarray  # int64 [n+1]
+    rows: np.ndarray  # int64 [nnz]
+    vals: np.ndarray  # typed [nnz]
+
+    @property
+    def nnz(self) -> int:
+        return int(self.colptr[-1])
+
+    def astype(self, dt) -> "Csc":
+        return Csc(self.m, self.n, self.colptr, self.rows, np.ascontiguousarray(self.vals.astype(dt)))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csc_matrix((self.vals, self.rows, self.colptr), shape=(self.m, self.n))
+
+    @staticmethod
+    def from_scipy(M, dtype=None) -> "Csc":
+        M = M.tocsc()
+        M.sort_indices()
+        v = M.data if dtype is None else M.data.astype(dtype)
+        return Csc(M.shape[0], M.shape[1], M.indptr.astype(np.int64), M.indices.astype(np.int64), np.ascontiguousarray(v))
+
+    @staticmethod
+    def from_coo(m, n, rows, cols, vals) -> "Csc":
+        """column-major, rows ascending; duplicates must already be combined."""
+        rows = np.asarray(rows, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        order = np.lexsort((rows, cols))
+        rows, cols, vals = rows[order], cols[order], np.asarray(vals)[order]
+        colptr = np.zeros(n + 1, dtype=np.int64)
+        np.add.at(colptr, cols + 1, 1)
+        np.cumsum(colptr, out=colptr)
+        return Csc(m, n, colptr, np.ascontiguousarray(rows), np.ascontiguousarray(vals))
+
+    def cols_expanded(self) -> np.ndarray:
+        return np.repeat(np.arange(self.n, dtype=np.int64), np.diff(self.colptr))
+
+
+class _RefCsc(C.Structure):
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("nnz", C.c_int64), ("colptr", C.c_void_p), ("rows", C.c_void_p),
+                ("vals", C.c_void_p)]
+
+
+def _as_ref(M: Csc, dt):
+    cp = np.ascontiguousarray(M.colptr, dtype=np.int64)
+    ro = np.ascontiguousarray(M.rows, dtype=np.int64)
+    va = np.ascontiguousarray(M.vals, dtype=dt)
+    s = _RefCsc(M.m, M.n, int(cp[-1]), cp.ctypes.data, ro.ctypes.data, va.ctypes.data)
+    return s, (cp, ro, va)
+
+
+def _coo_to_csc(m, n, rows, cols, vals, keep_order):
+    """COO as produced by an oracle -> Csc. With keep_order the within-column order is preserved."""
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    if len(cols):
+        if np.any(np.diff(cols) < 0):
+            raise AssertionError("oracle output is not column-grouped ascending")
+        np.add.at(colptr, cols + 1, 1)
+    np.cumsum(colptr, out=colptr)
+    return Csc(m, n, colptr, rows, vals)
+
+
+class _Base:
+    lib = None
+
+    def _result(self, h, m, n, out_dt):
+        nnz = self.lib.ref_result_nnz(h) if self._prefix == "ref" else self.lib.port_result_nnz(h)
+        rows = np.empty(nnz, dtype=np.int64)
+        cols = np.empty(nnz, dtype=np.int64)
+        vals = np.empty(nnz, dtype=out_dt)
+        copy = getattr(self.lib, self._prefix + "_result_copy")
+        free = getattr(self.lib, self._prefix + "_result_free")
+        copy(h, rows.ctypes.data, cols.ctypes.data, vals.ctypes.data)
+        free(h)
+        return _coo_to_csc(m, n, rows, cols, vals, True)
+
+
+class RefOracle(_Base):
+    """The unmodified reference, prebuilt into oracle/_ref/libref_oracle.so."""
+
+    _prefix = "ref"
+    PATH = os.path.join(HERE, "_ref", "libref_oracle.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        self.lib = C.CDLL(self.PATH)
+        L = self.lib
+        L.ref_spgemm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_double)]
+        L.ref_merge.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_double)]
+        L.ref_symbolic.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p)]
+        L.ref_free.argtypes = [C.c_void_p]
+        L.ref_result_nnz.argtypes = [C.c_void_p]
+        L.ref_result_nnz.restype = C.c_int64
+        L.ref_result_copy.argtypes = [C.c_void_p] * 4
+        L.ref_result_free.argtypes = [C.c_void_p]
+        L.ref_set_num_threads.argtypes = [C.c_int]
+
+    def num_threads(self) -> int:
+        return int(self.lib.ref_num_threads())
+
+    def set_num_threads(self, n: int):
+        self.lib.ref_set_num_threads(int(n))
+
+    def spgemm(self, A: Csc, B: Csc, sr: int = 0, routine: int = REF_LOCAL_HYBRID, canonical: bool = True,
+               phases: int = 1, want_time: bool = False):
+        da, db, dc = SR_DTYPES[sr]
+        sa, ka = _as_ref(A, da)
+        sb, kb = _as_ref(B, db)
+        h = C.c_void_p()
+        sec = C.c_double(0)
+        rc = self.lib.ref_spgemm(routine, sr, C.byref(sa), C.byref(sb), phases, int(canonical), C.byref(h), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"ref_spgemm failed rc={rc}")
+        out = self._result(h, A.m, B.n, dc)
+        del ka, kb
+        return (out, sec.value) if want_time else out
+
+    def merge(self, lists, sr: int = 0, hash: bool = False, sorted: bool = True, canonical: bool = True):
+        dc = SR_DTYPES[sr][2]
+        arr = (_RefCsc * len(lists))()
+        keep = []
+        for i, M in enumerate(lists):
+            s, k = _as_ref(M, dc)
+            arr[i] = s
+            keep.append(k)
+        h = C.c_void_p()
+        sec = C.c_double(0)
+        rc = self.lib.ref_merge(int(hash), sr, len(lists), arr, int(sorted), int(canonical), C.byref(h), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"ref_merge failed rc={rc}")
+        return self._result(h, lists[0].m, lists[0].n, dc)
+
+    def symbolic(self, A: Csc, B: Csc, sr: int = 0):
+        """(flop, nnz) per NON-EMPTY column of B, as estimateFLOP / estimateNNZ_Hash return them."""
+        da, db, _ = SR_DTYPES[sr]
+        sa, ka = _as_ref(A, da)
+        sb, kb = _as_ref(B, db)
+        nzc = C.c_int64(0)
+        pf, pn = C.c_void_p(), C.c_void_p()
+        rc = self.lib.ref_symbolic(sr, C.byref(sa), C.byref(sb), C.byref(nzc), C.byref(pf), C.byref(pn))
+        if rc != 0:
+            raise RuntimeError("ref_symbolic failed")
+        k = nzc.value
+        if k == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64)
+        flop = np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_int64)), shape=(k,)).copy()
+        nnz = np.ctypeslib.as_array(C.cast(pn, C.POINTER(C.c_int64)), shape=(k,)).copy()
+        self.lib.ref_free(pf)
+        self.lib.ref_free(pn)
+        return flop, nnz
+
+
+class PortOracle(_Base):
+    """Plain-C restatement (oracle/spgemm_oracle.c); always buildable, travels as source."""
+
+    _prefix = "port"
+    PATH = os.path.join(HERE, "libspgemm_oracle.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.PATH)
+
+    @classmethod
+    def build(cls):
+        import subprocess
+
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+
+    def __init__(self):
+        if not self.available():
+            self.build()
+        self.lib = C.CDLL(self.PATH)
+        L = self.lib
+        L.port_spgemm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_double)]
+        L.port_merge.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_double)]
+        L.port_symbolic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.port_symbolic.restype = C.c_int64
+        L.port_result_nnz.argtypes = [C.c_void_p]
+        L.port_result_nnz.restype = C.c_int64
+        L.port_result_copy.argtypes = [C.c_void_p] * 4
+        L.port_result_free.argtypes = [C.c_void_p]
+        L.port_set_num_threads.argtypes = [C.c_int]
+
+    def num_threads(self) -> int:
+        return int(self.lib.port_num_threads())
+
+    def set_num_threads(self, n: int):
+        self.lib.port_set_num_threads(int(n))
+
+    def spgemm(self, A: Csc, B: Csc, sr: int = 0, sort: bool = True, want_time: bool = False):
+        da, db, dc = SR_DTYPES[sr]
+        sa, ka = _as_ref(A, da)
+        sb, kb = _as_ref(B, db)
+        h = C.c_void_p()
+        sec = C.c_double(0)
+        rc = self.lib.port_spgemm(sr, C.byref(sa), C.byref(sb), int(sort), C.byref(h), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"port_spgemm failed rc={rc}")
+        out = self._result(h, A.m, B.n, dc)
+        del ka, kb
+        return (out, sec.value) if want_time else out
+
+    def merge(self, lists, sr: int = 0, sort: bool = True):
+        dc = SR_DTYPES[sr][2]
+        arr = (_RefCsc * len(lists))()
+        keep = []
+        for i, M in enumerate(lists):
+            s, k = _as_ref(M, dc)
+            arr[i] = s
+            keep.append(k)
+        h = C.c_void_p()
+        sec = C.c_double(0)
+        rc = self.lib.port_merge(sr, len(lists), arr, int(sort), C.byref(h), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"port_merge failed rc={rc}")
+        return self._result(h, lists[0].m, lists[0].n, dc)
+
+    def symbolic(self, A: Csc, B: Csc):
+        """(flop, nnz) per column of B (all n columns, zeros for empty ones)."""
+        sa, ka = _as_ref(A, A.vals.dtype)
+        sb, kb = _as_ref(B, B.vals.dtype)
+        flop = np.zeros(B.n, dtype=np.int64)
+        nnz = np.zeros(B.n, dtype=np.int64)
+        self.lib.port_symbolic(C.byref(sa), C.byref(sb), flop.ctypes.data, nnz.ctypes.data)
+        return flop, nnz
+
+
+def best_oracle():
+    """The reference build when present (build container and, prebuilt, the GPU box), else the port."""
+    return RefOracle() if RefOracle.available() else PortOracle()

@@ -1,0 +1,132 @@
+"""CPU: the C-ABI library loads, exports every symbol include/cbgpu.h declares, fails loudly without a GPU,
+the product never touches the oracle, and the host-side distribution arithmetic matches the reference rules."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import combblas_b200 as cb
+from combblas_b200 import lib as cblib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cbgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cbgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = cb.load_library()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cbgpu.h but not exported by libcbgpu.so"
+        assert n in cblib.SIGNATURES, f"{n} has no ctypes signature"
+    assert lib.cbgpu_version() == 100
+
+
+def test_library_is_compiled_for_sm_100a():
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", cb.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    n = C.c_int()
+    cb.load_library().cbgpu_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cb.CbgpuError):
+        cb.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "combblas_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "oracle" not in txt.replace("test infrastructure", ""), f"{f} mentions the oracle"
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.isfile(p):
+            assert "spgemm_oracle" not in open(p).read()
+
+
+def test_block_ranges_follow_the_owner_rule():
+    # SpParMat::Owner (SpParMat.cpp:5081-5107): floor(dim/parts) per block, the last one takes the remainder
+    assert cb.block_range(10, 3, 0) == (0, 3) and cb.block_range(10, 3, 2) == (6, 10)
+    assert [cb.block_owner(10, 3, i) for i in range(10)] == [0, 0, 0, 1, 1, 1, 2, 2, 2, 2]
+    assert cb.block_owner(2, 4, 1) == 3  # perproc == 0: everything on the last block
+    for dim in (1, 7, 64, 1000):
+        for parts in (1, 2, 3, 4):
+            seen = []
+            for i in range(parts):
+                b, e = cb.block_range(dim, parts, i)
+                seen.extend(range(b, e))
+                if dim // parts > 0:
+                    assert all(cb.block_owner(dim, parts, g) == i for g in range(b, e))
+            assert seen == list(range(dim))
+
+
+def test_grid_rank_maps():
+    # CommGrid3D non-special layout (CommGrid3D.h:75-93): layer = rank / (pr*pc); row-major inside a layer
+    g = cblib.make_grid(8, 5, 2)
+    assert (g.grid_rows, g.grid_cols, g.my_layer, g.my_row, g.my_col) == (2, 2, 1, 0, 1)
+    g = cblib.make_grid(4, 3, 1)
+    assert (g.my_layer, g.my_row, g.my_col) == (0, 1, 1)
+    g = cblib.make_grid(2, 1, 2)
+    assert (g.grid_rows, g.my_layer, g.my_row, g.my_col) == (1, 1, 0, 0)
+    with pytest.raises(cb.CbgpuError):  # 8 ranks are not a square 2D grid (src/CommGrid.cpp:44-54)
+        cblib.make_grid(8, 0, 1)
+    with pytest.raises(cb.CbgpuError):
+        cblib.make_grid(6, 0, 4)
+
+
+def test_3d_partition_tiles_the_matrix():
+    import scipy.sparse as sp
+
+    M = sp.random(37, 41, density=0.2, random_state=1, format="csc")
+    D = cb.SpDCCols.from_scipy(M, np.float64)
+    for world, layers in ((1, 1), (4, 1), (2, 2), (8, 2), (16, 4)):
+        for split_cols in (True, False):
+            total = 0
+            cover = np.zeros((37, 41), dtype=int)
+            for r in range(world):
+                g = cblib.make_grid(world, r, layers)
+                from combblas_b200.host import local_range
+
+                r0, r1, c0, c1 = local_range(g, 37, 41, split_cols)
+                cover[r0:r1, c0:c1] += 1
+                blk = cb.partition_3d(D, g, split_cols)
+                assert (blk.m, blk.n) == (r1 - r0, c1 - c0)
+                total += blk.nnz
+            assert cover.min() == 1 and cover.max() == 1
+            assert total == D.nnz
+
+
+def test_rmat_host_generator_is_deterministic_and_in_range():
+    lib = cb.load_library()
+    r1, c1 = np.empty(1000, np.int64), np.empty(1000, np.int64)
+    r2, c2 = np.empty(1000, np.int64), np.empty(1000, np.int64)
+    assert lib.cbgpu_rmat_edges_host(10, 1000, 5, 0.57, 0.19, 0.19, 1, r1.ctypes.data, c1.ctypes.data) == 0
+    assert lib.cbgpu_rmat_edges_host(10, 1000, 5, 0.57, 0.19, 0.19, 1, r2.ctypes.data, c2.ctypes.data) == 0
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+    assert r1.min() >= 0 and r1.max() < 1024 and c1.min() >= 0 and c1.max() < 1024
+    assert len(np.unique(r1)) > 300  # the scramble spreads the skewed ids
+
+
+def test_host_spdccols_roundtrip():
+    import scipy.sparse as sp
+
+    M = sp.random(50, 60, density=0.1, random_state=3, format="csc")
+    D = cb.SpDCCols.from_scipy(M, np.float64)
+    colptr, rows, vals = D.to_csc()
+    assert np.array_equal(colptr, M.indptr) and np.array_equal(rows, M.indices) and np.array_equal(vals, M.data)
+    assert D.nzc == int((np.diff(M.indptr) > 0).sum())
+    S = D.colslice(10, 30)
+    assert S.nnz == M[:, 10:30].nnz and S.n == 20

@@ -1,0 +1,239 @@
+"""GPU parity tests proper: every call goes through the C ABI (libcbgpu.so) and is compared with the CPU oracle
+(the compiled reference when present, else its C restatement) and with the committed reference outputs."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import combblas_b200 as cb
+from oracle.oracle import Csc, SR_DTYPES
+from tests.util import assert_same, random_pair, rmat, to_csc, to_dcsc, typed
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name, prefix):
+    z = np.load(os.path.join(GOLD, name))
+    m, n = z[prefix + "_shape"]
+    return Csc(int(m), int(n), z[prefix + "_colptr"], z[prefix + "_rows"], z[prefix + "_vals"])
+
+
+def dcsc_of(c: Csc, dt=None, idx=np.int64):
+    return cb.SpDCCols.from_csc(c.m, c.n, c.colptr, c.rows, c.vals if dt is None else c.vals.astype(dt), idx)
+
+
+def gpu_mult(ctx, sr, A, B, idx=np.int64):
+    return cb.LocalHybridSpGEMM(ctx, sr, to_dcsc(A, SR_DTYPES[sr][0], idx), to_dcsc(B, SR_DTYPES[sr][1], idx))
+
+
+def check_pair(ctx, oracle, sr, A, B, idx=np.int64):
+    got = gpu_mult(ctx, sr, A, B, idx)
+    want = oracle.spgemm(to_csc(A, SR_DTYPES[sr][0]), to_csc(B, SR_DTYPES[sr][1]), sr)
+    assert_same(got, want, sr)
+    return got
+
+
+def test_reference_known_answer_bcsstk01(ctx):
+    A, G = load("bcsstk01_squared.npz", "A"), load("bcsstk01_squared.npz", "C")
+    got = cb.LocalHybridSpGEMM(ctx, 0, dcsc_of(A), dcsc_of(A))
+    assert got.getnnz() == 1292
+    assert np.array_equal(got.rows, G.rows) and np.array_equal(got.cols, G.cols_expanded())
+    assert np.max(np.abs(got.vals - G.vals) / np.abs(G.vals)) < 1e-12
+
+
+@pytest.mark.parametrize("sr", range(9))
+def test_committed_reference_outputs(ctx, sr):
+    f = f"ref_sr{sr}.npz"
+    A, B, Cg = load(f, "A"), load(f, "B"), load(f, "C")
+    got = cb.LocalHybridSpGEMM(ctx, sr, dcsc_of(A), dcsc_of(B))
+    assert_same(got, Cg, sr)
+    parts = [dcsc_of(load(f, f"P{i}")) for i in range(3)]
+    mg = cb.MultiwayMerge(ctx, sr, parts)
+    assert_same(mg, load(f, "M"), sr)
+
+
+@pytest.mark.parametrize("sr", range(9))
+@pytest.mark.parametrize("shape", [(300, 220, 260, 0.05, 0.04), (64, 2000, 50, 0.02, 0.3), (3000, 40, 3000, 0.2, 0.01)])
+def test_every_semiring_random(ctx, oracle, sr, shape):
+    m, k, n, da, db = shape
+    A, B = random_pair(m, k, n, da, db, 11 + sr, SR_DTYPES[sr])
+    check_pair(ctx, oracle, sr, A, B)
+
+
+@pytest.mark.parametrize("scale", [8, 11, 13])
+def test_rmat_squared_plus_times(ctx, oracle, scale):
+    A = rmat(scale, 16, seed=1)
+    got = check_pair(ctx, oracle, 0, A, A)
+    assert got.getnnz() > 0
+
+
+def test_rmat_scale14_all_paths(ctx, oracle):
+    """heavy columns: exercises the bitmap path with shared and HBM accumulators next to the hash paths"""
+    A = rmat(14, 16, seed=2)
+    want = oracle.spgemm(to_csc(A, np.float64), to_csc(A, np.float64), 0)
+    dA = ctx.upload(to_dcsc(A, np.float64))
+    for force, smem_acc in ((0, 12288), (1, 12288), (2, 12288), (0, 256), (2, 256)):
+        ctx.set_option("force_path", force)
+        ctx.set_option("bitmap_smem_acc", smem_acc)
+        D, st = ctx.spgemm(0, dA, dA, want_stats=True)
+        rows, cols, vals = ctx.download_coo(D)
+        got = cb.SpTuples(A.shape[0], A.shape[1], rows, cols, vals)
+        assert_same(got, want, 0)
+        assert st.flops == int((A.T @ sp.csc_matrix(np.ones((A.shape[0], 1)))).T @ np.diff(A.indptr)) or st.flops > 0
+        assert st.nnz_out == want.nnz
+        if force == 2:
+            assert st.tasks_hash_warp + st.tasks_hash_cta == 0
+        if smem_acc == 256:
+            assert st.tasks_bitmap_gmem > 0
+        D.free()
+    ctx.set_option("force_path", 0)
+    ctx.set_option("bitmap_smem_acc", 12288)
+    dA.free()
+
+
+@pytest.mark.parametrize("wlog2", [10, 12])
+@pytest.mark.parametrize("sr", [0, 3, 5])
+def test_row_windows(ctx, oracle, wlog2, sr):
+    """several row windows per column (forced by a small window) must give the same block"""
+    ctx.set_option("bitmap_window_log2", wlog2)
+    try:
+        A = rmat(13, 16, seed=3)
+        B = rmat(13, 8, seed=4)
+        check_pair(ctx, oracle, sr, typed(A, SR_DTYPES[sr][0]), typed(B, SR_DTYPES[sr][1]))
+    finally:
+        ctx.set_option("bitmap_window_log2", 19)
+
+
+def test_tall_matrix_natural_windows(ctx, oracle):
+    """m > 2^19 rows: the default window size needs three windows"""
+    rng = np.random.default_rng(5)
+    m, k, n = 1_300_000, 3000, 400
+    A = sp.random(m, k, density=40.0 / m * 20, random_state=rng, format="csc")
+    B = sp.random(k, n, density=0.05, random_state=rng, format="csc")
+    check_pair(ctx, oracle, 0, A, B)
+    check_pair(ctx, oracle, 2, typed(A, np.int64), typed(B, np.int64))
+
+
+def test_select_max_er_config_reduced(ctx, oracle):
+    """config 2 at reduced size: ER d=8, A bool, B int64 = 1 + row id, SelectMaxSRing<bool,int64_t>, bit-exact"""
+    n, d = 1 << 15, 8
+    rng = np.random.default_rng(2)
+    r, c = rng.integers(0, n, n * d), rng.integers(0, n, n * d)
+    P = sp.coo_matrix((np.ones(n * d), (r, c)), shape=(n, n)).tocsc()
+    P.sum_duplicates()
+    P.sort_indices()
+    A = P.copy()
+    A.data[:] = 1
+    B = P.copy()
+    B.data = (1 + B.indices).astype(np.float64)
+    got = cb.LocalHybridSpGEMM(ctx, 3, to_dcsc(A, np.uint8), to_dcsc(B, np.int64))
+    want = oracle.spgemm(to_csc(A, np.uint8), to_csc(B, np.int64), 3)
+    assert_same(got, want, 3)
+
+
+def test_int32_local_indices(ctx, oracle):
+    """SpDCCols<int32_t,...> local blocks (MCL.cpp:846) go through the same entry"""
+    A, B = random_pair(500, 400, 300, 0.03, 0.03, 9, SR_DTYPES[0])
+    check_pair(ctx, oracle, 0, A, B, idx=np.int32)
+
+
+def test_empty_and_degenerate(ctx):
+    z = cb.SpDCCols.from_coo(5, 7, [], [], np.zeros(0))
+    a = cb.SpDCCols.from_coo(4, 5, [0, 3], [1, 4], np.array([2.0, 3.0]))
+    c = cb.LocalHybridSpGEMM(ctx, 0, a, z)
+    assert c.getnnz() == 0 and (c.m, c.n) == (4, 7)
+    c = cb.LocalHybridSpGEMM(ctx, 0, cb.SpDCCols.from_coo(4, 5, [], [], np.zeros(0)), cb.SpDCCols.from_coo(5, 2, [1], [1], np.ones(1)))
+    assert c.getnnz() == 0 and (c.m, c.n) == (4, 2)
+    # B columns that only select empty A columns give no output column
+    a = cb.SpDCCols.from_coo(3, 3, [0], [0], np.array([2.0]))
+    b = cb.SpDCCols.from_coo(3, 2, [0, 2], [0, 1], np.array([5.0, 7.0]))
+    c = cb.LocalHybridSpGEMM(ctx, 0, a, b)
+    assert c.getnnz() == 1 and c.rows[0] == 0 and c.cols[0] == 0 and c.vals[0] == 10.0
+    # explicit zeros are kept: cancellation stays a stored entry
+    x = cb.SpDCCols.from_coo(2, 2, [0, 0], [0, 1], np.array([1.0, -1.0]))
+    y = cb.SpDCCols.from_coo(2, 1, [0, 1], [0, 0], np.array([1.0, 1.0]))
+    c = cb.LocalHybridSpGEMM(ctx, 0, x, y)
+    assert c.getnnz() == 1 and c.vals[0] == 0.0
+    with pytest.raises(cb.CbgpuError) as e:
+        cb.LocalHybridSpGEMM(ctx, 0, a, cb.SpDCCols.from_coo(4, 2, [0], [0], np.ones(1)))
+    assert e.value.code == -5  # DIMMISMATCH
+    with pytest.raises(TypeError):
+        cb.LocalHybridSpGEMM(ctx, 3, a, b)
+
+
+def test_symbolic_matches_oracle(ctx, port_oracle):
+    A = rmat(12, 16, seed=6)
+    flop, nnz = port_oracle.symbolic(to_csc(A, np.float64), to_csc(A, np.float64))
+    f, z = cb.EstimateFLOP(ctx, to_dcsc(A, np.float64), to_dcsc(A, np.float64))
+    assert f == int(flop.sum()) and z == int(nnz.sum())
+
+
+@pytest.mark.parametrize("sr", [0, 2, 3, 4, 5])
+@pytest.mark.parametrize("k", [1, 2, 4, 7])
+def test_merge_matches_oracle(ctx, port_oracle, sr, k):
+    _, B = random_pair(400, 300, 350, 0.04, 0.04, 60 + sr, SR_DTYPES[sr])
+    b = to_csc(B, SR_DTYPES[sr][1])
+    parts = []
+    for i in range(k):
+        Ai, _ = random_pair(400, 300, 350, 0.04, 0.04, 700 + 9 * sr + i, SR_DTYPES[sr])
+        parts.append(port_oracle.spgemm(to_csc(Ai, SR_DTYPES[sr][0]), b, sr))
+    want = port_oracle.merge(parts, sr)
+    got = cb.MultiwayMerge(ctx, sr, [dcsc_of(p) for p in parts])
+    assert_same(got, want, sr)
+
+
+def test_merge_large_columns_and_windows(ctx, port_oracle):
+    A = rmat(13, 16, seed=8)
+    a = to_csc(A, np.float64)
+    parts = [port_oracle.spgemm(a, to_csc(rmat(13, 4, seed=20 + i), np.float64), 0) for i in range(3)]
+    want = port_oracle.merge(parts, 0)
+    for wlog2 in (19, 11):
+        ctx.set_option("bitmap_window_log2", wlog2)
+        got = cb.MultiwayMerge(ctx, 0, [dcsc_of(p) for p in parts])
+        assert_same(got, want, 0)
+    ctx.set_option("bitmap_window_log2", 19)
+
+
+def test_colsplit_concat_and_checksum(ctx):
+    A = rmat(11, 16, seed=9)
+    D = ctx.upload(to_dcsc(A, np.float64))
+    base = ctx.checksum(D)
+    parts = ctx.colsplit(D, 5)
+    assert sum(p.nnz for p in parts) == D.nnz and sum(p.shape[1] for p in parts) == A.shape[1]
+    # ColSplit rule (dcsc.cpp:1202): floor(n/parts) columns each, remainder to the last
+    assert [p.shape[1] for p in parts] == [A.shape[1] // 5] * 4 + [A.shape[1] - 4 * (A.shape[1] // 5)]
+    J = ctx.colconcat(parts)
+    assert ctx.checksum(J) == base
+    m, n, jc, cp, ir, numx = ctx.download(J)
+    ref = to_dcsc(A, np.float64)
+    assert np.array_equal(jc, ref.jc) and np.array_equal(cp, ref.cp) and np.array_equal(ir, ref.ir) and np.array_equal(numx, ref.numx)
+    S = ctx.colslice(D, 100, 900)
+    m, n, jc, cp, ir, numx = ctx.download(S, np.int32)
+    want = ref.colslice(100, 900)
+    assert n == 800 and np.array_equal(jc, want.jc) and np.array_equal(cp, want.cp) and np.array_equal(ir, want.ir)
+    # slab-wise multiply == whole multiply (what MemEfficientSpGEMM's phases do, ParFriends.h:553-772)
+    whole = ctx.spgemm(0, D, D)
+    slabs = [ctx.spgemm(0, D, p) for p in parts]
+    joined = ctx.colconcat(slabs)
+    a, b = ctx.checksum(whole), ctx.checksum(joined)
+    assert a[0] == b[0]
+    r1, c1, v1 = ctx.download_coo(whole)
+    r2, c2, v2 = ctx.download_coo(joined)
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and np.allclose(v1, v2, rtol=1e-12, atol=0)
+
+
+def test_device_generator_equals_host_generator(ctx):
+    for scale, ef, mode, dt in ((10, 16, 0, cb.F64), (12, 8, 1, cb.BOOL), (11, 8, 2, cb.I64)):
+        D = ctx.gen_rmat(scale, ef << scale, seed=5, dtype=dt, value_mode=mode)
+        A = rmat(scale, ef, seed=5)
+        m, n, jc, cp, ir, numx = ctx.download(D)
+        ref = to_dcsc(A, np.float64)
+        assert np.array_equal(jc, ref.jc) and np.array_equal(cp, ref.cp) and np.array_equal(ir, ref.ir)
+        if mode == 0:
+            assert np.array_equal(numx, ref.numx)
+        elif mode == 1:
+            assert np.all(numx == 1)
+        else:
+            assert np.array_equal(numx, 1 + ir)
