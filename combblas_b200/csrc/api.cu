@@ -199,6 +199,80 @@ int mat_colslice(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *M, int64_t c0, int64
   return CBGPU_OK;
 }
 
+// rows [r0, r1) of every stored column: counts, then copy with rebased row ids (rows are ascending per column)
+__global__ void rowrange_count_kernel(const int64_t *cp, const int32_t *ir, int64_t nzc, int64_t r0, int64_t r1, int64_t *lo,
+                                      int64_t *cnt) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nzc) return;
+  int64_t a = cp[c], b = cp[c + 1], e = b;
+  while (a < b) {
+    int64_t mid = (a + b) >> 1;
+    if (ir[mid] < r0) a = mid + 1;
+    else b = mid;
+  }
+  int64_t first = a;
+  b = e;
+  while (a < b) {
+    int64_t mid = (a + b) >> 1;
+    if (ir[mid] < r1) a = mid + 1;
+    else b = mid;
+  }
+  lo[c] = first;
+  cnt[c] = a - first;
+}
+__global__ void rowrange_copy_kernel(const int64_t *lo, const int64_t *newptr, const int32_t *ir, const unsigned char *vals,
+                                     int vbytes, int64_t nzc, int32_t r0, int32_t *oir, unsigned char *ovals) {
+  int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nzc) return;
+  int64_t src = lo[c], dst = newptr[c], n = newptr[c + 1] - dst;
+  for (int64_t i = threadIdx.x & 31; i < n; i += 32) {
+    oir[dst + i] = ir[src + i] - r0;
+    for (int b = 0; b < vbytes; ++b) ovals[(dst + i) * vbytes + b] = vals[(src + i) * vbytes + b];
+  }
+}
+
+int mat_submatrix(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *M, int64_t r0, int64_t r1, int64_t c0, int64_t c1,
+                  cbgpu_mat_impl **out) {
+  if (r0 < 0 || r1 < r0 || r1 > M->m) return set_error(ctx, CBGPU_ERR_INVALID, "bad row range");
+  cbgpu_mat_impl *S = nullptr;
+  CB_TRY(mat_colslice(ctx, M, c0, c1, &S));
+  if (r0 == 0 && r1 == M->m) {
+    *out = S;
+    return CBGPU_OK;
+  }
+  int64_t *lo = nullptr, *cnt = nullptr, *newptr = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &lo, (size_t)S->nzc + 1));
+  CB_TRY(dev_alloc_t(ctx, &cnt, (size_t)S->nzc + 1));
+  CB_TRY(dev_alloc_t(ctx, &newptr, (size_t)S->nzc + 1));
+  if (S->nzc > 0) {
+    rowrange_count_kernel<<<nblocks(S->nzc), 256, 0, ctx->stream>>>(S->cp, S->ir, S->nzc, r0, r1, lo, cnt);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  CB_TRY(exclusive_scan_i64(ctx, cnt, newptr, S->nzc));
+  int64_t nnz = 0;
+  CB_CUDA(ctx, cudaMemcpyAsync(&nnz, newptr + S->nzc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cbgpu_mat_impl *R = nullptr;
+  CB_TRY(mat_alloc(ctx, r1 - r0, S->n, nnz, -1, S->dtype, &R));
+  if (S->nzc > 0) {
+    rowrange_copy_kernel<<<nblocks(S->nzc * 32), 256, 0, ctx->stream>>>(lo, newptr, S->ir, (const unsigned char *)S->numx,
+                                                                       (int)dtype_size(S->dtype), S->nzc, (int32_t)r0, R->ir,
+                                                                       (unsigned char *)R->numx);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  int rc = compact_columns(ctx, S->jc, newptr, S->nzc, &R->jc, &R->cp, &R->nzc);
+  dev_free(ctx, lo);
+  dev_free(ctx, cnt);
+  dev_free(ctx, newptr);
+  mat_release(ctx, S);
+  if (rc != CBGPU_OK) {
+    mat_release(ctx, R);
+    return rc;
+  }
+  *out = R;
+  return CBGPU_OK;
+}
+
 int mat_colconcat(cbgpu_ctx_impl *ctx, int parts, cbgpu_mat_impl *const *in, cbgpu_mat_impl **out) {
   if (parts < 1) return set_error(ctx, CBGPU_ERR_INVALID, "colconcat needs at least one part");
   int64_t n = 0, nnz = 0, nzc = 0;
@@ -267,6 +341,7 @@ int cbgpu_create(int device, void *stream, cbgpu_ctx **out) {
     ctx->own_stream = true;
   }
   for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 2 * CBGPU_K_COUNT; ++i) cudaEventCreate(&ctx->kev[i]);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   // keep freed blocks in the stream-ordered pool: repeated multiplies must not hit cudaMalloc/cudaFree
@@ -284,6 +359,7 @@ int cbgpu_destroy(cbgpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2 * CBGPU_K_COUNT; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CBGPU_OK;
@@ -443,6 +519,14 @@ int cbgpu_mat_colslice(cbgpu_ctx *ctx, const cbgpu_mat *M, int64_t c0, int64_t c
   cbgpu_mat_impl *S = nullptr;
   CB_TRY(mat_colslice(ctx, M, c0, c1, &S));
   *out = (S);
+  return CBGPU_OK;
+}
+
+int cbgpu_mat_submatrix(cbgpu_ctx *ctx, const cbgpu_mat *M, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cbgpu_mat **out) {
+  if (!ctx || !M || !out) return CBGPU_ERR_INVALID;
+  cbgpu_mat_impl *S = nullptr;
+  CB_TRY(mat_submatrix(ctx, M, r0, r1, c0, c1, &S));
+  *out = S;
   return CBGPU_OK;
 }
 

@@ -42,6 +42,7 @@ struct cbgpu_ctx {
   int sm_count = cbgpu::kSMs;
   int max_smem_optin = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[2 * CBGPU_K_COUNT] = {};
 };
 
 struct cbgpu_mat {

@@ -235,6 +235,8 @@ static void add_stats(cbgpu_stats &acc, const cbgpu_stats &s) {
   acc.tasks_bitmap_smem += s.tasks_bitmap_smem; acc.tasks_bitmap_gmem += s.tasks_bitmap_gmem;
   acc.flops_hash_warp += s.flops_hash_warp; acc.flops_hash_cta += s.flops_hash_cta;
   acc.flops_bitmap_smem += s.flops_bitmap_smem; acc.flops_bitmap_gmem += s.flops_bitmap_gmem;
+  acc.nnz_out += s.nnz_out;
+  for (int i = 0; i < CBGPU_K_COUNT; ++i) acc.ms_kernel[i] += s.ms_kernel[i];
 }
 
 struct Timer {

@@ -74,6 +74,9 @@ inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
   return CBGPU_OK;
 }
 
+#define CB_KBEGIN(id) do { used[id] = true; cudaEventRecord(ctx->kev[2 * (id)], st); } while (0)
+#define CB_KEND(id) cudaEventRecord(ctx->kev[2 * (id) + 1], st)
+
 struct EngineIO {
   // A side (or the concatenated merge lists)
   const int64_t *Acolptr;
@@ -99,6 +102,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   const int64_t launches0 = ctx->launches;
   cbgpu_stats stats;
   memset(&stats, 0, sizeof(stats));
+  bool used[CBGPU_K_COUNT] = {};
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
 
   const int64_t ncol = io.ncol;
@@ -174,7 +178,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     CB_CUDA(ctx, cudaMemsetAsync(tasknnz, 0, sizeof(int64_t) * (size_t)ntask, st));
     sym_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(taskflop, ntask, bucket);
     CB_LAUNCH_CHECK(ctx);
-    CB_TRY(bin_tasks(ctx, bucket, taskflop, ntask, order, &bins));
+    CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, order, &bins));
   }
   for (int b = 1; b < 256; ++b) stats.flops += bins.weight[b];
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -188,37 +192,52 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     if (cnt > 0) {
       auto kern = sym_bitmap_kernel<SR, MERGE>;
       CB_TRY(optin_smem(ctx, kern, bm_bytes));
+      CB_KBEGIN(CBGPU_K_SYM_BITMAP);
       kern<<<(unsigned)cnt, kBitmapThreads, bm_bytes, st>>>(src, order + beg, cnt, io.m, tasknnz);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_SYM_BITMAP);
+      for (int b = 16; b <= 39; ++b) stats.flops_sym[0] += bins.weight[b];
     }
     bucket_range(bins, 13, 15, &beg, &cnt);
     if (cnt > 0) {
       auto kern = sym_hash_kernel<SR, MERGE, 16, 15>;
       size_t sm = sizeof(unsigned) << 15;
       CB_TRY(optin_smem(ctx, kern, sm));
+      CB_KBEGIN(CBGPU_K_SYM_HASH_CTA_L);
       kern<<<(unsigned)cnt, 512, sm, st>>>(src, order + beg, cnt, tasknnz);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_SYM_HASH_CTA_L);
+      for (int b = 13; b <= 15; ++b) stats.flops_sym[1] += bins.weight[b];
     }
     bucket_range(bins, 10, 12, &beg, &cnt);
     if (cnt > 0) {
       auto kern = sym_hash_kernel<SR, MERGE, 8, 12>;
       size_t sm = sizeof(unsigned) << 12;
+      CB_KBEGIN(CBGPU_K_SYM_HASH_CTA);
       kern<<<(unsigned)cnt, 256, sm, st>>>(src, order + beg, cnt, tasknnz);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_SYM_HASH_CTA);
+      for (int b = 10; b <= 12; ++b) stats.flops_sym[2] += bins.weight[b];
     }
     bucket_range(bins, 7, 9, &beg, &cnt);
     if (cnt > 0) {
       auto kern = sym_hash_kernel<SR, MERGE, 1, 9>;
       size_t sm = 8 * (sizeof(unsigned) << 9);
+      CB_KBEGIN(CBGPU_K_SYM_HASH_WARP);
       kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, tasknnz);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_SYM_HASH_WARP);
+      for (int b = 7; b <= 9; ++b) stats.flops_sym[3] += bins.weight[b];
     }
     bucket_range(bins, 1, 6, &beg, &cnt);
     if (cnt > 0) {
       auto kern = sym_hash_kernel<SR, MERGE, 1, 6>;
       size_t sm = 8 * (sizeof(unsigned) << 6);
+      CB_KBEGIN(CBGPU_K_SYM_HASH_WARP_S);
       kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, tasknnz);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_SYM_HASH_WARP_S);
+      for (int b = 1; b <= 6; ++b) stats.flops_sym[4] += bins.weight[b];
     }
   }
   // ---- K3: scan -> output offsets
@@ -245,7 +264,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048,
                                                                         opt.bitmap_smem_acc, (int)opt.force_path, bucket);
       CB_LAUNCH_CHECK(ctx);
-      CB_TRY(bin_tasks(ctx, bucket, taskflop, ntask, order, &nb));
+      CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, order, &nb));
     }
     out_t *Cval = reinterpret_cast<out_t *>(Cm->numx);
     int64_t beg, cnt;
@@ -255,10 +274,12 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       auto kern = num_bitmap_kernel<SR, MERGE, true>;
       size_t sm = bm_bytes + (size_t)max_cells * 4 + 16;
       CB_TRY(optin_smem(ctx, kern, sm));
+      CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
       kern<<<(unsigned)cnt, kBitmapThreads, sm, st>>>(src, order + beg, cnt, io.m, max_cells, taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
       stats.tasks_bitmap_gmem = cnt;
-      for (int b = 81; b <= 119; ++b) stats.flops_bitmap_gmem += nb.weight[b];
+      for (int b = 81; b <= 119; ++b) { stats.flops_bitmap_gmem += nb.weight[b]; stats.nnz_bitmap_gmem += nb.weight2[b]; }
     }
     // bitmap, accumulators in shared memory
     bucket_range(nb, 41, 79, &beg, &cnt);
@@ -266,10 +287,12 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       auto kern = num_bitmap_kernel<SR, MERGE, false>;
       size_t sm = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)opt.bitmap_smem_acc * sizeof(acc_t);
       CB_TRY(optin_smem(ctx, kern, sm));
+      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
       kern<<<(unsigned)cnt, kBitmapThreads, sm, st>>>(src, order + beg, cnt, io.m, max_cells, taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
       stats.tasks_bitmap_smem = cnt;
-      for (int b = 41; b <= 79; ++b) stats.flops_bitmap_smem += nb.weight[b];
+      for (int b = 41; b <= 79; ++b) { stats.flops_bitmap_smem += nb.weight[b]; stats.nnz_bitmap_smem += nb.weight2[b]; }
     }
     // hash per CTA: 257..2048 outputs
     bucket_range(nb, 10, 39, &beg, &cnt);
@@ -277,10 +300,12 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       auto kern = num_hash_kernel<SR, MERGE, 8, 12>;
       size_t sm = ((size_t)1 << 12) * (8 + sizeof(acc_t) + 4) + 16;
       CB_TRY(optin_smem(ctx, kern, sm));
+      CB_KBEGIN(CBGPU_K_NUM_HASH_CTA);
       kern<<<(unsigned)cnt, 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_HASH_CTA);
       stats.tasks_hash_cta = cnt;
-      for (int b = 10; b <= 39; ++b) stats.flops_hash_cta += nb.weight[b];
+      for (int b = 10; b <= 39; ++b) { stats.flops_hash_cta += nb.weight[b]; stats.nnz_hash_cta += nb.weight2[b]; }
     }
     // hash per warp: 33..256 outputs
     bucket_range(nb, 7, 9, &beg, &cnt);
@@ -288,20 +313,24 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 9>;
       size_t sm = 8 * ((size_t)1 << 9) * (8 + sizeof(acc_t) + 4) + 64;
       CB_TRY(optin_smem(ctx, kern, sm));
+      CB_KBEGIN(CBGPU_K_NUM_HASH_WARP);
       kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_HASH_WARP);
       stats.tasks_hash_warp += cnt;
-      for (int b = 7; b <= 9; ++b) stats.flops_hash_warp += nb.weight[b];
+      for (int b = 7; b <= 9; ++b) { stats.flops_hash_warp += nb.weight[b]; stats.nnz_hash_warp += nb.weight2[b]; }
     }
     // hash per warp: <= 32 outputs
     bucket_range(nb, 1, 6, &beg, &cnt);
     if (cnt > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 6>;
       size_t sm = 8 * ((size_t)1 << 6) * (8 + sizeof(acc_t) + 4) + 64;
+      CB_KBEGIN(CBGPU_K_NUM_HASH_WARP_S);
       kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_HASH_WARP_S);
       stats.tasks_hash_warp += cnt;
-      for (int b = 1; b <= 6; ++b) stats.flops_hash_warp += nb.weight[b];
+      for (int b = 1; b <= 6; ++b) { stats.flops_hash_warp += nb.weight[b]; stats.nnz_hash_warp += nb.weight2[b]; }
     }
     // ---- DCSC assembly: column pointers of the candidate columns, then drop the empty ones
     const int64_t *cand_ptr = taskptr;
@@ -337,6 +366,8 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   cudaEventElapsedTime(&stats.ms_symbolic, ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&stats.ms_numeric, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&stats.ms_total, ctx->ev[0], ctx->ev[3]);
+  for (int i = 0; i < CBGPU_K_COUNT; ++i)
+    if (used[i]) cudaEventElapsedTime(&stats.ms_kernel[i], ctx->kev[2 * i], ctx->kev[2 * i + 1]);
   stats.kernel_launches = ctx->launches - launches0;
   if (io.stats) *io.stats = stats;
   if (io.C) *io.C = Cm;

@@ -209,12 +209,14 @@ int build_window_table(cbgpu_ctx_impl *ctx, const int64_t *colptr, const int32_t
 
 // ------------------------------------------------------------------------------------------------ binning
 __global__ void __launch_bounds__(256)
-bucket_hist_kernel(const uint8_t *bucket, const int64_t *weight, int64_t n, unsigned long long *hist,
-                   unsigned long long *whist) {
+bucket_hist_kernel(const uint8_t *bucket, const int64_t *weight, const int64_t *weight2, int64_t n,
+                   unsigned long long *hist, unsigned long long *whist, unsigned long long *whist2) {
   __shared__ unsigned int h[256];
   __shared__ unsigned long long wh[256];
+  __shared__ unsigned long long wh2[256];
   h[threadIdx.x] = 0;
   wh[threadIdx.x] = 0;
+  wh2[threadIdx.x] = 0;
   __syncthreads();
   int64_t base = (int64_t)blockIdx.x * 4096;
   for (int i = 0; i < 16; ++i) {
@@ -223,12 +225,14 @@ bucket_hist_kernel(const uint8_t *bucket, const int64_t *weight, int64_t n, unsi
       int b = bucket[idx];
       atomicAdd(&h[b], 1u);
       if (weight) atomicAdd(&wh[b], (unsigned long long)weight[idx]);
+      if (weight2) atomicAdd(&wh2[b], (unsigned long long)weight2[idx]);
     }
   }
   __syncthreads();
   if (h[threadIdx.x]) {
     atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
     if (weight) atomicAdd(&whist[threadIdx.x], wh[threadIdx.x]);
+    if (weight2) atomicAdd(&whist2[threadIdx.x], wh2[threadIdx.x]);
   }
 }
 
@@ -260,16 +264,17 @@ bucket_scatter_kernel(const uint8_t *bucket, int64_t n, unsigned long long *curs
   }
 }
 
-int bin_tasks(cbgpu_ctx_impl *ctx, const uint8_t *bucket, const int64_t *weight, int64_t n, int32_t *order, BinResult *res) {
+int bin_tasks(cbgpu_ctx_impl *ctx, const uint8_t *bucket, const int64_t *weight, const int64_t *weight2, int64_t n,
+              int32_t *order, BinResult *res) {
   memset(res, 0, sizeof(*res));
   if (n <= 0) return CBGPU_OK;
   unsigned long long *dh = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &dh, 768));
-  CB_CUDA(ctx, cudaMemsetAsync(dh, 0, 768 * sizeof(unsigned long long), ctx->stream));
+  CB_TRY(dev_alloc_t(ctx, &dh, 1024));
+  CB_CUDA(ctx, cudaMemsetAsync(dh, 0, 1024 * sizeof(unsigned long long), ctx->stream));
   unsigned nblk = (unsigned)((n + 4095) / 4096);
-  bucket_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, weight, n, dh, dh + 256);
+  bucket_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, weight, weight2, n, dh, dh + 256, dh + 512);
   CB_LAUNCH_CHECK(ctx);
-  unsigned long long hh[512];
+  unsigned long long hh[768];
   CB_CUDA(ctx, cudaMemcpyAsync(hh, dh, sizeof(hh), cudaMemcpyDeviceToHost, ctx->stream));
   CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // descending bucket order: larger work first
@@ -278,6 +283,7 @@ int bin_tasks(cbgpu_ctx_impl *ctx, const uint8_t *bucket, const int64_t *weight,
   for (int b = 255; b >= 1; --b) {
     res->count[b] = (int64_t)hh[b];
     res->weight[b] = (int64_t)hh[256 + b];
+    res->weight2[b] = (int64_t)hh[512 + b];
     res->offset[b] = off;
     cur[b] = (unsigned long long)off;
     off += (int64_t)hh[b];
@@ -286,8 +292,8 @@ int bin_tasks(cbgpu_ctx_impl *ctx, const uint8_t *bucket, const int64_t *weight,
   res->offset[0] = off;
   cur[0] = (unsigned long long)off;
   res->listed = off;
-  CB_CUDA(ctx, cudaMemcpyAsync(dh + 512, cur, sizeof(cur), cudaMemcpyHostToDevice, ctx->stream));
-  bucket_scatter_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, n, dh + 512, order);
+  CB_CUDA(ctx, cudaMemcpyAsync(dh + 768, cur, sizeof(cur), cudaMemcpyHostToDevice, ctx->stream));
+  bucket_scatter_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, n, dh + 768, order);
   CB_LAUNCH_CHECK(ctx);
   // `cur` lives on this stack frame: make sure the copy has been consumed before returning
   CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

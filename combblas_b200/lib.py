@@ -44,10 +44,18 @@ class Stats(C.Structure):
                 ("ms_numeric", C.c_float), ("ms_total", C.c_float),
                 ("tasks_hash_warp", C.c_int64), ("tasks_hash_cta", C.c_int64), ("tasks_bitmap_smem", C.c_int64),
                 ("tasks_bitmap_gmem", C.c_int64), ("flops_hash_warp", C.c_int64), ("flops_hash_cta", C.c_int64),
-                ("flops_bitmap_smem", C.c_int64), ("flops_bitmap_gmem", C.c_int64)]
+                ("flops_bitmap_smem", C.c_int64), ("flops_bitmap_gmem", C.c_int64),
+                ("nnz_hash_warp", C.c_int64), ("nnz_hash_cta", C.c_int64), ("nnz_bitmap_smem", C.c_int64),
+                ("nnz_bitmap_gmem", C.c_int64), ("ms_kernel", C.c_float * 12), ("flops_sym", C.c_int64 * 5)]
+
+    KERNELS = ["sym_bitmap", "sym_hash_cta_large", "sym_hash_cta", "sym_hash_warp", "sym_hash_warp_small",
+               "num_bitmap_gmem", "num_bitmap_smem", "num_hash_cta", "num_hash_warp", "num_hash_warp_small", "flop", "-"]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_kernel", "flops_sym")}
+        d["ms_kernel"] = {n: round(float(self.ms_kernel[i]), 4) for i, n in enumerate(self.KERNELS) if self.ms_kernel[i] > 0}
+        d["flops_sym"] = [int(x) for x in self.flops_sym]
+        return d
 
 
 class DistStats(C.Structure):
@@ -91,6 +99,7 @@ SIGNATURES = {
     "cbgpu_mat_colsplit": (C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
     "cbgpu_mat_colslice": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "cbgpu_mat_colconcat": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "cbgpu_mat_submatrix": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "cbgpu_spgemm_local": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_spgemm_symbolic": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_spgemm_local_host": (C.c_int, [_P, C.c_int, C.POINTER(_DcscView), C.POINTER(_DcscView), C.POINTER(_P), C.POINTER(Stats)]),
@@ -268,6 +277,11 @@ class Context:
     def colslice(self, D: DeviceMatrix, c0: int, c1: int) -> DeviceMatrix:
         h = _P()
         self._check(self.lib.cbgpu_mat_colslice(self.handle, D.handle, c0, c1, C.byref(h)))
+        return DeviceMatrix(self, h)
+
+    def submatrix(self, D: DeviceMatrix, r0: int, r1: int, c0: int, c1: int) -> DeviceMatrix:
+        h = _P()
+        self._check(self.lib.cbgpu_mat_submatrix(self.handle, D.handle, r0, r1, c0, c1, C.byref(h)))
         return DeviceMatrix(self, h)
 
     def colsplit(self, D: DeviceMatrix, parts: int):

@@ -96,7 +96,17 @@ typedef struct {
   float ms_total;
   int64_t tasks_hash_warp, tasks_hash_cta, tasks_bitmap_smem, tasks_bitmap_gmem; /* numeric path census */
   int64_t flops_hash_warp, flops_hash_cta, flops_bitmap_smem, flops_bitmap_gmem;
+  int64_t nnz_hash_warp, nnz_hash_cta, nnz_bitmap_smem, nnz_bitmap_gmem; /* outputs written per numeric path */
+  /* device time of each kernel class of this call (CUDA events on the context's stream), see CBGPU_K_* */
+  float ms_kernel[12];
+  int64_t flops_sym[5]; /* products walked by the symbolic classes CBGPU_K_SYM_* */
 } cbgpu_stats;
+
+enum {
+  CBGPU_K_SYM_BITMAP = 0, CBGPU_K_SYM_HASH_CTA_L = 1, CBGPU_K_SYM_HASH_CTA = 2, CBGPU_K_SYM_HASH_WARP = 3,
+  CBGPU_K_SYM_HASH_WARP_S = 4, CBGPU_K_NUM_BITMAP_GMEM = 5, CBGPU_K_NUM_BITMAP_SMEM = 6, CBGPU_K_NUM_HASH_CTA = 7,
+  CBGPU_K_NUM_HASH_WARP = 8, CBGPU_K_NUM_HASH_WARP_S = 9, CBGPU_K_FLOP = 10, CBGPU_K_COUNT = 12
+};
 
 /* ---------------------------------------------------------------- lifecycle */
 int cbgpu_version(void);
@@ -135,6 +145,10 @@ int cbgpu_mat_checksum(cbgpu_ctx *ctx, const cbgpu_mat *mat, uint64_t *pattern_s
 int cbgpu_mat_colsplit(cbgpu_ctx *ctx, const cbgpu_mat *mat, int parts, cbgpu_mat **out /* parts */);
 int cbgpu_mat_colslice(cbgpu_ctx *ctx, const cbgpu_mat *mat, int64_t col_begin, int64_t col_end, cbgpu_mat **out);
 int cbgpu_mat_colconcat(cbgpu_ctx *ctx, int parts, cbgpu_mat *const *in, cbgpu_mat **out);
+/* block [row_begin,row_end) x [col_begin,col_end) with local indices: what the 2D/3D distributions hand each rank
+ * (SpParMat::Owner SpParMat.cpp:5081; SpParMat3D ctor SpParMat3D.cpp:187-283 does this through an all-to-all) */
+int cbgpu_mat_submatrix(cbgpu_ctx *ctx, const cbgpu_mat *mat, int64_t row_begin, int64_t row_end, int64_t col_begin,
+                        int64_t col_end, cbgpu_mat **out);
 
 /* ---------------------------------------------------------------- local multiply (K1-K4)
  * replaces: LocalHybridSpGEMM (mtSpGEMM.h:213-460), LocalSpGEMMHash (:463-656), LocalSpGEMM (:74-202)
