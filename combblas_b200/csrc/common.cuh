@@ -23,9 +23,9 @@ struct Options {
   int64_t num_warp_max = 256;    // warp table 512
   int64_t num_cta_max = 2048;    // CTA(256) table 4096
   // bitmap path
-  int64_t bitmap_window_log2 = 19; // rows per window (2^19 rows = 64 KiB bitmap + 32 KiB rank index)
+  int64_t bitmap_window_log2 = 17; // rows per window (2^17 rows = 16 KiB bitmap + 8 KiB rank index)
   int64_t bitmap_min_nnz = 0;      // 0 = automatic: clamp(window_rows/2048, 32, num_cta_max)
-  int64_t bitmap_smem_acc = 12288; // accumulators kept in shared memory up to this many outputs per task
+  int64_t bitmap_smem_acc = 2048;  // accumulators kept in shared memory up to this many outputs per task
   int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only
 };
 

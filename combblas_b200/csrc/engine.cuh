@@ -26,10 +26,8 @@
 namespace cbgpu {
 
 constexpr int kWarpLong = 48;    // segments at least this long are walked by a whole warp
-constexpr int kCtaLong = 1536;   // ... and at least this long by the whole CTA (via a small queue)
-constexpr int kQueueCap = 96;
 constexpr int kBitmapThreads = 512;
-constexpr int kLightMax = 2048;  // with several row windows, columns up to this many products stay one task
+constexpr int kLightMax = 256;   // with several row windows, columns up to this many products stay one task (warp hash)
 
 // ------------------------------------------------------------------------------------------------ source
 template <class SR, bool MERGE>
@@ -112,12 +110,15 @@ __device__ __forceinline__ uint8_t shfl_mult<uint8_t>(uint8_t v, int src) {
   return (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)v, src);
 }
 
+// shared-memory workspace of the balanced CTA walk (one chunk of up to 512 segments at a time)
+constexpr int kWalkChunk = 512;
 struct CtaQueue {
-  int n;
-  int len[kQueueCap];
-  long long beg[kQueueCap];
-  unsigned long long mult[kQueueCap]; // raw bits of the multiplier
+  long long pre[kWalkChunk + 1];         // exclusive prefix of the segment lengths of the chunk (in products)
+  long long beg[kWalkChunk];             // first position of every segment
+  unsigned long long mult[kWalkChunk];   // raw bits of the multiplier
+  long long warp_sums[32];
 };
+struct NoQueue {};
 
 template <class M>
 __device__ __forceinline__ unsigned long long mult_bits(M v) {
@@ -132,82 +133,126 @@ __device__ __forceinline__ M bits_mult(unsigned long long r) {
   return v;
 }
 
-// One warp walks the segments [first + 32*chunk...] assigned to it. f(pos, mult) is invoked once per product by
-// exactly one lane. Long segments are strided by the whole warp (coalesced), the rest are flattened so that
-// all 32 lanes stay busy on short A-columns. Segments >= kCtaLong are deferred to `q` when given.
+// One warp processes up to 32 segments, one held per lane as (beg, len, mult). f(pos, mult) is invoked once per
+// product by exactly one lane. Long segments are strided by the whole warp (coalesced), the rest are flattened
+// so that all 32 lanes stay busy on short A-columns.
+template <class mult_t, bool NEED_MULT, class F>
+__device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult, F &&f) {
+  const int lane = lane_id();
+  unsigned longmask = __ballot_sync(0xFFFFFFFFu, len >= kWarpLong);
+  while (longmask) {
+    int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    int64_t b = __shfl_sync(0xFFFFFFFFu, beg, src);
+    int l = __shfl_sync(0xFFFFFFFFu, len, src);
+    mult_t mu = mult_t();
+    if (NEED_MULT) mu = shfl_mult<mult_t>(mult, src);
+    for (int i = lane; i < l; i += 32) f(b + i, mu);
+  }
+  int slen = (len >= kWarpLong) ? 0 : len;
+  int incl = slen;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int excl = incl - slen;
+  int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    int t = t0 + lane;
+    int idx = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      int e = __shfl_sync(0xFFFFFFFFu, excl, idx + step);
+      if (e <= t) idx += step;
+    }
+    int e0 = __shfl_sync(0xFFFFFFFFu, excl, idx);
+    int64_t b = __shfl_sync(0xFFFFFFFFu, beg, idx);
+    mult_t mu = mult_t();
+    if (NEED_MULT) mu = shfl_mult<mult_t>(mult, idx);
+    if (t < total) f(b + (t - e0), mu);
+  }
+}
+
+// One warp walks all segments of a task, 32 at a time (small tasks: one task per warp).
 template <class SR, bool MERGE, bool NEED_MULT, class F>
-__device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task &k, int warp_in_group, int group_warps,
-                                          CtaQueue *q, F &&f) {
+__device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task &k, F &&f) {
   typedef typename SR::b_t mult_t;
   const int lane = lane_id();
-  for (int64_t base = k.seg_begin + (int64_t)warp_in_group * 32; base < k.seg_end; base += (int64_t)group_warps * 32) {
+  for (int64_t base = k.seg_begin; base < k.seg_end; base += 32) {
     int64_t p = base + lane;
     int64_t beg = 0;
     int len = 0;
     mult_t mult = mult_t();
     if (p < k.seg_end) load_segment<SR, MERGE, NEED_MULT>(s, k, p, beg, len, mult);
-    if (q != nullptr && len >= kCtaLong) {
-      int qi = atomicAdd(&q->n, 1);
-      if (qi < kQueueCap) {
-        q->len[qi] = len;
-        q->beg[qi] = beg;
-        if (NEED_MULT) q->mult[qi] = mult_bits<mult_t>(mult);
-        len = 0;
-      }
-    }
-    // long segments: whole warp, coalesced
-    unsigned longmask = __ballot_sync(0xFFFFFFFFu, len >= kWarpLong);
-    while (longmask) {
-      int src = __ffs(longmask) - 1;
-      longmask &= longmask - 1;
-      int64_t b = __shfl_sync(0xFFFFFFFFu, beg, src);
-      int l = __shfl_sync(0xFFFFFFFFu, len, src);
-      mult_t mu = mult_t();
-      if (NEED_MULT) mu = shfl_mult<mult_t>(mult, src);
-      for (int i = lane; i < l; i += 32) f(b + i, mu);
-    }
-    // short segments: flatten over the warp
-    int slen = (len >= kWarpLong) ? 0 : len;
-    int incl = slen;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    int excl = incl - slen;
-    int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      int t = t0 + lane;
-      int idx = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        int e = __shfl_sync(0xFFFFFFFFu, excl, idx + step);
-        if (e <= t) idx += step;
-      }
-      int e0 = __shfl_sync(0xFFFFFFFFu, excl, idx);
-      int64_t b = __shfl_sync(0xFFFFFFFFu, beg, idx);
-      mult_t mu = mult_t();
-      if (NEED_MULT) mu = shfl_mult<mult_t>(mult, idx);
-      if (t < total) f(b + (t - e0), mu);
-    }
+    warp_process32<mult_t, NEED_MULT>(beg, len, mult, f);
   }
 }
 
-// whole-CTA walk = per-warp walk + cooperative pass over the queued very long segments. All threads must call.
+// Whole-CTA walk with equal shares of PRODUCTS per warp: the CTA stages a chunk of segments in shared memory with the
+// running sum of their lengths; warp w then owns products [w*P/nw, (w+1)*P/nw) of the chunk, wherever the segment
+// boundaries fall, so one very long A-column can no longer stall the other warps at the barrier. All threads must call.
 template <class SR, bool MERGE, bool NEED_MULT, class F>
 __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueue *q, F &&f) {
   typedef typename SR::b_t mult_t;
-  if (threadIdx.x == 0) q->n = 0;
-  __syncthreads();
-  warp_walk<SR, MERGE, NEED_MULT>(s, k, threadIdx.x >> 5, blockDim.x >> 5, q, f);
-  __syncthreads();
-  int nq = min(q->n, kQueueCap);
-  for (int e = 0; e < nq; ++e) {
-    int64_t b = q->beg[e];
-    int l = q->len[e];
-    mult_t mu = mult_t();
-    if (NEED_MULT) mu = bits_mult<mult_t>(q->mult[e]);
-    for (int i = threadIdx.x; i < l; i += blockDim.x) f(b + i, mu);
+  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int CH = min((int)blockDim.x, kWalkChunk);
+  for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
+    __syncthreads(); // previous chunk fully consumed
+    const int nseg = (int)min((int64_t)CH, k.seg_end - cbase);
+    int64_t beg = 0;
+    int len = 0;
+    mult_t mult = mult_t();
+    if ((int)threadIdx.x < nseg) load_segment<SR, MERGE, NEED_MULT>(s, k, cbase + threadIdx.x, beg, len, mult);
+    // block-wide exclusive scan of len (64-bit)
+    long long incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      long long v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) q->warp_sums[warp] = incl;
+    __syncthreads();
+    long long woff = 0, total = 0;
+    for (int w = 0; w < nwarp; ++w) {
+      long long v = q->warp_sums[w];
+      if (w < warp) woff += v;
+      total += v;
+    }
+    if ((int)threadIdx.x < CH) {
+      q->pre[threadIdx.x] = woff + incl - len;
+      q->beg[threadIdx.x] = beg;
+      if (NEED_MULT) q->mult[threadIdx.x] = mult_bits<mult_t>(mult);
+    }
+    if (threadIdx.x == 0) q->pre[CH] = total;
+    __syncthreads();
+    if (total == 0) continue;
+    const long long lo = total * warp / nwarp, hi = total * (warp + 1) / nwarp;
+    if (hi <= lo) continue;
+    // first segment whose range contains product `lo`: largest i with pre[i] <= lo
+    int a = 0, b = nseg - 1;
+    while (a < b) {
+      int mid = (a + b + 1) >> 1;
+      if (q->pre[mid] <= lo) a = mid;
+      else b = mid - 1;
+    }
+    for (int sb = a; sb < nseg; sb += 32) {
+      if (q->pre[sb] >= hi) break; // warp-uniform
+      int si = sb + lane;
+      int64_t mybeg = 0;
+      int mylen = 0;
+      mult_t mymult = mult_t();
+      if (si < nseg) {
+        long long pb = q->pre[si], pe = (si + 1 < nseg) ? q->pre[si + 1] : total;
+        long long x = pb > lo ? pb : lo, y = pe < hi ? pe : hi;
+        if (y > x) {
+          mybeg = q->beg[si] + (x - pb);
+          mylen = (int)(y - x);
+          if (NEED_MULT) mymult = bits_mult<mult_t>(q->mult[si]);
+        }
+      }
+      warp_process32<mult_t, NEED_MULT>(mybeg, mylen, mymult, f);
+    }
   }
   __syncthreads();
 }
@@ -273,7 +318,7 @@ sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_
   constexpr int GT = GROUP_WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned *keys_all = reinterpret_cast<unsigned *>(smem_raw);
-  __shared__ CtaQueue queue;
+  __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueue>::type queue;
   __shared__ int cta_count;
   const int group = GROUP_WARPS == 1 ? (threadIdx.x >> 5) : 0;
   const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
@@ -293,8 +338,8 @@ sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_
     table_insert<LOG2T>(keys, (unsigned)s.Air[pos], fresh);
     mine += fresh ? 1 : 0;
   };
-  if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, 0, 1, nullptr, f);
-  else cta_walk<SR, MERGE, false>(s, k, &queue, f);
+  if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, f);
+  else cta_walk<SR, MERGE, false>(s, k, reinterpret_cast<CtaQueue *>(&queue), f);
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
   if (GROUP_WARPS == 1) {
@@ -342,7 +387,7 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   acc_t *acc_all = reinterpret_cast<acc_t *>(sort_all + GROUPS * T);
   unsigned *keys_all = reinterpret_cast<unsigned *>(acc_all + GROUPS * T);
   int *cnt_all = reinterpret_cast<int *>(keys_all + GROUPS * T);
-  __shared__ CtaQueue queue;
+  __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueue>::type queue;
   const int group = GROUP_WARPS == 1 ? (threadIdx.x >> 5) : 0;
   const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
   int64_t ti = (int64_t)blockIdx.x * GROUPS + group;
@@ -369,10 +414,10 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
     SR::accumulate(&acc[slot], v);
   };
   if (GROUP_WARPS == 1) {
-    warp_walk<SR, MERGE, true>(s, k, 0, 1, nullptr, f);
+    warp_walk<SR, MERGE, true>(s, k, f);
     __syncwarp();
   } else {
-    cta_walk<SR, MERGE, true>(s, k, &queue, f);
+    cta_walk<SR, MERGE, true>(s, k, reinterpret_cast<CtaQueue *>(&queue), f);
   }
   // compact the occupied slots
   for (int i = gtid; i < T; i += GT) {

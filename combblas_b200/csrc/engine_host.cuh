@@ -14,9 +14,22 @@ __device__ __forceinline__ int size_bucket(int64_t v) {
   return b > 39 ? 39 : b;
 }
 
-static __global__ void sym_bucket_kernel(const int64_t *flop, int64_t ntask, uint8_t *bucket) {
+// symbolic path choice per task: bucket = size bucket of the products (+0 hash, +40 bitmap)
+static __global__ void sym_bucket_kernel(const int64_t *flop, const uint32_t *task_win, int nwin, int64_t ntask,
+                                         int64_t bitmap_min_flop, int force_path, uint8_t *bucket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ntask) bucket[i] = (uint8_t)size_bucket(flop[i]);
+  if (i >= ntask) return;
+  int64_t v = flop[i];
+  int sb = size_bucket(v);
+  bool can_bitmap = true;
+  if (nwin > 1 && task_win) {
+    unsigned w = task_win[i];
+    can_bitmap = ((w >> 16) - (w & 0xFFFFu)) == 1;
+  }
+  bool use_bitmap = can_bitmap && (v >= bitmap_min_flop || v > 2048);
+  if (force_path == 1 && v <= 2048) use_bitmap = false;
+  if (force_path == 2 && can_bitmap) use_bitmap = true;
+  bucket[i] = (uint8_t)((sb == 0 || !use_bitmap) ? sb : sb + 40);
 }
 
 // numeric path choice per task: bucket = size bucket (+0 hash, +40 bitmap/shared accumulators, +80 bitmap/HBM accumulators)
@@ -70,7 +83,8 @@ static __global__ void gather_ptr_kernel(const int64_t *taskptr, const int64_t *
 
 template <class K>
 inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) CB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // static + dynamic shared memory above 48 KiB needs the opt-in; the kernels here also carry static workspaces
+  if (bytes > 16 * 1024) CB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return CBGPU_OK;
 }
 
@@ -176,7 +190,9 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   memset(&bins, 0, sizeof(bins));
   if (ntask > 0) {
     CB_CUDA(ctx, cudaMemsetAsync(tasknnz, 0, sizeof(int64_t) * (size_t)ntask, st));
-    sym_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(taskflop, ntask, bucket);
+    int64_t sym_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 256, 64), 2048);
+    sym_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(taskflop, task_win, nwin, ntask, sym_min,
+                                                                      (int)opt.force_path, bucket);
     CB_LAUNCH_CHECK(ctx);
     CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, order, &bins));
   }
@@ -188,26 +204,24 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   const size_t bm_bytes = (size_t)max_cells * 8;
   {
     int64_t beg, cnt;
-    bucket_range(bins, 16, 39, &beg, &cnt);
-    if (cnt > 0) {
+    // bitmap: large tasks (more than 8192 products) by 512 threads, the rest by 128 threads
+    bucket_range(bins, 55, 79, &beg, &cnt);
+    int64_t beg2, cnt2;
+    bucket_range(bins, 41, 54, &beg2, &cnt2);
+    if (cnt + cnt2 > 0) {
       auto kern = sym_bitmap_kernel<SR, MERGE>;
       CB_TRY(optin_smem(ctx, kern, bm_bytes));
       CB_KBEGIN(CBGPU_K_SYM_BITMAP);
-      kern<<<(unsigned)cnt, kBitmapThreads, bm_bytes, st>>>(src, order + beg, cnt, io.m, tasknnz);
-      CB_LAUNCH_CHECK(ctx);
+      if (cnt > 0) {
+        kern<<<(unsigned)cnt, kBitmapThreads, bm_bytes, st>>>(src, order + beg, cnt, io.m, tasknnz);
+        CB_LAUNCH_CHECK(ctx);
+      }
+      if (cnt2 > 0) {
+        kern<<<(unsigned)cnt2, 128, bm_bytes, st>>>(src, order + beg2, cnt2, io.m, tasknnz);
+        CB_LAUNCH_CHECK(ctx);
+      }
       CB_KEND(CBGPU_K_SYM_BITMAP);
-      for (int b = 16; b <= 39; ++b) stats.flops_sym[0] += bins.weight[b];
-    }
-    bucket_range(bins, 13, 15, &beg, &cnt);
-    if (cnt > 0) {
-      auto kern = sym_hash_kernel<SR, MERGE, 16, 15>;
-      size_t sm = sizeof(unsigned) << 15;
-      CB_TRY(optin_smem(ctx, kern, sm));
-      CB_KBEGIN(CBGPU_K_SYM_HASH_CTA_L);
-      kern<<<(unsigned)cnt, 512, sm, st>>>(src, order + beg, cnt, tasknnz);
-      CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_SYM_HASH_CTA_L);
-      for (int b = 13; b <= 15; ++b) stats.flops_sym[1] += bins.weight[b];
+      for (int b = 41; b <= 79; ++b) stats.flops_sym[0] += bins.weight[b];
     }
     bucket_range(bins, 10, 12, &beg, &cnt);
     if (cnt > 0) {
@@ -281,18 +295,29 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       stats.tasks_bitmap_gmem = cnt;
       for (int b = 81; b <= 119; ++b) { stats.flops_bitmap_gmem += nb.weight[b]; stats.nnz_bitmap_gmem += nb.weight2[b]; }
     }
-    // bitmap, accumulators in shared memory
-    bucket_range(nb, 41, 79, &beg, &cnt);
-    if (cnt > 0) {
-      auto kern = num_bitmap_kernel<SR, MERGE, false>;
-      size_t sm = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)opt.bitmap_smem_acc * sizeof(acc_t);
-      CB_TRY(optin_smem(ctx, kern, sm));
-      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
-      kern<<<(unsigned)cnt, kBitmapThreads, sm, st>>>(src, order + beg, cnt, io.m, max_cells, taskptr, Cm->ir, Cval);
-      CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
-      stats.tasks_bitmap_smem = cnt;
-      for (int b = 41; b <= 79; ++b) { stats.flops_bitmap_smem += nb.weight[b]; stats.nnz_bitmap_smem += nb.weight2[b]; }
+    // bitmap, accumulators in shared memory: more than 2048 outputs by 512 threads, the rest by 128 threads
+    {
+      int64_t begL, cntL, begS, cntS;
+      bucket_range(nb, 53, 79, &begL, &cntL);
+      bucket_range(nb, 41, 52, &begS, &cntS);
+      if (cntL + cntS > 0) {
+        auto kern = num_bitmap_kernel<SR, MERGE, false>;
+        size_t smL = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)opt.bitmap_smem_acc * sizeof(acc_t);
+        size_t smS = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)2048 * sizeof(acc_t);
+        CB_TRY(optin_smem(ctx, kern, std::max(smL, smS)));
+        CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
+        if (cntL > 0) {
+          kern<<<(unsigned)cntL, kBitmapThreads, smL, st>>>(src, order + begL, cntL, io.m, max_cells, taskptr, Cm->ir, Cval);
+          CB_LAUNCH_CHECK(ctx);
+        }
+        if (cntS > 0) {
+          kern<<<(unsigned)cntS, 128, smS, st>>>(src, order + begS, cntS, io.m, max_cells, taskptr, Cm->ir, Cval);
+          CB_LAUNCH_CHECK(ctx);
+        }
+        CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
+        stats.tasks_bitmap_smem = cntL + cntS;
+        for (int b = 41; b <= 79; ++b) { stats.flops_bitmap_smem += nb.weight[b]; stats.nnz_bitmap_smem += nb.weight2[b]; }
+      }
     }
     // hash per CTA: 257..2048 outputs
     bucket_range(nb, 10, 39, &beg, &cnt);

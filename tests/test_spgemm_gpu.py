@@ -74,7 +74,7 @@ def test_rmat_scale14_all_paths(ctx, oracle):
     A = rmat(14, 16, seed=2)
     want = oracle.spgemm(to_csc(A, np.float64), to_csc(A, np.float64), 0)
     dA = ctx.upload(to_dcsc(A, np.float64))
-    for force, smem_acc in ((0, 12288), (1, 12288), (2, 12288), (0, 256), (2, 256)):
+    for force, smem_acc in ((0, 2048), (1, 2048), (2, 8192), (0, 256), (2, 256)):
         ctx.set_option("force_path", force)
         ctx.set_option("bitmap_smem_acc", smem_acc)
         D, st = ctx.spgemm(0, dA, dA, want_stats=True)
@@ -89,7 +89,7 @@ def test_rmat_scale14_all_paths(ctx, oracle):
             assert st.tasks_bitmap_gmem > 0
         D.free()
     ctx.set_option("force_path", 0)
-    ctx.set_option("bitmap_smem_acc", 12288)
+    ctx.set_option("bitmap_smem_acc", 2048)
     dA.free()
 
 
@@ -103,7 +103,7 @@ def test_row_windows(ctx, oracle, wlog2, sr):
         B = rmat(13, 8, seed=4)
         check_pair(ctx, oracle, sr, typed(A, SR_DTYPES[sr][0]), typed(B, SR_DTYPES[sr][1]))
     finally:
-        ctx.set_option("bitmap_window_log2", 19)
+        ctx.set_option("bitmap_window_log2", 17)
 
 
 def test_tall_matrix_natural_windows(ctx, oracle):
@@ -189,11 +189,11 @@ def test_merge_large_columns_and_windows(ctx, port_oracle):
     a = to_csc(A, np.float64)
     parts = [port_oracle.spgemm(a, to_csc(rmat(13, 4, seed=20 + i), np.float64), 0) for i in range(3)]
     want = port_oracle.merge(parts, 0)
-    for wlog2 in (19, 11):
+    for wlog2 in (17, 11):
         ctx.set_option("bitmap_window_log2", wlog2)
         got = cb.MultiwayMerge(ctx, 0, [dcsc_of(p) for p in parts])
         assert_same(got, want, 0)
-    ctx.set_option("bitmap_window_log2", 19)
+    ctx.set_option("bitmap_window_log2", 17)
 
 
 def test_colsplit_concat_and_checksum(ctx):
