@@ -357,6 +357,7 @@ int cbgpu_create(int device, void *stream, cbgpu_ctx **out) {
 int cbgpu_destroy(cbgpu_ctx *ctx) {
   if (!ctx) return CBGPU_OK;
   cudaSetDevice(ctx->device);
+  release_cached_blocks(ctx);
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2 * CBGPU_K_COUNT; ++i) if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);

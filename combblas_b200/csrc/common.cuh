@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/cbgpu.h"
@@ -43,6 +44,11 @@ struct cbgpu_ctx {
   int max_smem_optin = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[2 * CBGPU_K_COUNT] = {};
+  // large-block cache in front of the stream-ordered pool: result arrays of tens of GB are recycled between
+  // multiplies (and between the column slabs of a phased multiply) without going back to the driver
+  std::map<void *, size_t> big_live;              // live large blocks -> size
+  std::multimap<size_t, void *> big_free;         // cached large blocks by size
+  size_t big_free_bytes = 0;
 };
 
 struct cbgpu_mat {
@@ -97,6 +103,7 @@ int set_error(cbgpu_ctx_impl *ctx, int code, const char *fmt, ...);
 // stream-ordered allocation helpers (cudaMallocAsync pool; no implicit device sync)
 int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes);
 int dev_free(cbgpu_ctx_impl *ctx, void *p);
+void release_cached_blocks(cbgpu_ctx_impl *ctx);
 template <class T>
 inline int dev_alloc_t(cbgpu_ctx_impl *ctx, T **p, size_t count) {
   return dev_alloc(ctx, reinterpret_cast<void **>(p), count * sizeof(T));

@@ -17,23 +17,59 @@ int set_error(cbgpu_ctx_impl *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
+constexpr size_t kBigBlock = (size_t)64 << 20; // blocks from 64 MiB are cached by the context
+
+static void flush_big_cache(cbgpu_ctx_impl *ctx) {
+  for (auto &kv : ctx->big_free) cudaFreeAsync(kv.second, ctx->stream);
+  ctx->big_free.clear();
+  ctx->big_free_bytes = 0;
+}
+
 int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
+  if (bytes >= kBigBlock) {
+    // smallest cached block that fits and wastes at most a quarter
+    auto it = ctx->big_free.lower_bound(bytes);
+    if (it != ctx->big_free.end() && it->first <= bytes + bytes / 4) {
+      *p = it->second;
+      ctx->big_live[*p] = it->first;
+      ctx->big_free_bytes -= it->first;
+      ctx->big_free.erase(it);
+      return CBGPU_OK;
+    }
+  }
   cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess && !ctx->big_free.empty()) { // give the cached blocks back and try once more
+    cudaGetLastError();
+    flush_big_cache(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaMallocAsync(p, bytes, ctx->stream);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(ctx, e == cudaErrorMemoryAllocation ? CBGPU_ERR_NOMEM : CBGPU_ERR_CUDA,
                      "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
   }
+  if (bytes >= kBigBlock) ctx->big_live[*p] = bytes;
   return CBGPU_OK;
 }
 
 int dev_free(cbgpu_ctx_impl *ctx, void *p) {
   if (!p) return CBGPU_OK;
+  auto it = ctx->big_live.find(p);
+  if (it != ctx->big_live.end()) {
+    // stream order makes the reuse safe: every consumer of this block was enqueued on ctx->stream before now
+    ctx->big_free.emplace(it->second, p);
+    ctx->big_free_bytes += it->second;
+    ctx->big_live.erase(it);
+    return CBGPU_OK;
+  }
   CB_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
   return CBGPU_OK;
 }
+
+void release_cached_blocks(cbgpu_ctx_impl *ctx) { flush_big_cache(ctx); }
 
 // ------------------------------------------------------------------------------------------------ scan
 // three-phase exclusive scan of int64: per-tile sums, scan of the sums by one block, per-tile scan + offset
