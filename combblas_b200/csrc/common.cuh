@@ -59,6 +59,11 @@ struct cbgpu_mat {
   int32_t *ir = nullptr;     // [nnz]
   void *numx = nullptr;      // [nnz]
   int64_t *colptr = nullptr; // [n+1] dense column index, built on demand (replaces Dcsc::ConstructAux/FillColInds)
+  // window-major copy for use as the A operand (built on demand, keyed by the window size)
+  int win_log2 = 0, win_nwin = 0;
+  int64_t *win_T2 = nullptr; // [nwin*n + 1]
+  int32_t *win_ir = nullptr; // [nnz]
+  void *win_val = nullptr;   // [nnz]
   int device = 0;
 };
 
@@ -113,6 +118,7 @@ inline int dev_alloc_t(cbgpu_ctx_impl *ctx, T **p, size_t count) {
 int exclusive_scan_i64(cbgpu_ctx_impl *ctx, const int64_t *in, int64_t *out, int64_t n); // out has n+1 entries
 int fill_i64(cbgpu_ctx_impl *ctx, int64_t *p, int64_t n, int64_t v);
 int ensure_dense_colptr(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M);
+int ensure_window_major(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M, int nwin, int wlog2);
 int mat_alloc(cbgpu_ctx_impl *ctx, int64_t m, int64_t n, int64_t nnz, int64_t nzc, int dtype, cbgpu_mat_impl **out);
 int mat_release(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M);
 // builds DCSC (jc, cp) of the non-empty columns from per-column counts over `ncols_in` candidate columns

@@ -34,11 +34,17 @@ template <class SR, bool MERGE>
 struct Source {
   typedef typename std::conditional<MERGE, typename SR::out_t, typename SR::a_t>::type aval_t;
   typedef typename SR::b_t mult_t;
-  const int64_t *T;   // segment table, stride nwin
+  const int64_t *T;   // dense column pointers of A (or of the concatenated merge lists): whole columns
   int nwin;
   int wlog2;
   const int32_t *Air;
   const aval_t *Aval;
+  // window-major copy of A (nwin > 1): piece (window w, column c) is [T2[w*N+c], T2[w*N+c+1]) of Wir/Wval, so that all
+  // tasks of one row window gather from one contiguous, L2-sized slice instead of striding through every column of A
+  const int64_t *T2;
+  int64_t N;
+  const int32_t *Wir;
+  const aval_t *Wval;
   // multiply
   const int64_t *Bcp;
   const int32_t *Bir;
@@ -53,8 +59,10 @@ struct Source {
 
 struct Task {
   int col;      // multiply: index into B's non-empty columns; merge: column id
-  int wlo, whi; // row windows [wlo, whi)
+  int wlo, whi; // row windows [wlo, whi): either one window or all of them
   int64_t seg_begin, seg_end;
+  const int32_t *rows; // where this task's segments live: A itself (all rows) or its window-major copy
+  const void *vals;
 };
 
 template <class Src>
@@ -82,6 +90,9 @@ __device__ __forceinline__ void task_segments(const Source<SR, MERGE> &s, Task &
     k.seg_begin = s.Bcp[k.col];
     k.seg_end = s.Bcp[k.col + 1];
   }
+  const bool whole = (k.whi - k.wlo) == s.nwin;
+  k.rows = whole ? s.Air : s.Wir;
+  k.vals = whole ? (const void *)s.Aval : (const void *)s.Wval;
 }
 
 // segment p of task k: [beg, beg+len) in Air/Aval, with its multiplier
@@ -95,9 +106,14 @@ __device__ __forceinline__ void load_segment(const Source<SR, MERGE> &s, const T
     col = s.Bir[p];
     if (NEED_MULT) mult = s.Bval[p];
   }
-  const int64_t *t = s.T + col * s.nwin;
-  beg = t[k.wlo];
-  len = (int)(t[k.whi] - beg);
+  if ((k.whi - k.wlo) == s.nwin) {
+    beg = s.T[col];
+    len = (int)(s.T[col + 1] - beg);
+  } else {
+    const int64_t *t = s.T2 + (int64_t)k.wlo * s.N + col;
+    beg = t[0];
+    len = (int)(t[1] - beg);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ product walk
@@ -335,7 +351,7 @@ sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_
   int mine = 0;
   auto f = [&](int64_t pos, typename SR::b_t) {
     bool fresh;
-    table_insert<LOG2T>(keys, (unsigned)s.Air[pos], fresh);
+    table_insert<LOG2T>(keys, (unsigned)k.rows[pos], fresh);
     mine += fresh ? 1 : 0;
   };
   if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, f);
@@ -407,10 +423,10 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   task_segments(s, k);
   auto f = [&](int64_t pos, typename SR::b_t mu) {
     bool fresh;
-    int slot = table_insert<LOG2T>(keys, (unsigned)s.Air[pos], fresh);
+    int slot = table_insert<LOG2T>(keys, (unsigned)k.rows[pos], fresh);
     acc_t v;
-    if (MERGE) v = SR::from_out((typename SR::out_t)s.Aval[pos]);
-    else v = SR::mul((typename SR::a_t)s.Aval[pos], mu);
+    if (MERGE) v = SR::from_out(((const typename SR::out_t *)k.vals)[pos]);
+    else v = SR::mul(((const typename SR::a_t *)k.vals)[pos], mu);
     SR::accumulate(&acc[slot], v);
   };
   if (GROUP_WARPS == 1) {
@@ -476,7 +492,7 @@ __device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Ta
   const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) bm4[i] = make_uint4(0, 0, 0, 0);
   auto f = [&](int64_t pos, typename SR::b_t) {
-    unsigned r = (unsigned)(s.Air[pos] - rbase);
+    unsigned r = (unsigned)(k.rows[pos] - rbase);
     atomicOr(&bm[r >> 5], 1u << (r & 31));
   };
   cta_walk<SR, MERGE, false>(s, k, q, f); // starts and ends with __syncthreads
@@ -562,15 +578,15 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   }
   __syncthreads();
   auto f = [&](int64_t pos, typename SR::b_t mu) {
-    unsigned r = (unsigned)(s.Air[pos] - rbase);
+    unsigned r = (unsigned)(k.rows[pos] - rbase);
     unsigned cell = r >> 6, bit = r & 63;
     uint2 w = reinterpret_cast<const uint2 *>(bm)[cell];
     unsigned rank = pre[cell];
     if (bit >= 32) rank += __popc(w.x) + __popc(w.y & ((1u << (bit - 32)) - 1u));
     else rank += __popc(w.x & ((1u << bit) - 1u));
     acc_t v;
-    if (MERGE) v = SR::from_out((out_t)s.Aval[pos]);
-    else v = SR::mul((typename SR::a_t)s.Aval[pos], mu);
+    if (MERGE) v = SR::from_out(((const out_t *)k.vals)[pos]);
+    else v = SR::mul(((const typename SR::a_t *)k.vals)[pos], mu);
     if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
     else SR::accumulate(&acc[rank], v);
   };

@@ -1,4 +1,4 @@
-// Host-side orchestration of the accumulation engine (engine.cuh): task construction, size binning,
+// Host-side orchestration of the accumulation engine (engine.cuh): task construction, size/window ordering,
 // symbolic pass, scan, numeric pass, DCSC assembly. Instantiated once per semiring (sr_instance.cu).
 #pragma once
 #include <algorithm>
@@ -14,6 +14,12 @@ __device__ __forceinline__ int size_bucket(int64_t v) {
   return b > 39 ? 39 : b;
 }
 
+__device__ __forceinline__ bool task_is_one_window(const uint32_t *task_win, int nwin, int64_t i) {
+  if (nwin <= 1 || !task_win) return true;
+  unsigned w = task_win[i];
+  return ((w >> 16) - (w & 0xFFFFu)) == 1;
+}
+
 // symbolic path choice per task: bucket = size bucket of the products (+0 hash, +40 bitmap)
 static __global__ void sym_bucket_kernel(const int64_t *flop, const uint32_t *task_win, int nwin, int64_t ntask,
                                          int64_t bitmap_min_flop, int force_path, uint8_t *bucket) {
@@ -21,21 +27,18 @@ static __global__ void sym_bucket_kernel(const int64_t *flop, const uint32_t *ta
   if (i >= ntask) return;
   int64_t v = flop[i];
   int sb = size_bucket(v);
-  bool can_bitmap = true;
-  if (nwin > 1 && task_win) {
-    unsigned w = task_win[i];
-    can_bitmap = ((w >> 16) - (w & 0xFFFFu)) == 1;
-  }
+  bool can_bitmap = task_is_one_window(task_win, nwin, i);
   bool use_bitmap = can_bitmap && (v >= bitmap_min_flop || v > 2048);
   if (force_path == 1 && v <= 2048) use_bitmap = false;
   if (force_path == 2 && can_bitmap) use_bitmap = true;
   bucket[i] = (uint8_t)((sb == 0 || !use_bitmap) ? sb : sb + 40);
 }
 
-// numeric path choice per task: bucket = size bucket (+0 hash, +40 bitmap/shared accumulators, +80 bitmap/HBM accumulators)
+// numeric path choice per task: bucket = size bucket of the outputs (+0 hash, +40 bitmap/shared accumulators,
+// +80 bitmap/accumulators in C itself)
 static __global__ void num_bucket_kernel(const int64_t *nnz, const uint32_t *task_win, int nwin, int64_t ntask,
-                                  int64_t bitmap_min_nnz, int64_t hash_max_nnz, int64_t smem_acc_max, int force_path,
-                                  uint8_t *bucket) {
+                                         int64_t bitmap_min_nnz, int64_t hash_max_nnz, int64_t smem_acc_max, int force_path,
+                                         uint8_t *bucket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntask) return;
   int64_t v = nnz[i];
@@ -44,11 +47,7 @@ static __global__ void num_bucket_kernel(const int64_t *nnz, const uint32_t *tas
     bucket[i] = 0;
     return;
   }
-  bool can_bitmap = true;
-  if (nwin > 1 && task_win) {
-    unsigned w = task_win[i];
-    can_bitmap = ((w >> 16) - (w & 0xFFFFu)) == 1;
-  }
+  bool can_bitmap = task_is_one_window(task_win, nwin, i);
   bool use_bitmap = can_bitmap && (v >= bitmap_min_nnz || v > hash_max_nnz);
   if (force_path == 1 && v <= hash_max_nnz) use_bitmap = false;
   if (force_path == 2 && can_bitmap) use_bitmap = true;
@@ -91,6 +90,16 @@ inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
 #define CB_KBEGIN(id) do { used[id] = true; cudaEventRecord(ctx->kev[2 * (id)], st); } while (0)
 #define CB_KEND(id) cudaEventRecord(ctx->kev[2 * (id) + 1], st)
 
+// row windows of an m-row block under the context's options
+inline void engine_windows(const cbgpu_ctx_impl *ctx, int64_t m, int *nwin, int *wlog2) {
+  int wl = (int)ctx->opt.bitmap_window_log2;
+  if (wl < 10) wl = 10;
+  if (wl > 19) wl = 19;
+  const int64_t W = (int64_t)1 << wl;
+  *wlog2 = wl;
+  *nwin = (int)std::max<int64_t>(1, (m + W - 1) / W);
+}
+
 struct EngineIO {
   // A side (or the concatenated merge lists)
   const int64_t *Acolptr;
@@ -107,6 +116,11 @@ struct EngineIO {
   int64_t *flops_out, *nnz_out;
 };
 
+// symbolic kernel classes (launch order) and numeric kernel classes
+enum { SYM_BM_L = 0, SYM_BM_S = 1, SYM_H_CTA = 2, SYM_H_WARP = 3, SYM_H_WARP_S = 4 };
+enum { NUM_BM_G = 0, NUM_BM_L = 1, NUM_BM_S = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_S = 5 };
+
+// src must arrive with Air/Aval (whole columns) and, when the block has several row windows, T2/Wir/Wval set.
 template <class SR, bool MERGE>
 int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   typedef typename SR::acc_t acc_t;
@@ -123,23 +137,14 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   if (ncol >= (int64_t)1 << 31 || io.m >= ((int64_t)1 << 31) - 1)
     return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "local dimensions must stay below 2^31 (m=%lld, columns=%lld)",
                      (long long)io.m, (long long)ncol);
-
-  // ---- row windows
-  int wlog2 = (int)opt.bitmap_window_log2;
-  if (wlog2 < 10) wlog2 = 10;
-  if (wlog2 > 19) wlog2 = 19;
-  const int64_t W = (int64_t)1 << wlog2;
-  const int nwin = (int)std::max<int64_t>(1, (io.m + W - 1) / W);
+  int nwin, wlog2;
+  engine_windows(ctx, io.m, &nwin, &wlog2);
   if (nwin > 65535) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many row windows (%d)", nwin);
-  int64_t *Ttab = nullptr;
-  if (nwin == 1) {
-    src.T = io.Acolptr;
-  } else {
-    CB_TRY(build_window_table(ctx, io.Acolptr, src.Air, io.ncolA, nwin, wlog2, &Ttab));
-    src.T = Ttab;
-  }
+  const int64_t W = (int64_t)1 << wlog2;
+  src.T = io.Acolptr;
   src.nwin = nwin;
   src.wlog2 = wlog2;
+  src.N = io.ncolA;
   src.task_col = nullptr;
   src.task_win = nullptr;
 
@@ -178,7 +183,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   }
   stats.tasks = ntask;
 
-  // ---- symbolic binning
+  // ---- symbolic ordering
   uint8_t *bucket = nullptr;
   int32_t *order = nullptr;
   int64_t *tasknnz = nullptr, *taskptr = nullptr;
@@ -187,72 +192,80 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   CB_TRY(dev_alloc_t(ctx, &tasknnz, (size_t)ntask + 1));
   CB_TRY(dev_alloc_t(ctx, &taskptr, (size_t)ntask + 2));
   BinResult bins;
+  ClassRanges sc;
   memset(&bins, 0, sizeof(bins));
+  memset(&sc, 0, sizeof(sc));
+  uint8_t sym_class[256];
+  for (int b = 0; b < 256; ++b) {
+    uint8_t c = 15;
+    if (b >= 1 && b <= 6) c = SYM_H_WARP_S;
+    else if (b >= 7 && b <= 9) c = SYM_H_WARP;
+    else if (b >= 10 && b <= 39) c = SYM_H_CTA;
+    else if (b >= 41 && b <= 54) c = SYM_BM_S;
+    else if (b >= 55 && b <= 79) c = SYM_BM_L;
+    sym_class[b] = c;
+  }
   if (ntask > 0) {
     CB_CUDA(ctx, cudaMemsetAsync(tasknnz, 0, sizeof(int64_t) * (size_t)ntask, st));
     int64_t sym_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 256, 64), 2048);
     sym_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(taskflop, task_win, nwin, ntask, sym_min,
                                                                       (int)opt.force_path, bucket);
     CB_LAUNCH_CHECK(ctx);
-    CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, order, &bins));
+    CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, task_win, sym_class, order, &bins, &sc));
   }
   for (int b = 1; b < 256; ++b) stats.flops += bins.weight[b];
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
 
-  // ---- K2: symbolic kernels, largest tasks first
+  // ---- K2: symbolic kernels
   const int max_cells = (int)((std::min<int64_t>(io.m, W) + 63) / 64 + 1) & ~1; // even, covers the uint4 clear
   const size_t bm_bytes = (size_t)max_cells * 8;
-  {
-    int64_t beg, cnt;
-    // bitmap: large tasks (more than 8192 products) by 512 threads, the rest by 128 threads
-    bucket_range(bins, 55, 79, &beg, &cnt);
-    int64_t beg2, cnt2;
-    bucket_range(bins, 41, 54, &beg2, &cnt2);
-    if (cnt + cnt2 > 0) {
-      auto kern = sym_bitmap_kernel<SR, MERGE>;
-      CB_TRY(optin_smem(ctx, kern, bm_bytes));
-      CB_KBEGIN(CBGPU_K_SYM_BITMAP);
-      if (cnt > 0) {
-        kern<<<(unsigned)cnt, kBitmapThreads, bm_bytes, st>>>(src, order + beg, cnt, io.m, tasknnz);
-        CB_LAUNCH_CHECK(ctx);
-      }
-      if (cnt2 > 0) {
-        kern<<<(unsigned)cnt2, 128, bm_bytes, st>>>(src, order + beg2, cnt2, io.m, tasknnz);
-        CB_LAUNCH_CHECK(ctx);
-      }
-      CB_KEND(CBGPU_K_SYM_BITMAP);
-      for (int b = 41; b <= 79; ++b) stats.flops_sym[0] += bins.weight[b];
-    }
-    bucket_range(bins, 10, 12, &beg, &cnt);
-    if (cnt > 0) {
-      auto kern = sym_hash_kernel<SR, MERGE, 8, 12>;
-      size_t sm = sizeof(unsigned) << 12;
-      CB_KBEGIN(CBGPU_K_SYM_HASH_CTA);
-      kern<<<(unsigned)cnt, 256, sm, st>>>(src, order + beg, cnt, tasknnz);
+  auto class_weight = [](const BinResult &r, const uint8_t *tab, int c, bool second) {
+    int64_t s = 0;
+    for (int b = 0; b < 256; ++b)
+      if (tab[b] == c) s += second ? r.weight2[b] : r.weight[b];
+    return s;
+  };
+  if (sc.count[SYM_BM_L] + sc.count[SYM_BM_S] > 0) {
+    auto kern = sym_bitmap_kernel<SR, MERGE>;
+    CB_TRY(optin_smem(ctx, kern, bm_bytes));
+    CB_KBEGIN(CBGPU_K_SYM_BITMAP);
+    if (sc.count[SYM_BM_L] > 0) {
+      kern<<<(unsigned)sc.count[SYM_BM_L], kBitmapThreads, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
       CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_SYM_HASH_CTA);
-      for (int b = 10; b <= 12; ++b) stats.flops_sym[2] += bins.weight[b];
     }
-    bucket_range(bins, 7, 9, &beg, &cnt);
-    if (cnt > 0) {
-      auto kern = sym_hash_kernel<SR, MERGE, 1, 9>;
-      size_t sm = 8 * (sizeof(unsigned) << 9);
-      CB_KBEGIN(CBGPU_K_SYM_HASH_WARP);
-      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, tasknnz);
+    if (sc.count[SYM_BM_S] > 0) {
+      kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
       CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_SYM_HASH_WARP);
-      for (int b = 7; b <= 9; ++b) stats.flops_sym[3] += bins.weight[b];
     }
-    bucket_range(bins, 1, 6, &beg, &cnt);
-    if (cnt > 0) {
-      auto kern = sym_hash_kernel<SR, MERGE, 1, 6>;
-      size_t sm = 8 * (sizeof(unsigned) << 6);
-      CB_KBEGIN(CBGPU_K_SYM_HASH_WARP_S);
-      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, tasknnz);
-      CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_SYM_HASH_WARP_S);
-      for (int b = 1; b <= 6; ++b) stats.flops_sym[4] += bins.weight[b];
-    }
+    CB_KEND(CBGPU_K_SYM_BITMAP);
+    stats.flops_sym[0] = class_weight(bins, sym_class, SYM_BM_L, false) + class_weight(bins, sym_class, SYM_BM_S, false);
+  }
+  if (sc.count[SYM_H_CTA] > 0) {
+    auto kern = sym_hash_kernel<SR, MERGE, 8, 12>;
+    size_t sm = sizeof(unsigned) << 12;
+    CB_KBEGIN(CBGPU_K_SYM_HASH_CTA);
+    kern<<<(unsigned)sc.count[SYM_H_CTA], 256, sm, st>>>(src, order + sc.begin[SYM_H_CTA], sc.count[SYM_H_CTA], tasknnz);
+    CB_LAUNCH_CHECK(ctx);
+    CB_KEND(CBGPU_K_SYM_HASH_CTA);
+    stats.flops_sym[2] = class_weight(bins, sym_class, SYM_H_CTA, false);
+  }
+  if (sc.count[SYM_H_WARP] > 0) {
+    auto kern = sym_hash_kernel<SR, MERGE, 1, 9>;
+    size_t sm = 8 * (sizeof(unsigned) << 9);
+    CB_KBEGIN(CBGPU_K_SYM_HASH_WARP);
+    kern<<<(unsigned)((sc.count[SYM_H_WARP] + 7) / 8), 256, sm, st>>>(src, order + sc.begin[SYM_H_WARP], sc.count[SYM_H_WARP], tasknnz);
+    CB_LAUNCH_CHECK(ctx);
+    CB_KEND(CBGPU_K_SYM_HASH_WARP);
+    stats.flops_sym[3] = class_weight(bins, sym_class, SYM_H_WARP, false);
+  }
+  if (sc.count[SYM_H_WARP_S] > 0) {
+    auto kern = sym_hash_kernel<SR, MERGE, 1, 6>;
+    size_t sm = 8 * (sizeof(unsigned) << 6);
+    CB_KBEGIN(CBGPU_K_SYM_HASH_WARP_S);
+    kern<<<(unsigned)((sc.count[SYM_H_WARP_S] + 7) / 8), 256, sm, st>>>(src, order + sc.begin[SYM_H_WARP_S], sc.count[SYM_H_WARP_S], tasknnz);
+    CB_LAUNCH_CHECK(ctx);
+    CB_KEND(CBGPU_K_SYM_HASH_WARP_S);
+    stats.flops_sym[4] = class_weight(bins, sym_class, SYM_H_WARP_S, false);
   }
   // ---- K3: scan -> output offsets
   CB_TRY(exclusive_scan_i64(ctx, tasknnz, taskptr, ntask));
@@ -269,93 +282,107 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   if (io.C) {
     // ---- output block
     CB_TRY(mat_alloc(ctx, io.m, io.n_out, nnzC, -1, io.out_dtype, &Cm));
-    // ---- numeric binning by exact output size
+    // ---- numeric ordering by exact output size
     BinResult nb;
+    ClassRanges nc;
     memset(&nb, 0, sizeof(nb));
+    memset(&nc, 0, sizeof(nc));
+    uint8_t num_class[256];
+    for (int b = 0; b < 256; ++b) {
+      uint8_t c = 15;
+      if (b >= 1 && b <= 6) c = NUM_H_WARP_S;
+      else if (b >= 7 && b <= 9) c = NUM_H_WARP;
+      else if (b >= 10 && b <= 39) c = NUM_H_CTA;
+      else if (b >= 41 && b <= 52) c = NUM_BM_S;
+      else if (b >= 53 && b <= 79) c = NUM_BM_L;
+      else if (b >= 81 && b <= 119) c = NUM_BM_G;
+      num_class[b] = c;
+    }
     if (ntask > 0) {
       int64_t auto_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 2048, 32), 2048);
       int64_t bmin = opt.bitmap_min_nnz > 0 ? opt.bitmap_min_nnz : auto_min;
       num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048,
                                                                         opt.bitmap_smem_acc, (int)opt.force_path, bucket);
       CB_LAUNCH_CHECK(ctx);
-      CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, order, &nb));
+      CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, task_win, num_class, order, &nb, &nc));
     }
     out_t *Cval = reinterpret_cast<out_t *>(Cm->numx);
-    int64_t beg, cnt;
-    // bitmap, accumulators in HBM (largest tasks)
-    bucket_range(nb, 81, 119, &beg, &cnt);
-    if (cnt > 0) {
+    // bitmap, accumulators in C itself (largest tasks)
+    if (nc.count[NUM_BM_G] > 0) {
       auto kern = num_bitmap_kernel<SR, MERGE, true>;
       size_t sm = bm_bytes + (size_t)max_cells * 4 + 16;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
-      kern<<<(unsigned)cnt, kBitmapThreads, sm, st>>>(src, order + beg, cnt, io.m, max_cells, taskptr, Cm->ir, Cval);
+      kern<<<(unsigned)nc.count[NUM_BM_G], kBitmapThreads, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m,
+                                                                   max_cells, taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
-      stats.tasks_bitmap_gmem = cnt;
-      for (int b = 81; b <= 119; ++b) { stats.flops_bitmap_gmem += nb.weight[b]; stats.nnz_bitmap_gmem += nb.weight2[b]; }
+      stats.tasks_bitmap_gmem = nc.count[NUM_BM_G];
+      stats.flops_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, false);
+      stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true);
     }
     // bitmap, accumulators in shared memory: more than 2048 outputs by 512 threads, the rest by 128 threads
-    {
-      int64_t begL, cntL, begS, cntS;
-      bucket_range(nb, 53, 79, &begL, &cntL);
-      bucket_range(nb, 41, 52, &begS, &cntS);
-      if (cntL + cntS > 0) {
-        auto kern = num_bitmap_kernel<SR, MERGE, false>;
-        size_t smL = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)opt.bitmap_smem_acc * sizeof(acc_t);
-        size_t smS = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)2048 * sizeof(acc_t);
-        CB_TRY(optin_smem(ctx, kern, std::max(smL, smS)));
-        CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
-        if (cntL > 0) {
-          kern<<<(unsigned)cntL, kBitmapThreads, smL, st>>>(src, order + begL, cntL, io.m, max_cells, taskptr, Cm->ir, Cval);
-          CB_LAUNCH_CHECK(ctx);
-        }
-        if (cntS > 0) {
-          kern<<<(unsigned)cntS, 128, smS, st>>>(src, order + begS, cntS, io.m, max_cells, taskptr, Cm->ir, Cval);
-          CB_LAUNCH_CHECK(ctx);
-        }
-        CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
-        stats.tasks_bitmap_smem = cntL + cntS;
-        for (int b = 41; b <= 79; ++b) { stats.flops_bitmap_smem += nb.weight[b]; stats.nnz_bitmap_smem += nb.weight2[b]; }
+    if (nc.count[NUM_BM_L] + nc.count[NUM_BM_S] > 0) {
+      auto kern = num_bitmap_kernel<SR, MERGE, false>;
+      size_t smL = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)std::max<int64_t>(opt.bitmap_smem_acc, 2048) * sizeof(acc_t);
+      size_t smS = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)2048 * sizeof(acc_t);
+      CB_TRY(optin_smem(ctx, kern, std::max(smL, smS)));
+      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
+      if (nc.count[NUM_BM_L] > 0) {
+        kern<<<(unsigned)nc.count[NUM_BM_L], kBitmapThreads, smL, st>>>(src, order + nc.begin[NUM_BM_L], nc.count[NUM_BM_L], io.m,
+                                                                      max_cells, taskptr, Cm->ir, Cval);
+        CB_LAUNCH_CHECK(ctx);
       }
+      if (nc.count[NUM_BM_S] > 0) {
+        kern<<<(unsigned)nc.count[NUM_BM_S], 128, smS, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
+                                                            taskptr, Cm->ir, Cval);
+        CB_LAUNCH_CHECK(ctx);
+      }
+      CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
+      stats.tasks_bitmap_smem = nc.count[NUM_BM_L] + nc.count[NUM_BM_S];
+      stats.flops_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, false) + class_weight(nb, num_class, NUM_BM_S, false);
+      stats.nnz_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, true) + class_weight(nb, num_class, NUM_BM_S, true);
     }
     // hash per CTA: 257..2048 outputs
-    bucket_range(nb, 10, 39, &beg, &cnt);
-    if (cnt > 0) {
+    if (nc.count[NUM_H_CTA] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 8, 12>;
       size_t sm = ((size_t)1 << 12) * (8 + sizeof(acc_t) + 4) + 16;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_CTA);
-      kern<<<(unsigned)cnt, 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
+      kern<<<(unsigned)nc.count[NUM_H_CTA], 256, sm, st>>>(src, order + nc.begin[NUM_H_CTA], nc.count[NUM_H_CTA], taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_HASH_CTA);
-      stats.tasks_hash_cta = cnt;
-      for (int b = 10; b <= 39; ++b) { stats.flops_hash_cta += nb.weight[b]; stats.nnz_hash_cta += nb.weight2[b]; }
+      stats.tasks_hash_cta = nc.count[NUM_H_CTA];
+      stats.flops_hash_cta = class_weight(nb, num_class, NUM_H_CTA, false);
+      stats.nnz_hash_cta = class_weight(nb, num_class, NUM_H_CTA, true);
     }
     // hash per warp: 33..256 outputs
-    bucket_range(nb, 7, 9, &beg, &cnt);
-    if (cnt > 0) {
+    if (nc.count[NUM_H_WARP] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 9>;
       size_t sm = 8 * ((size_t)1 << 9) * (8 + sizeof(acc_t) + 4) + 64;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_WARP);
-      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
+      kern<<<(unsigned)((nc.count[NUM_H_WARP] + 7) / 8), 256, sm, st>>>(src, order + nc.begin[NUM_H_WARP], nc.count[NUM_H_WARP], taskptr,
+                                                                       Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_HASH_WARP);
-      stats.tasks_hash_warp += cnt;
-      for (int b = 7; b <= 9; ++b) { stats.flops_hash_warp += nb.weight[b]; stats.nnz_hash_warp += nb.weight2[b]; }
+      stats.tasks_hash_warp += nc.count[NUM_H_WARP];
+      stats.flops_hash_warp += class_weight(nb, num_class, NUM_H_WARP, false);
+      stats.nnz_hash_warp += class_weight(nb, num_class, NUM_H_WARP, true);
     }
     // hash per warp: <= 32 outputs
-    bucket_range(nb, 1, 6, &beg, &cnt);
-    if (cnt > 0) {
+    if (nc.count[NUM_H_WARP_S] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 6>;
       size_t sm = 8 * ((size_t)1 << 6) * (8 + sizeof(acc_t) + 4) + 64;
+      CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_WARP_S);
-      kern<<<(unsigned)((cnt + 7) / 8), 256, sm, st>>>(src, order + beg, cnt, taskptr, Cm->ir, Cval);
+      kern<<<(unsigned)((nc.count[NUM_H_WARP_S] + 7) / 8), 256, sm, st>>>(src, order + nc.begin[NUM_H_WARP_S], nc.count[NUM_H_WARP_S],
+                                                                         taskptr, Cm->ir, Cval);
       CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_HASH_WARP_S);
-      stats.tasks_hash_warp += cnt;
-      for (int b = 1; b <= 6; ++b) { stats.flops_hash_warp += nb.weight[b]; stats.nnz_hash_warp += nb.weight2[b]; }
+      stats.tasks_hash_warp += nc.count[NUM_H_WARP_S];
+      stats.flops_hash_warp += class_weight(nb, num_class, NUM_H_WARP_S, false);
+      stats.nnz_hash_warp += class_weight(nb, num_class, NUM_H_WARP_S, true);
     }
     // ---- DCSC assembly: column pointers of the candidate columns, then drop the empty ones
     const int64_t *cand_ptr = taskptr;
@@ -381,7 +408,6 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   dev_free(ctx, order);
   dev_free(ctx, tasknnz);
   dev_free(ctx, taskptr);
-  dev_free(ctx, Ttab);
   if (rc != CBGPU_OK) {
     mat_release(ctx, Cm);
     return rc;

@@ -15,8 +15,14 @@ static int spgemm_impl(const SpgemmArgs &a) {
   cbgpu_ctx_impl *ctx = a.ctx;
   cbgpu_mat_impl *A = a.A, *B = a.B;
   CB_TRY(ensure_dense_colptr(ctx, A));
+  int nwin, wlog2;
+  engine_windows(ctx, A->m, &nwin, &wlog2);
+  if (nwin > 1 && A->nnz > 0 && B->nnz > 0) CB_TRY(ensure_window_major(ctx, A, nwin, wlog2)); // cached on A
   Source<SR, false> src;
   memset(&src, 0, sizeof(src));
+  src.T2 = A->win_T2;
+  src.Wir = A->win_ir;
+  src.Wval = reinterpret_cast<const SR::a_t *>(A->win_val);
   src.Air = A->ir;
   src.Aval = reinterpret_cast<const SR::a_t *>(A->numx);
   src.Bcp = B->cp;
@@ -76,6 +82,16 @@ static int merge_impl(const MergeArgs &a) {
   }
   Source<SR, true> src;
   memset(&src, 0, sizeof(src));
+  int nwin, wlog2;
+  engine_windows(ctx, m, &nwin, &wlog2);
+  int64_t *T2 = nullptr;
+  int32_t *Wir = nullptr;
+  void *Wval = nullptr;
+  if (nwin > 1 && total > 0)
+    CB_TRY(build_window_major(ctx, colptr, rows, vals, (int)sizeof(out_t), (int64_t)k * n, total, nwin, wlog2, &T2, &Wir, &Wval));
+  src.T2 = T2;
+  src.Wir = Wir;
+  src.Wval = reinterpret_cast<const out_t *>(Wval);
   src.Air = rows;
   src.Aval = vals;
   src.k = k;
@@ -92,6 +108,9 @@ static int merge_impl(const MergeArgs &a) {
   io.C = a.out;
   io.stats = a.stats;
   int rc = run_engine<SR, true>(ctx, src, io);
+  dev_free(ctx, T2);
+  dev_free(ctx, Wir);
+  dev_free(ctx, Wval);
   dev_free(ctx, rows);
   dev_free(ctx, vals);
   dev_free(ctx, colptr);

@@ -1,6 +1,7 @@
 // Device-wide helper kernels: scan, task binning, dense column index, row-window table, column compaction.
 // Hand-written (no CUB/Thrust) so every launch on the hot path is ours and counted.
 #include <stdarg.h>
+#include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 #include "util.cuh"
 
@@ -243,6 +244,71 @@ int build_window_table(cbgpu_ctx_impl *ctx, const int64_t *colptr, const int32_t
   return CBGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ window-major copy
+__global__ void piece_len_kernel(const int64_t *T, int64_t ncols, int nwin, int64_t *len2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // i = w * ncols + c
+  if (i >= ncols * nwin) return;
+  int64_t w = i / ncols, c = i - w * ncols;
+  const int64_t *t = T + c * nwin + w;
+  len2[i] = t[1] - t[0];
+}
+template <int VB>
+__global__ void piece_copy_kernel(const int64_t *T, const int64_t *T2, const int32_t *rows, const unsigned char *vals,
+                                  int64_t ncols, int nwin, int32_t *wrows, unsigned char *wvals) {
+  int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= ncols) return;
+  const int lane = threadIdx.x & 31;
+  for (int w = 0; w < nwin; ++w) {
+    int64_t src = T[c * nwin + w], n = T[c * nwin + w + 1] - src, dst = T2[(int64_t)w * ncols + c];
+    for (int64_t i = lane; i < n; i += 32) {
+      wrows[dst + i] = rows[src + i];
+      if (VB == 8) reinterpret_cast<uint64_t *>(wvals)[dst + i] = reinterpret_cast<const uint64_t *>(vals)[src + i];
+      else if (VB == 4) reinterpret_cast<uint32_t *>(wvals)[dst + i] = reinterpret_cast<const uint32_t *>(vals)[src + i];
+      else wvals[dst + i] = vals[src + i];
+    }
+  }
+}
+
+int build_window_major(cbgpu_ctx_impl *ctx, const int64_t *colptr, const int32_t *rows, const void *vals, int vbytes,
+                       int64_t ncols, int64_t nnz, int nwin, int wlog2, int64_t **T2, int32_t **Wir, void **Wval) {
+  int64_t *T = nullptr, *len2 = nullptr;
+  CB_TRY(build_window_table(ctx, colptr, rows, ncols, nwin, wlog2, &T));
+  const int64_t np = ncols * nwin;
+  CB_TRY(dev_alloc_t(ctx, &len2, (size_t)np + 1));
+  CB_TRY(dev_alloc_t(ctx, T2, (size_t)np + 1));
+  CB_TRY(dev_alloc_t(ctx, Wir, (size_t)nnz));
+  CB_TRY(dev_alloc(ctx, Wval, (size_t)nnz * vbytes));
+  if (np > 0) {
+    piece_len_kernel<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(T, ncols, nwin, len2);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  CB_TRY(exclusive_scan_i64(ctx, len2, *T2, np));
+  if (ncols > 0) {
+    unsigned nb = (unsigned)((ncols * 32 + 255) / 256);
+    const unsigned char *v = (const unsigned char *)vals;
+    unsigned char *wv = (unsigned char *)*Wval;
+    if (vbytes == 8) piece_copy_kernel<8><<<nb, 256, 0, ctx->stream>>>(T, *T2, rows, v, ncols, nwin, *Wir, wv);
+    else if (vbytes == 4) piece_copy_kernel<4><<<nb, 256, 0, ctx->stream>>>(T, *T2, rows, v, ncols, nwin, *Wir, wv);
+    else piece_copy_kernel<1><<<nb, 256, 0, ctx->stream>>>(T, *T2, rows, v, ncols, nwin, *Wir, wv);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  CB_TRY(dev_free(ctx, T));
+  CB_TRY(dev_free(ctx, len2));
+  return CBGPU_OK;
+}
+
+int ensure_window_major(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M, int nwin, int wlog2) {
+  if (M->win_T2 && M->win_log2 == wlog2 && M->win_nwin == nwin) return CBGPU_OK;
+  dev_free(ctx, M->win_T2); dev_free(ctx, M->win_ir); dev_free(ctx, M->win_val);
+  M->win_T2 = nullptr; M->win_ir = nullptr; M->win_val = nullptr;
+  CB_TRY(ensure_dense_colptr(ctx, M));
+  CB_TRY(build_window_major(ctx, M->colptr, M->ir, M->numx, (int)dtype_size(M->dtype), M->n, M->nnz, nwin, wlog2, &M->win_T2,
+                            &M->win_ir, &M->win_val));
+  M->win_log2 = wlog2;
+  M->win_nwin = nwin;
+  return CBGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ binning
 __global__ void __launch_bounds__(256)
 bucket_hist_kernel(const uint8_t *bucket, const int64_t *weight, const int64_t *weight2, int64_t n,
@@ -272,68 +338,69 @@ bucket_hist_kernel(const uint8_t *bucket, const int64_t *weight, const int64_t *
   }
 }
 
-__global__ void __launch_bounds__(256)
-bucket_scatter_kernel(const uint8_t *bucket, int64_t n, unsigned long long *cursor, int32_t *order) {
-  __shared__ unsigned int h[256];
-  __shared__ unsigned long long base_of[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  int64_t base = (int64_t)blockIdx.x * 4096;
-  for (int i = 0; i < 16; ++i) {
-    int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
-    if (idx < n) atomicAdd(&h[bucket[idx]], 1u);
+struct ClassTable { uint8_t c[256]; };
+__global__ void task_key_kernel(const uint8_t *bucket, const uint32_t *task_win, ClassTable tab, int64_t n, unsigned *keys,
+                                int32_t *ids) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned b = bucket[i];
+  unsigned w = 0;
+  if (task_win) {
+    unsigned tw = task_win[i];
+    if (((tw >> 16) - (tw & 0xFFFFu)) == 1) w = tw & 0xFFFFu;
   }
-  __syncthreads();
-  if (h[threadIdx.x]) base_of[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)h[threadIdx.x]);
-  __syncthreads();
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  for (int i = 0; i < 16; ++i) {
-    int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
-    if (idx < n) {
-      int b = bucket[idx];
-      if (b != 0) { // bucket 0 = nothing to do; not listed
-        unsigned int off = atomicAdd(&h[b], 1u);
-        order[base_of[b] + off] = (int32_t)idx;
-      }
-    }
-  }
+  keys[i] = ((unsigned)tab.c[b] << 28) | ((w & 0xFFFFu) << 8) | (255u - b);
+  ids[i] = (int32_t)i;
 }
 
 int bin_tasks(cbgpu_ctx_impl *ctx, const uint8_t *bucket, const int64_t *weight, const int64_t *weight2, int64_t n,
-              int32_t *order, BinResult *res) {
+              const uint32_t *task_win, const uint8_t class_of_bucket[256], int32_t *order, BinResult *res,
+              ClassRanges *classes) {
   memset(res, 0, sizeof(*res));
+  memset(classes, 0, sizeof(*classes));
   if (n <= 0) return CBGPU_OK;
   unsigned long long *dh = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &dh, 1024));
-  CB_CUDA(ctx, cudaMemsetAsync(dh, 0, 1024 * sizeof(unsigned long long), ctx->stream));
+  CB_TRY(dev_alloc_t(ctx, &dh, 768));
+  CB_CUDA(ctx, cudaMemsetAsync(dh, 0, 768 * sizeof(unsigned long long), ctx->stream));
   unsigned nblk = (unsigned)((n + 4095) / 4096);
   bucket_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, weight, weight2, n, dh, dh + 256, dh + 512);
   CB_LAUNCH_CHECK(ctx);
   unsigned long long hh[768];
   CB_CUDA(ctx, cudaMemcpyAsync(hh, dh, sizeof(hh), cudaMemcpyDeviceToHost, ctx->stream));
+  // ordering: sort task ids by (class, window, descending bucket) -- CUB radix sort (library call on a few MB)
+  ClassTable tab;
+  memcpy(tab.c, class_of_bucket, 256);
+  unsigned *keys = nullptr, *keys2 = nullptr;
+  int32_t *ids = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &keys, (size_t)n));
+  CB_TRY(dev_alloc_t(ctx, &keys2, (size_t)n));
+  CB_TRY(dev_alloc_t(ctx, &ids, (size_t)n));
+  task_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(bucket, task_win, tab, n, keys, ids);
+  CB_LAUNCH_CHECK(ctx);
+  size_t tmp_bytes = 0;
+  CB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ids, order, n, 0, 32, ctx->stream));
+  void *tmp = nullptr;
+  CB_TRY(dev_alloc(ctx, &tmp, tmp_bytes));
+  CB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, order, n, 0, 32, ctx->stream));
+  ctx->launches += 4;
   CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // descending bucket order: larger work first
-  unsigned long long cur[256];
-  int64_t off = 0;
-  for (int b = 255; b >= 1; --b) {
+  CB_TRY(dev_free(ctx, tmp));
+  CB_TRY(dev_free(ctx, keys));
+  CB_TRY(dev_free(ctx, keys2));
+  CB_TRY(dev_free(ctx, ids));
+  CB_TRY(dev_free(ctx, dh));
+  for (int b = 0; b < 256; ++b) {
     res->count[b] = (int64_t)hh[b];
     res->weight[b] = (int64_t)hh[256 + b];
     res->weight2[b] = (int64_t)hh[512 + b];
-    res->offset[b] = off;
-    cur[b] = (unsigned long long)off;
-    off += (int64_t)hh[b];
+    classes->count[class_of_bucket[b] & 15] += (int64_t)hh[b];
   }
-  res->count[0] = (int64_t)hh[0];
-  res->offset[0] = off;
-  cur[0] = (unsigned long long)off;
-  res->listed = off;
-  CB_CUDA(ctx, cudaMemcpyAsync(dh + 768, cur, sizeof(cur), cudaMemcpyHostToDevice, ctx->stream));
-  bucket_scatter_kernel<<<nblk, 256, 0, ctx->stream>>>(bucket, n, dh + 768, order);
-  CB_LAUNCH_CHECK(ctx);
-  // `cur` lives on this stack frame: make sure the copy has been consumed before returning
-  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  CB_TRY(dev_free(ctx, dh));
+  int64_t off = 0;
+  for (int c = 0; c < 16; ++c) {
+    classes->begin[c] = off;
+    off += classes->count[c];
+  }
+  res->listed = off - classes->count[15];
   return CBGPU_OK;
 }
 
@@ -409,6 +476,9 @@ int mat_release(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M) {
   dev_free(ctx, M->ir);
   dev_free(ctx, M->numx);
   dev_free(ctx, M->colptr);
+  dev_free(ctx, M->win_T2);
+  dev_free(ctx, M->win_ir);
+  dev_free(ctx, M->win_val);
   delete M;
   return CBGPU_OK;
 }
