@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--phases", type=int, default=0, help="column slabs of B/C per step (0 = automatic from the symbolic pass)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -201,6 +202,9 @@ def main():
     stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library launches on it, torch events time it
     torch.cuda.set_stream(stream)
     ctx = cb.Context(local_rank, stream=stream.cuda_stream)
+    for o in args.opt:
+        k_, v_ = o.split("=")
+        ctx.set_option(k_, int(v_))
     scale = args.scale
     n = 1 << scale
     layers = {1: 1, 2: 2, 4: 1, 8: 2}.get(world)
