@@ -127,11 +127,11 @@ __device__ __forceinline__ uint8_t shfl_mult<uint8_t>(uint8_t v, int src) {
 }
 
 // shared-memory workspace of the balanced CTA walk (one chunk of up to 512 segments at a time)
-constexpr int kWalkChunk = 512;
-struct CtaQueue {
-  long long pre[kWalkChunk + 1];         // exclusive prefix of the segment lengths of the chunk (in products)
-  long long beg[kWalkChunk];             // first position of every segment
-  unsigned long long mult[kWalkChunk];   // raw bits of the multiplier
+template <int CHUNK>
+struct CtaQueueT {
+  long long pre[CHUNK + 1];         // exclusive prefix of the segment lengths of the chunk (in products)
+  long long beg[CHUNK];             // first position of every segment
+  unsigned long long mult[CHUNK];   // raw bits of the multiplier
   long long warp_sums[32];
 };
 struct NoQueue {};
@@ -208,11 +208,10 @@ __device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task
 // Whole-CTA walk with equal shares of PRODUCTS per warp: the CTA stages a chunk of segments in shared memory with the
 // running sum of their lengths; warp w then owns products [w*P/nw, (w+1)*P/nw) of the chunk, wherever the segment
 // boundaries fall, so one very long A-column can no longer stall the other warps at the barrier. All threads must call.
-template <class SR, bool MERGE, bool NEED_MULT, class F>
-__device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueue *q, F &&f) {
+template <class SR, bool MERGE, bool NEED_MULT, int CH, class F>
+__device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<CH> *q, F &&f) {
   typedef typename SR::b_t mult_t;
-  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int CH = min((int)blockDim.x, kWalkChunk);
+  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = CH >> 5; // blockDim.x == CH
   for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
     __syncthreads(); // previous chunk fully consumed
     const int nseg = (int)min((int64_t)CH, k.seg_end - cbase);
@@ -334,7 +333,7 @@ sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_
   constexpr int GT = GROUP_WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned *keys_all = reinterpret_cast<unsigned *>(smem_raw);
-  __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueue>::type queue;
+  __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueueT<GROUP_WARPS * 32>>::type queue;
   __shared__ int cta_count;
   const int group = GROUP_WARPS == 1 ? (threadIdx.x >> 5) : 0;
   const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
@@ -355,7 +354,7 @@ sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_
     mine += fresh ? 1 : 0;
   };
   if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, f);
-  else cta_walk<SR, MERGE, false>(s, k, reinterpret_cast<CtaQueue *>(&queue), f);
+  else cta_walk<SR, MERGE, false>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), f);
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
   if (GROUP_WARPS == 1) {
@@ -403,7 +402,7 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   acc_t *acc_all = reinterpret_cast<acc_t *>(sort_all + GROUPS * T);
   unsigned *keys_all = reinterpret_cast<unsigned *>(acc_all + GROUPS * T);
   int *cnt_all = reinterpret_cast<int *>(keys_all + GROUPS * T);
-  __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueue>::type queue;
+  __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueueT<GROUP_WARPS * 32>>::type queue;
   const int group = GROUP_WARPS == 1 ? (threadIdx.x >> 5) : 0;
   const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
   int64_t ti = (int64_t)blockIdx.x * GROUPS + group;
@@ -433,7 +432,7 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
     warp_walk<SR, MERGE, true>(s, k, f);
     __syncwarp();
   } else {
-    cta_walk<SR, MERGE, true>(s, k, reinterpret_cast<CtaQueue *>(&queue), f);
+    cta_walk<SR, MERGE, true>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), f);
   }
   // compact the occupied slots
   for (int i = gtid; i < T; i += GT) {
@@ -485,8 +484,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /*[32]
   return warp_sums[warp] + incl - v;
 }
 
-template <class SR, bool MERGE>
-__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, CtaQueue *q, unsigned *bm,
+template <class SR, bool MERGE, int THREADS>
+__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<THREADS> *q, unsigned *bm,
                                             int ncell, int rbase) {
   uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
   const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
@@ -499,12 +498,12 @@ __device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Ta
 }
 
 // K2 (bitmap): rows of the window present in the task
-template <class SR, bool MERGE>
-__global__ void __launch_bounds__(kBitmapThreads)
+template <class SR, bool MERGE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int64_t *tasknnz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned *bm = reinterpret_cast<unsigned *>(smem_raw);
-  __shared__ CtaQueue queue;
+  __shared__ CtaQueueT<THREADS> queue;
   __shared__ int warp_sums[32];
   __shared__ int total;
   int t = order[blockIdx.x];
@@ -524,8 +523,8 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
 // K4 (bitmap): rank every present row by popcount, accumulate values at their final sorted position.
 // GMEM_ACC == false: accumulators in shared memory, copied out at the end;
 // GMEM_ACC == true : accumulators are C's value array itself (atomics resolve in L2).
-template <class SR, bool MERGE, bool GMEM_ACC>
-__global__ void __launch_bounds__(kBitmapThreads)
+template <class SR, bool MERGE, bool GMEM_ACC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int max_cells,
                   const int64_t *taskptr, int32_t *Cir, typename SR::out_t *Cval) {
   typedef typename SR::acc_t acc_t;
@@ -535,7 +534,7 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   unsigned *bm = reinterpret_cast<unsigned *>(smem_raw);
   unsigned *pre = bm + 2 * (size_t)max_cells;
   acc_t *acc = reinterpret_cast<acc_t *>(pre + max_cells + (max_cells & 1));
-  __shared__ CtaQueue queue;
+  __shared__ CtaQueueT<THREADS> queue;
   __shared__ int warp_sums[32];
   __shared__ int total;
   int t = order[blockIdx.x];

@@ -226,14 +226,16 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     return s;
   };
   if (sc.count[SYM_BM_L] + sc.count[SYM_BM_S] > 0) {
-    auto kern = sym_bitmap_kernel<SR, MERGE>;
-    CB_TRY(optin_smem(ctx, kern, bm_bytes));
     CB_KBEGIN(CBGPU_K_SYM_BITMAP);
     if (sc.count[SYM_BM_L] > 0) {
-      kern<<<(unsigned)sc.count[SYM_BM_L], kBitmapThreads, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
+      auto kern = sym_bitmap_kernel<SR, MERGE, 512>;
+      CB_TRY(optin_smem(ctx, kern, bm_bytes));
+      kern<<<(unsigned)sc.count[SYM_BM_L], 512, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
       CB_LAUNCH_CHECK(ctx);
     }
     if (sc.count[SYM_BM_S] > 0) {
+      auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
+      CB_TRY(optin_smem(ctx, kern, bm_bytes));
       kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
       CB_LAUNCH_CHECK(ctx);
     }
@@ -307,41 +309,44 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, task_win, num_class, order, &nb, &nc));
     }
     out_t *Cval = reinterpret_cast<out_t *>(Cm->numx);
-    // bitmap, accumulators in C itself (largest tasks)
-    if (nc.count[NUM_BM_G] > 0) {
-      auto kern = num_bitmap_kernel<SR, MERGE, true>;
+    // bitmap, accumulators in C itself: RED.ADD straight into the (L2-resident) output slice of the task.
+    // Largest tasks by 512 threads; the many small ones (<= 2048 outputs) by 128 threads with a small shared-memory
+    // footprint so that many of them are in flight per SM (their cost is dependent-load latency, not bandwidth).
+    if (nc.count[NUM_BM_G] + nc.count[NUM_BM_S] > 0) {
       size_t sm = bm_bytes + (size_t)max_cells * 4 + 16;
-      CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
-      kern<<<(unsigned)nc.count[NUM_BM_G], kBitmapThreads, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m,
-                                                                   max_cells, taskptr, Cm->ir, Cval);
-      CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
-      stats.tasks_bitmap_gmem = nc.count[NUM_BM_G];
-      stats.flops_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, false);
-      stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true);
-    }
-    // bitmap, accumulators in shared memory: more than 2048 outputs by 512 threads, the rest by 128 threads
-    if (nc.count[NUM_BM_L] + nc.count[NUM_BM_S] > 0) {
-      auto kern = num_bitmap_kernel<SR, MERGE, false>;
-      size_t smL = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)std::max<int64_t>(opt.bitmap_smem_acc, 2048) * sizeof(acc_t);
-      size_t smS = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)2048 * sizeof(acc_t);
-      CB_TRY(optin_smem(ctx, kern, std::max(smL, smS)));
-      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
-      if (nc.count[NUM_BM_L] > 0) {
-        kern<<<(unsigned)nc.count[NUM_BM_L], kBitmapThreads, smL, st>>>(src, order + nc.begin[NUM_BM_L], nc.count[NUM_BM_L], io.m,
-                                                                      max_cells, taskptr, Cm->ir, Cval);
+      if (nc.count[NUM_BM_G] > 0) {
+        auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
+        CB_TRY(optin_smem(ctx, kern, sm));
+        kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
+                                                           taskptr, Cm->ir, Cval);
         CB_LAUNCH_CHECK(ctx);
       }
       if (nc.count[NUM_BM_S] > 0) {
-        kern<<<(unsigned)nc.count[NUM_BM_S], 128, smS, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                            taskptr, Cm->ir, Cval);
+        auto kern = num_bitmap_kernel<SR, MERGE, true, 128>;
+        CB_TRY(optin_smem(ctx, kern, sm));
+        kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
+                                                           taskptr, Cm->ir, Cval);
         CB_LAUNCH_CHECK(ctx);
       }
+      CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
+      stats.tasks_bitmap_gmem = nc.count[NUM_BM_G] + nc.count[NUM_BM_S];
+      stats.flops_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, false) + class_weight(nb, num_class, NUM_BM_S, false);
+      stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true) + class_weight(nb, num_class, NUM_BM_S, true);
+    }
+    // bitmap, accumulators in shared memory (2049 .. bitmap_smem_acc outputs; empty with the default options)
+    if (nc.count[NUM_BM_L] > 0) {
+      auto kern = num_bitmap_kernel<SR, MERGE, false, 512>;
+      size_t smL = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)std::max<int64_t>(opt.bitmap_smem_acc, 2048) * sizeof(acc_t);
+      CB_TRY(optin_smem(ctx, kern, smL));
+      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
+      kern<<<(unsigned)nc.count[NUM_BM_L], 512, smL, st>>>(src, order + nc.begin[NUM_BM_L], nc.count[NUM_BM_L], io.m, max_cells,
+                                                          taskptr, Cm->ir, Cval);
+      CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
-      stats.tasks_bitmap_smem = nc.count[NUM_BM_L] + nc.count[NUM_BM_S];
-      stats.flops_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, false) + class_weight(nb, num_class, NUM_BM_S, false);
-      stats.nnz_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, true) + class_weight(nb, num_class, NUM_BM_S, true);
+      stats.tasks_bitmap_smem = nc.count[NUM_BM_L];
+      stats.flops_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, false);
+      stats.nnz_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, true);
     }
     // hash per CTA: 257..2048 outputs
     if (nc.count[NUM_H_CTA] > 0) {
