@@ -454,6 +454,8 @@ int cbgpu_mat_info(const cbgpu_mat *M, cbgpu_mat_info_t *info) {
 int cbgpu_mat_download(cbgpu_ctx *ctx, const cbgpu_mat *M, const cbgpu_dcsc_out *h) {
   if (!ctx || !M || !h) return CBGPU_ERR_INVALID;
   if (h->idx_bytes != 4 && h->idx_bytes != 8) return set_error(ctx, CBGPU_ERR_INVALID, "idx_bytes must be 4 or 8");
+  if (h->idx_bytes == 4 && (M->nnz > 0x7FFFFFFFLL || M->n > 0x7FFFFFFFLL))
+    return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "block with %lld entries does not fit 32-bit column pointers", (long long)M->nnz);
   CB_TRY(download_index_array(ctx, h->jc, h->idx_bytes, M->nzc, M->jc, nullptr));
   CB_TRY(download_index_array(ctx, h->cp, h->idx_bytes, M->nzc + 1, M->cp, nullptr));
   CB_TRY(download_index_array(ctx, h->ir, h->idx_bytes, M->nnz, nullptr, M->ir));

@@ -237,3 +237,50 @@ def test_device_generator_equals_host_generator(ctx):
             assert np.all(numx == 1)
         else:
             assert np.array_equal(numx, 1 + ir)
+
+
+def test_er_config_full_size(ctx, port_oracle):
+    """BASELINE config 2 at full size: Erdos-Renyi n = 2^22, d = 8, A bool, B int64 = 1 + row id,
+    SelectMaxSRing<bool,int64_t>, bit-exact against the CPU oracle."""
+    scale, d = 22, 8
+    dA = ctx.gen_rmat(scale, d << scale, seed=2, a=0.25, b=0.25, c=0.25, scramble=False, dtype=cb.BOOL, value_mode=1)
+    dB = ctx.gen_rmat(scale, d << scale, seed=2, a=0.25, b=0.25, c=0.25, scramble=False, dtype=cb.I64, value_mode=2)
+    D, st = ctx.spgemm(cb.SelectMaxSRing_bool_i64, dA, dB, want_stats=True)
+    m, n, jc, cp, ir, numx = ctx.download(dA)
+    a = Csc(m, n, cb.SpDCCols(m, n, jc, cp, ir, numx).to_csc()[0], ir, numx)
+    m, n, jc, cp, ir, vb = ctx.download(dB)
+    b = Csc(m, n, a.colptr, ir, vb)
+    want = port_oracle.spgemm(a, b, 3)
+    rows, cols, vals = ctx.download_coo(D)
+    assert st.nnz_out == want.nnz and st.flops > 2.5e8
+    assert np.array_equal(rows, want.rows) and np.array_equal(cols, want.cols_expanded()) and np.array_equal(vals, want.vals)
+
+
+def test_rmat_scale16_config1(ctx, oracle):
+    """BASELINE config 1: R-MAT scale 16, edge factor 16, A^2, PlusTimes<double> against the reference's CPU kernel"""
+    A = rmat(16, 16, seed=1)
+    check_pair(ctx, oracle, 0, A, A)
+
+
+def test_large_scale_properties(ctx):
+    """size-independent properties at a size beyond the oracle-checked cases (R-MAT scale 18, 1.3e9 outputs): slab-wise product == whole
+    product (checksums), symbolic == numeric counts, every column sorted and duplicate free"""
+    G = ctx.gen_rmat(18, 16 << 18, seed=4)
+    C, st = ctx.spgemm(0, G, G, want_stats=True)
+    f, z = ctx.symbolic(G, G)
+    assert (f, z) == (st.flops, st.nnz_out) and C.nnz == z
+    slabs = [ctx.spgemm(0, G, Bs) for Bs in ctx.colsplit(G, 4)]
+    J = ctx.colconcat(slabs)
+    assert ctx.checksum(J)[0] == ctx.checksum(C)[0] and J.nnz == C.nnz
+    for s in slabs:
+        s.free()
+    m, n, jc, cp, ir, numx = ctx.download(J, np.int32)
+    J.free()
+    assert np.all(np.diff(jc) > 0) and np.all(np.diff(cp) > 0)
+    d = np.diff(ir.astype(np.int64))
+    interior = np.ones(len(ir) - 1, dtype=bool)
+    interior[cp[1:-1].astype(np.int64) - 1] = False  # positions where one column ends and the next begins
+    assert np.all(d[interior] > 0), "rows must be strictly ascending inside every column"
+    # all values of A are positive integers (multiplicities): every entry of A^2 is a positive integer too
+    assert np.all(numx >= 1) and np.all(numx == np.floor(numx))
+    C.free()
