@@ -167,6 +167,10 @@ def bytes_alg(nnzA, nzcA, nnzB, nzcB, nnzC, nzcC, sv=8):
 
 
 def main():
+    # exactly one JSON line may reach stdout: libraries (NCCL banner, ...) that print there are sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -90,7 +90,7 @@ __device__ __forceinline__ void task_segments(const Source<SR, MERGE> &s, Task &
     k.seg_begin = s.Bcp[k.col];
     k.seg_end = s.Bcp[k.col + 1];
   }
-  const bool whole = (k.whi - k.wlo) == s.nwin;
+  const bool whole = (k.whi - k.wlo) == s.nwin || s.T2 == nullptr;
   k.rows = whole ? s.Air : s.Wir;
   k.vals = whole ? (const void *)s.Aval : (const void *)s.Wval;
 }
@@ -109,10 +109,28 @@ __device__ __forceinline__ void load_segment(const Source<SR, MERGE> &s, const T
   if ((k.whi - k.wlo) == s.nwin) {
     beg = s.T[col];
     len = (int)(s.T[col + 1] - beg);
-  } else {
+  } else if (s.T2 != nullptr) {
     const int64_t *t = s.T2 + (int64_t)k.wlo * s.N + col;
     beg = t[0];
     len = (int)(t[1] - beg);
+  } else {
+    // no window-major copy (merge: few, long segments): cut the row-sorted column by binary search
+    int64_t b0 = s.T[col], e0 = s.T[col + 1];
+    const int64_t lo = (int64_t)k.wlo << s.wlog2, hi = (int64_t)k.whi << s.wlog2;
+    int64_t a = b0, b = e0;
+    while (a < b) {
+      int64_t mid = (a + b) >> 1;
+      if ((int64_t)s.Air[mid] < lo) a = mid + 1;
+      else b = mid;
+    }
+    beg = a;
+    b = e0;
+    while (a < b) {
+      int64_t mid = (a + b) >> 1;
+      if ((int64_t)s.Air[mid] < hi) a = mid + 1;
+      else b = mid;
+    }
+    len = (int)(a - beg);
   }
 }
 

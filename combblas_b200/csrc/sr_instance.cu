@@ -87,8 +87,7 @@ static int merge_impl(const MergeArgs &a) {
   int64_t *T2 = nullptr;
   int32_t *Wir = nullptr;
   void *Wval = nullptr;
-  if (nwin > 1 && total > 0)
-    CB_TRY(build_window_major(ctx, colptr, rows, vals, (int)sizeof(out_t), (int64_t)k * n, total, nwin, wlog2, &T2, &Wir, &Wval));
+  (void)nwin; // merge segments are few and long: they are cut per window by binary search, no window-major copy
   src.T2 = T2;
   src.Wir = Wir;
   src.Wval = reinterpret_cast<const out_t *>(Wval);
