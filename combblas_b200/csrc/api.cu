@@ -379,6 +379,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "bitmap_min_nnz")) return &o.bitmap_min_nnz;
   if (!strcmp(name, "bitmap_smem_acc")) return &o.bitmap_smem_acc;
   if (!strcmp(name, "force_path")) return &o.force_path;
+  if (!strcmp(name, "merge_engine")) return &o.merge_engine;
   return nullptr;
 }
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {

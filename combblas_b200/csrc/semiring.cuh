@@ -10,6 +10,7 @@
 //                      mtSpGEMM.h:398-416, equals "initialise with identity, add everything")
 //   accumulate(p, v)   *p = SR::add(v, *p), atomically; p may point to shared or global memory
 //   accumulate_out(p,v) same, but p points into C's value array (out_t) in global memory
+//   add(a, b)          SR::add on two stored values (used by the streaming 2-way merge)
 //   to_out / from_out  conversion between acc_t and out_t
 #pragma once
 #include <cuda_runtime.h>
@@ -41,6 +42,7 @@ struct Semiring<0> {
   __device__ static __forceinline__ acc_t identity() { return 0.0; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a + b; } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -52,6 +54,7 @@ struct Semiring<1> {
   __device__ static __forceinline__ acc_t identity() { return 0.0f; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a + b; } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -63,6 +66,7 @@ struct Semiring<2> {
   __device__ static __forceinline__ acc_t identity() { return 0ull; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return (out_t)((acc_t)a + (acc_t)b); } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return (out_t)v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return (acc_t)v; }
 };
@@ -74,6 +78,7 @@ struct Semiring<3> {
   __device__ static __forceinline__ acc_t identity() { return LLONG_MIN; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicMax(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a > b ? a : b; } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -85,6 +90,7 @@ struct Semiring<4> {
   __device__ static __forceinline__ acc_t identity() { return __longlong_as_double(0x7FF0000000000000LL); } // +inf
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomic_min_f64(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return b < a ? b : a; } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -97,6 +103,7 @@ struct Semiring<5> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { if (v) atomicOr(p, 1u); }
   // OR into a byte of C: every writer stores the same value, so a plain store is race-free in effect
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { if (v) *reinterpret_cast<volatile uint8_t *>(p) = 1; }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return (out_t)((a || b) ? 1 : 0); } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v ? 1 : 0; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v ? 1u : 0u; }
 };
@@ -108,6 +115,7 @@ struct Semiring<6> {
   __device__ static __forceinline__ acc_t identity() { return 0.0; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a + b; } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -119,6 +127,7 @@ struct Semiring<7> {
   __device__ static __forceinline__ acc_t identity() { return 0u; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return (out_t)((acc_t)a + (acc_t)b); } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return (out_t)v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return (acc_t)v; }
 };
@@ -130,6 +139,7 @@ struct Semiring<8> {
   __device__ static __forceinline__ acc_t identity() { return LLONG_MIN; }
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicMax(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
+  __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a > b ? a : b; } // SR::add on stored values
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };

@@ -2,6 +2,7 @@
 // multiply (LocalHybridSpGEMM / LocalSpGEMMHash, mtSpGEMM.h:213,:463) and the k-way merge
 // (MultiwayMerge / MultiwayMergeHash, MultiwayMerge.h:428,:553) of that semiring.
 #include "engine_host.cuh"
+#include "merge2.cuh"
 
 #ifndef CB_SR
 #error "compile with -DCB_SR=<semiring id>"
@@ -54,7 +55,50 @@ static __global__ void concat_colptr_kernel(const int64_t *colptr, int64_t n, in
   if (last && j == n) out[n] = colptr[n] + offset;
 }
 
+// k-way merge by rounds of streaming 2-way merges (k = 2 is the case 2x2 SUMMA and 2-layer fibers produce);
+// the accumulation engine remains available as the general k-way path (option "merge_engine" = 1).
+static int merge_engine_impl(const MergeArgs &a);
 static int merge_impl(const MergeArgs &a) {
+  cbgpu_ctx_impl *ctx = a.ctx;
+  if (ctx->opt.merge_engine || a.k < 2) return merge_engine_impl(a);
+  std::vector<cbgpu_mat_impl *> cur(a.lists, a.lists + a.k);
+  std::vector<bool> owned(a.k, false);
+  cbgpu_stats total;
+  memset(&total, 0, sizeof(total));
+  while (cur.size() > 1) {
+    std::vector<cbgpu_mat_impl *> next;
+    std::vector<bool> next_owned;
+    for (size_t i = 0; i + 1 < cur.size(); i += 2) {
+      cbgpu_mat_impl *C = nullptr;
+      cbgpu_stats st;
+      int rc = merge2_run<SR>(ctx, cur[i], cur[i + 1], &C, &st);
+      if (owned[i]) mat_release(ctx, cur[i]);
+      if (owned[i + 1]) mat_release(ctx, cur[i + 1]);
+      if (rc != CBGPU_OK) {
+        for (size_t q = i + 2; q < cur.size(); ++q) if (owned[q]) mat_release(ctx, cur[q]);
+        for (size_t q = 0; q < next.size(); ++q) if (next_owned[q]) mat_release(ctx, next[q]);
+        return rc;
+      }
+      total.flops += st.flops; total.tasks += st.tasks; total.kernel_launches += st.kernel_launches;
+      total.ms_setup += st.ms_setup; total.ms_symbolic += st.ms_symbolic; total.ms_numeric += st.ms_numeric; total.ms_total += st.ms_total;
+      next.push_back(C);
+      next_owned.push_back(true);
+    }
+    if (cur.size() & 1) {
+      next.push_back(cur.back());
+      next_owned.push_back(owned.back());
+    }
+    cur.swap(next);
+    owned.swap(next_owned);
+  }
+  total.nnz_out = cur[0]->nnz;
+  total.nzc_out = cur[0]->nzc;
+  if (a.stats) *a.stats = total;
+  *a.out = cur[0];
+  return CBGPU_OK;
+}
+
+static int merge_engine_impl(const MergeArgs &a) {
   cbgpu_ctx_impl *ctx = a.ctx;
   const int k = a.k;
   typedef SR::out_t out_t;
