@@ -167,11 +167,19 @@ __device__ __forceinline__ M bits_mult(unsigned long long r) {
   return v;
 }
 
-// One warp processes up to 32 segments, one held per lane as (beg, len, mult). f(pos, mult) is invoked once per
-// product by exactly one lane. Long segments are strided by the whole warp (coalesced), the rest are flattened
-// so that all 32 lanes stay busy on short A-columns.
-template <class mult_t, bool NEED_MULT, class F>
-__device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult, F &&f) {
+template <class V>
+struct RowVal {
+  int row;
+  V val;
+};
+
+// One warp processes up to 32 segments, one held per lane as (beg, len, mult). Each product is loaded by ld(pos) and
+// consumed by use(loaded, mult) by exactly one lane. Long segments are strided by the whole warp (coalesced) with four
+// independent loads in flight per lane; the rest are flattened so that all 32 lanes stay busy on short A-columns (two
+// batches in flight). Splitting load from use is what lets the loads of several products overlap: the consumers are
+// atomics, which the compiler will not reorder loads across.
+template <class mult_t, bool NEED_MULT, class LD, class USE>
+__device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult, LD &&ld, USE &&use) {
   const int lane = lane_id();
   unsigned longmask = __ballot_sync(0xFFFFFFFFu, len >= kWarpLong);
   while (longmask) {
@@ -181,7 +189,18 @@ __device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult
     int l = __shfl_sync(0xFFFFFFFFu, len, src);
     mult_t mu = mult_t();
     if (NEED_MULT) mu = shfl_mult<mult_t>(mult, src);
-    for (int i = lane; i < l; i += 32) f(b + i, mu);
+    int i = lane;
+    for (; i + 96 < l; i += 128) {
+      auto x0 = ld(b + i);
+      auto x1 = ld(b + i + 32);
+      auto x2 = ld(b + i + 64);
+      auto x3 = ld(b + i + 96);
+      use(x0, mu);
+      use(x1, mu);
+      use(x2, mu);
+      use(x3, mu);
+    }
+    for (; i < l; i += 32) use(ld(b + i), mu);
   }
   int slen = (len >= kWarpLong) ? 0 : len;
   int incl = slen;
@@ -192,25 +211,35 @@ __device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult
   }
   int excl = incl - slen;
   int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  for (int t0 = 0; t0 < total; t0 += 32) {
-    int t = t0 + lane;
-    int idx = 0;
+  for (int t0 = 0; t0 < total; t0 += 64) {
+    int ta = t0 + lane, tb = t0 + 32 + lane;
+    int ia = 0, ib = 0;
 #pragma unroll
     for (int step = 16; step >= 1; step >>= 1) {
-      int e = __shfl_sync(0xFFFFFFFFu, excl, idx + step);
-      if (e <= t) idx += step;
+      int ea = __shfl_sync(0xFFFFFFFFu, excl, ia + step);
+      int eb = __shfl_sync(0xFFFFFFFFu, excl, ib + step);
+      if (ea <= ta) ia += step;
+      if (eb <= tb) ib += step;
     }
-    int e0 = __shfl_sync(0xFFFFFFFFu, excl, idx);
-    int64_t b = __shfl_sync(0xFFFFFFFFu, beg, idx);
-    mult_t mu = mult_t();
-    if (NEED_MULT) mu = shfl_mult<mult_t>(mult, idx);
-    if (t < total) f(b + (t - e0), mu);
+    int e0a = __shfl_sync(0xFFFFFFFFu, excl, ia), e0b = __shfl_sync(0xFFFFFFFFu, excl, ib);
+    int64_t ba = __shfl_sync(0xFFFFFFFFu, beg, ia), bb = __shfl_sync(0xFFFFFFFFu, beg, ib);
+    mult_t ma = mult_t(), mb = mult_t();
+    if (NEED_MULT) {
+      ma = shfl_mult<mult_t>(mult, ia);
+      mb = shfl_mult<mult_t>(mult, ib);
+    }
+    const bool va = ta < total, vb = tb < total;
+    decltype(ld(0)) xa{}, xb{};
+    if (va) xa = ld(ba + (ta - e0a));
+    if (vb) xb = ld(bb + (tb - e0b));
+    if (va) use(xa, ma);
+    if (vb) use(xb, mb);
   }
 }
 
 // One warp walks all segments of a task, 32 at a time (small tasks: one task per warp).
-template <class SR, bool MERGE, bool NEED_MULT, class F>
-__device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task &k, F &&f) {
+template <class SR, bool MERGE, bool NEED_MULT, class LD, class USE>
+__device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task &k, LD &&ld, USE &&use) {
   typedef typename SR::b_t mult_t;
   const int lane = lane_id();
   for (int64_t base = k.seg_begin; base < k.seg_end; base += 32) {
@@ -219,15 +248,15 @@ __device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task
     int len = 0;
     mult_t mult = mult_t();
     if (p < k.seg_end) load_segment<SR, MERGE, NEED_MULT>(s, k, p, beg, len, mult);
-    warp_process32<mult_t, NEED_MULT>(beg, len, mult, f);
+    warp_process32<mult_t, NEED_MULT>(beg, len, mult, ld, use);
   }
 }
 
 // Whole-CTA walk with equal shares of PRODUCTS per warp: the CTA stages a chunk of segments in shared memory with the
 // running sum of their lengths; warp w then owns products [w*P/nw, (w+1)*P/nw) of the chunk, wherever the segment
 // boundaries fall, so one very long A-column can no longer stall the other warps at the barrier. All threads must call.
-template <class SR, bool MERGE, bool NEED_MULT, int CH, class F>
-__device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<CH> *q, F &&f) {
+template <class SR, bool MERGE, bool NEED_MULT, int CH, class LD, class USE>
+__device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<CH> *q, LD &&ld, USE &&use) {
   typedef typename SR::b_t mult_t;
   const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = CH >> 5; // blockDim.x == CH
   for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
@@ -284,7 +313,7 @@ __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task 
           if (NEED_MULT) mymult = bits_mult<mult_t>(q->mult[si]);
         }
       }
-      warp_process32<mult_t, NEED_MULT>(mybeg, mylen, mymult, f);
+      warp_process32<mult_t, NEED_MULT>(mybeg, mylen, mymult, ld, use);
     }
   }
   __syncthreads();
@@ -366,13 +395,14 @@ sym_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_
   Task k = load_task(s, t);
   task_segments(s, k);
   int mine = 0;
-  auto f = [&](int64_t pos, typename SR::b_t) {
+  auto ld = [&](int64_t pos) { return k.rows[pos]; };
+  auto use = [&](int row, typename SR::b_t) {
     bool fresh;
-    table_insert<LOG2T>(keys, (unsigned)k.rows[pos], fresh);
+    table_insert<LOG2T>(keys, (unsigned)row, fresh);
     mine += fresh ? 1 : 0;
   };
-  if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, f);
-  else cta_walk<SR, MERGE, false>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), f);
+  if (GROUP_WARPS == 1) warp_walk<SR, MERGE, false>(s, k, ld, use);
+  else cta_walk<SR, MERGE, false>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), ld, use);
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
   if (GROUP_WARPS == 1) {
@@ -438,19 +468,21 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   int t = order[ti];
   Task k = load_task(s, t);
   task_segments(s, k);
-  auto f = [&](int64_t pos, typename SR::b_t mu) {
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  auto ld = [&](int64_t pos) { return RowVal<aval_t>{k.rows[pos], ((const aval_t *)k.vals)[pos]}; };
+  auto use = [&](const RowVal<aval_t> &x, typename SR::b_t mu) {
     bool fresh;
-    int slot = table_insert<LOG2T>(keys, (unsigned)k.rows[pos], fresh);
+    int slot = table_insert<LOG2T>(keys, (unsigned)x.row, fresh);
     acc_t v;
-    if (MERGE) v = SR::from_out(((const typename SR::out_t *)k.vals)[pos]);
-    else v = SR::mul(((const typename SR::a_t *)k.vals)[pos], mu);
+    if (MERGE) v = SR::from_out((typename SR::out_t)x.val);
+    else v = SR::mul((typename SR::a_t)x.val, mu);
     SR::accumulate(&acc[slot], v);
   };
   if (GROUP_WARPS == 1) {
-    warp_walk<SR, MERGE, true>(s, k, f);
+    warp_walk<SR, MERGE, true>(s, k, ld, use);
     __syncwarp();
   } else {
-    cta_walk<SR, MERGE, true>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), f);
+    cta_walk<SR, MERGE, true>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), ld, use);
   }
   // compact the occupied slots
   for (int i = gtid; i < T; i += GT) {
@@ -508,11 +540,12 @@ __device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Ta
   uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
   const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) bm4[i] = make_uint4(0, 0, 0, 0);
-  auto f = [&](int64_t pos, typename SR::b_t) {
-    unsigned r = (unsigned)(k.rows[pos] - rbase);
+  auto ld = [&](int64_t pos) { return k.rows[pos]; };
+  auto use = [&](int row, typename SR::b_t) {
+    unsigned r = (unsigned)(row - rbase);
     atomicOr(&bm[r >> 5], 1u << (r & 31));
   };
-  cta_walk<SR, MERGE, false>(s, k, q, f); // starts and ends with __syncthreads
+  cta_walk<SR, MERGE, false>(s, k, q, ld, use); // starts and ends with __syncthreads
 }
 
 // K2 (bitmap): rows of the window present in the task
@@ -594,20 +627,22 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) acc[i] = SR::identity();
   }
   __syncthreads();
-  auto f = [&](int64_t pos, typename SR::b_t mu) {
-    unsigned r = (unsigned)(k.rows[pos] - rbase);
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  auto ld = [&](int64_t pos) { return RowVal<aval_t>{k.rows[pos], ((const aval_t *)k.vals)[pos]}; };
+  auto use = [&](const RowVal<aval_t> &x, typename SR::b_t mu) {
+    unsigned r = (unsigned)(x.row - rbase);
     unsigned cell = r >> 6, bit = r & 63;
     uint2 w = reinterpret_cast<const uint2 *>(bm)[cell];
     unsigned rank = pre[cell];
     if (bit >= 32) rank += __popc(w.x) + __popc(w.y & ((1u << (bit - 32)) - 1u));
     else rank += __popc(w.x & ((1u << bit) - 1u));
     acc_t v;
-    if (MERGE) v = SR::from_out(((const out_t *)k.vals)[pos]);
-    else v = SR::mul(((const typename SR::a_t *)k.vals)[pos], mu);
+    if (MERGE) v = SR::from_out((out_t)x.val);
+    else v = SR::mul((typename SR::a_t)x.val, mu);
     if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
     else SR::accumulate(&acc[rank], v);
   };
-  cta_walk<SR, MERGE, true>(s, k, &queue, f);
+  cta_walk<SR, MERGE, true>(s, k, &queue, ld, use);
   if (!GMEM_ACC) {
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(acc[i]);
   }
