@@ -380,6 +380,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "bitmap_smem_acc")) return &o.bitmap_smem_acc;
   if (!strcmp(name, "force_path")) return &o.force_path;
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
+  if (!strcmp(name, "debug_numeric")) return &o.debug_numeric;
   return nullptr;
 }
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {

@@ -55,6 +55,7 @@ struct Source {
   // tasks (null task_col: task t is column t over all windows)
   const int32_t *task_col;
   const uint32_t *task_win;
+  int debug; // profiling experiments only (results are wrong when non-zero): 1 = no accumulate, 2 = no rank, 3 = no value load
 };
 
 struct Task {
@@ -612,21 +613,25 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
     while (lo) {
       int b = __ffs(lo) - 1;
       lo &= lo - 1;
-      Cir[obase + run++] = rowbase + b;
+      if (s.debug != 2) Cir[obase + run] = rowbase + b;
+      ++run;
     }
     rowbase += 32;
     while (hi) {
       int b = __ffs(hi) - 1;
       hi &= hi - 1;
-      Cir[obase + run++] = rowbase + b;
+      if (s.debug != 2) Cir[obase + run] = rowbase + b;
+      ++run;
     }
   }
+  if (s.debug == 4) return; // mark + scan + row emission only
   if (GMEM_ACC) {
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(SR::identity());
   } else {
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) acc[i] = SR::identity();
   }
   __syncthreads();
+  if (s.debug == 3) return; // everything but the accumulate walk
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   auto ld = [&](int64_t pos) { return RowVal<aval_t>{k.rows[pos], ((const aval_t *)k.vals)[pos]}; };
   auto use = [&](const RowVal<aval_t> &x, typename SR::b_t mu) {
@@ -639,7 +644,9 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
     acc_t v;
     if (MERGE) v = SR::from_out((out_t)x.val);
     else v = SR::mul((typename SR::a_t)x.val, mu);
-    if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
+    if (s.debug == 1) {
+      if (v == SR::identity() && rank == 0x7FFFFFFFu) Cval[obase] = SR::to_out(v); // keep the work alive, never taken
+    } else if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
     else SR::accumulate(&acc[rank], v);
   };
   cta_walk<SR, MERGE, true>(s, k, &queue, ld, use);

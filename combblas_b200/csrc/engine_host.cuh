@@ -147,6 +147,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   src.N = io.ncolA;
   src.task_col = nullptr;
   src.task_win = nullptr;
+  src.debug = (int)opt.debug_numeric;
 
   // ---- K1: products per column, then tasks
   int64_t *colflop = nullptr;
