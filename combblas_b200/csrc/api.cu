@@ -273,6 +273,88 @@ int mat_submatrix(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *M, int64_t r0, int6
   return CBGPU_OK;
 }
 
+// vertical stack [B_0; B_1; ...] of blocks with equal column count: column j of the result is the concatenation of the
+// parts' columns j with their rows shifted by the rows of the parts above. Used by the fused SUMMA, where
+// sum_i A_i * B_i is computed as ONE multiply [A_0 A_1 ...] * [B_0; B_1; ...] instead of per-stage products + a merge.
+constexpr int kMaxStack = 16;
+struct StackParts {
+  int parts;
+  const int64_t *colptr[kMaxStack];
+  const int32_t *ir[kMaxStack];
+  const unsigned char *val[kMaxStack];
+  int64_t rowoff[kMaxStack];
+};
+__global__ void rowstack_count_kernel(StackParts sp, int64_t n, int64_t *cnt) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int64_t c = 0;
+  for (int i = 0; i < sp.parts; ++i) c += sp.colptr[i][j + 1] - sp.colptr[i][j];
+  cnt[j] = c;
+}
+template <int VB>
+__global__ void rowstack_copy_kernel(StackParts sp, int64_t n, const int64_t *outptr, int32_t *oir, unsigned char *oval) {
+  int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= n) return;
+  const int lane = threadIdx.x & 31;
+  int64_t dst = outptr[j];
+  for (int i = 0; i < sp.parts; ++i) {
+    int64_t src = sp.colptr[i][j], len = sp.colptr[i][j + 1] - src;
+    for (int64_t q = lane; q < len; q += 32) {
+      oir[dst + q] = sp.ir[i][src + q] + (int32_t)sp.rowoff[i];
+      if (VB == 8) reinterpret_cast<uint64_t *>(oval)[dst + q] = reinterpret_cast<const uint64_t *>(sp.val[i])[src + q];
+      else if (VB == 4) reinterpret_cast<uint32_t *>(oval)[dst + q] = reinterpret_cast<const uint32_t *>(sp.val[i])[src + q];
+      else oval[dst + q] = sp.val[i][src + q];
+    }
+    dst += len;
+  }
+}
+
+int mat_rowstack(cbgpu_ctx_impl *ctx, int parts, cbgpu_mat_impl *const *in, cbgpu_mat_impl **out) {
+  if (parts < 1 || parts > kMaxStack) return set_error(ctx, CBGPU_ERR_INVALID, "rowstack supports 1..%d parts", kMaxStack);
+  StackParts sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.parts = parts;
+  int64_t m = 0, nnz = 0;
+  const int64_t n = in[0]->n;
+  for (int i = 0; i < parts; ++i) {
+    if (in[i]->n != n || in[i]->dtype != in[0]->dtype) return set_error(ctx, CBGPU_ERR_DIMMISMATCH, "rowstack: column count or type differs");
+    CB_TRY(ensure_dense_colptr(ctx, in[i]));
+    sp.colptr[i] = in[i]->colptr;
+    sp.ir[i] = in[i]->ir;
+    sp.val[i] = (const unsigned char *)in[i]->numx;
+    sp.rowoff[i] = m;
+    m += in[i]->m;
+    nnz += in[i]->nnz;
+  }
+  if (m >= ((int64_t)1 << 31) - 1) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "stacked block has too many rows");
+  cbgpu_mat_impl *S = nullptr;
+  CB_TRY(mat_alloc(ctx, m, n, nnz, -1, in[0]->dtype, &S));
+  int64_t *cnt = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &cnt, (size_t)n + 1));
+  CB_TRY(dev_alloc_t(ctx, &S->colptr, (size_t)n + 1));
+  if (n > 0) {
+    rowstack_count_kernel<<<nblocks(n), 256, 0, ctx->stream>>>(sp, n, cnt);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  CB_TRY(exclusive_scan_i64(ctx, cnt, S->colptr, n));
+  if (n > 0 && nnz > 0) {
+    const int vb = (int)dtype_size(S->dtype);
+    unsigned nb = nblocks(n * 32);
+    if (vb == 8) rowstack_copy_kernel<8><<<nb, 256, 0, ctx->stream>>>(sp, n, S->colptr, S->ir, (unsigned char *)S->numx);
+    else if (vb == 4) rowstack_copy_kernel<4><<<nb, 256, 0, ctx->stream>>>(sp, n, S->colptr, S->ir, (unsigned char *)S->numx);
+    else rowstack_copy_kernel<1><<<nb, 256, 0, ctx->stream>>>(sp, n, S->colptr, S->ir, (unsigned char *)S->numx);
+    CB_LAUNCH_CHECK(ctx);
+  }
+  int rc = compact_columns(ctx, nullptr, S->colptr, n, &S->jc, &S->cp, &S->nzc);
+  dev_free(ctx, cnt);
+  if (rc != CBGPU_OK) {
+    mat_release(ctx, S);
+    return rc;
+  }
+  *out = S;
+  return CBGPU_OK;
+}
+
 int mat_colconcat(cbgpu_ctx_impl *ctx, int parts, cbgpu_mat_impl *const *in, cbgpu_mat_impl **out) {
   if (parts < 1) return set_error(ctx, CBGPU_ERR_INVALID, "colconcat needs at least one part");
   int64_t n = 0, nnz = 0, nzc = 0;
@@ -380,6 +462,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "bitmap_smem_acc")) return &o.bitmap_smem_acc;
   if (!strcmp(name, "force_path")) return &o.force_path;
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
+  if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "debug_numeric")) return &o.debug_numeric;
   return nullptr;
 }

@@ -17,6 +17,8 @@
 
 namespace cbgpu {
 int mat_colslice(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *M, int64_t c0, int64_t c1, cbgpu_mat_impl **out);
+int mat_colconcat(cbgpu_ctx_impl *ctx, int parts, cbgpu_mat_impl *const *in, cbgpu_mat_impl **out);
+int mat_rowstack(cbgpu_ctx_impl *ctx, int parts, cbgpu_mat_impl *const *in, cbgpu_mat_impl **out);
 
 struct NcclApi {
   void *handle = nullptr;
@@ -267,8 +269,52 @@ static int summa_layer(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
     essB = {B->nnz, B->nzc, B->m, B->n};
   }
   ds->ms_bcast += tm.stop();
-  std::vector<cbgpu_mat *> partial;
   int rc = CBGPU_OK;
+  if (stages > 1 && ctx->opt.summa_fused) {
+    // Fused SUMMA: receive the blocks of every stage, then compute sum_i A_i (x) B_i as ONE local multiply
+    // [A_0 A_1 ...] (x) [B_0; B_1; ...]. Same products and the same result as the stage loop + MultiwayMerge
+    // (ParFriends.h:1482-1548), but the partial results are never materialised and never merged.
+    std::vector<cbgpu_mat *> Ablk(stages, nullptr), Bblk(stages, nullptr), Arecv(stages, nullptr), Brecv(stages, nullptr);
+    tm.start();
+    for (int i = 0; i < stages && rc == CBGPU_OK; ++i) {
+      rc = bcast_block(ctx, comm->row, i, g.my_col, A, &essA[4 * i], ta, &Arecv[i], &ds->bytes_bcast);
+      if (rc == CBGPU_OK) rc = bcast_block(ctx, comm->col, i, g.my_row, B, &essB[4 * i], tb, &Brecv[i], &ds->bytes_bcast);
+      Ablk[i] = Arecv[i] ? Arecv[i] : const_cast<cbgpu_mat *>(A);
+      Bblk[i] = Brecv[i] ? Brecv[i] : const_cast<cbgpu_mat *>(B);
+      if (rc == CBGPU_OK && Ablk[i]->n != Bblk[i]->m)
+        rc = set_error(ctx, CBGPU_ERR_DIMMISMATCH, "stage %d: inner block dimensions differ (%lld vs %lld)", i, (long long)Ablk[i]->n, (long long)Bblk[i]->m);
+      ds->stages++;
+    }
+    ds->ms_bcast += tm.stop();
+    cbgpu_mat *Acat = nullptr, *Bcat = nullptr;
+    if (rc == CBGPU_OK) {
+      tm.start();
+      rc = mat_colconcat(ctx, stages, Ablk.data(), &Acat);
+      if (rc == CBGPU_OK) rc = mat_rowstack(ctx, stages, Bblk.data(), &Bcat);
+      for (int i = 0; i < stages; ++i) {
+        mat_release(ctx, Arecv[i]);
+        mat_release(ctx, Brecv[i]);
+        Arecv[i] = Brecv[i] = nullptr;
+      }
+      ds->ms_merge += tm.stop(); // time of assembling the stacked operands
+    }
+    if (rc == CBGPU_OK) {
+      cbgpu_stats st;
+      memset(&st, 0, sizeof(st));
+      tm.start();
+      rc = cbgpu_spgemm_local(ctx, semiring, Acat, Bcat, C, &st);
+      ds->ms_multiply += tm.stop();
+      if (rc == CBGPU_OK) add_stats(ds->local, st);
+    }
+    mat_release(ctx, Acat);
+    mat_release(ctx, Bcat);
+    for (int i = 0; i < stages; ++i) {
+      mat_release(ctx, Arecv[i]);
+      mat_release(ctx, Brecv[i]);
+    }
+    return rc;
+  }
+  std::vector<cbgpu_mat *> partial;
   for (int i = 0; i < stages && rc == CBGPU_OK; ++i) {
     cbgpu_mat *Ar = nullptr, *Br = nullptr;
     const cbgpu_mat *Ause = A, *Buse = B;

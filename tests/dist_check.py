@@ -49,6 +49,12 @@ def main():
             dC, st = comm.summa2d(sr, dA, dB)
         else:
             dC, st = comm.summa3d(sr, dA, dB)
+        if grid.grid_cols > 1:  # the stage loop + merge formulation must give the same block as the fused one
+            ctx.set_option("summa_fused", 0)
+            dC2, _ = (comm.summa2d if layers == 1 else comm.summa3d)(sr, dA, dB)
+            ctx.set_option("summa_fused", 1)
+            assert ctx.checksum(dC2)[0] == ctx.checksum(dC)[0] and dC2.nnz == dC.nnz, "fused and staged SUMMA differ"
+            dC2.free()
         rows, cols, vals = ctx.download_coo(dC)
         m_loc, n_loc = dC.shape
         want_global = orc.spgemm(Csc.from_scipy(GA, ta), Csc.from_scipy(GB, tb), sr)
