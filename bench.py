@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=int, default=int(os.environ.get("CBGPU_BENCH_SCALE", "20")))
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("CBGPU_BENCH_SCALE", "22")))
     ap.add_argument("--phases", type=int, default=0, help="column slabs of B/C per step (0 = automatic from the symbolic pass)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
