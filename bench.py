@@ -246,7 +246,7 @@ def main():
         per_rank = est_nnz * 12 / (world // layers)
         phases = max(1, int(np.ceil(per_rank / 40e9)))
     phases = max(1, phases)
-    slabs = ctx.colsplit(Bloc, phases) if phases > 1 else None
+    slabs = ctx.colsplit(Bloc, phases) if (world == 1 and phases > 1) else None
 
     class SlabResult:
         """what a phased step leaves behind: per-slab essentials and checksums (the slabs themselves are consumed)"""
@@ -290,23 +290,13 @@ def main():
         if world == 1:
             Cd, st = ctx.spgemm(cb.PlusTimesSRing_f64, Aloc, Bloc, want_stats=True)
             return Cd, st, None
-        mult = comm.summa2d if layers == 1 else comm.summa3d
-        if phases == 1:
-            Cd, ds = mult(cb.PlusTimesSRing_f64, Aloc, Bloc)
-            return Cd, ds.local, ds
-        # phased distributed multiply (MemEfficientSpGEMM / MemEfficientSpGEMM3D, ParFriends.h:579-768, :3774-4164):
-        # one SUMMA per column slab of B; the A blocks are broadcast again in every phase, as the reference does
-        res, acc, dacc = SlabResult(), None, None
-        for Bs in slabs:
-            Cs, ds = mult(cb.PlusTimesSRing_f64, Aloc, Bs)
-            inf = Cs.info()
-            res.nnz += inf.nnz
-            res.nzc += inf.nzc
-            Cs.free()
-            acc = add_stats(acc, ds.local)
-            dacc = add_stats(dacc, ds)
-        dacc.local = acc
-        return res, acc, dacc
+        # distributed: cbgpu_summa_phased = MemEfficientSpGEMM / MemEfficientSpGEMM3D without the pruning (one SUMMA per
+        # column slab of B, slabs consumed as they finish; with layers the fiber stage of slab p overlaps slab p+1)
+        results, _, ds = comm.summa_phased(cb.PlusTimesSRing_f64, Aloc, Bloc, phases)
+        res = SlabResult()
+        res.nnz = sum(r.nnz for r in results)
+        res.nzc = sum(r.nzc for r in results)
+        return res, ds.local, ds
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 

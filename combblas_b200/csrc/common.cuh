@@ -47,11 +47,6 @@ struct cbgpu_ctx {
   int max_smem_optin = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[2 * CBGPU_K_COUNT] = {};
-  // large-block cache in front of the stream-ordered pool: result arrays of tens of GB are recycled between
-  // multiplies (and between the column slabs of a phased multiply) without going back to the driver
-  std::map<void *, size_t> big_live;              // live large blocks -> size
-  std::multimap<size_t, void *> big_free;         // cached large blocks by size
-  size_t big_free_bytes = 0;
 };
 
 struct cbgpu_mat {

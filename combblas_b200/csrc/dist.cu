@@ -9,7 +9,10 @@
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2 -- inside a torch process this is torch's own copy), so
 // the library loads on machines without NCCL and single-GPU use never touches it.
+#include <condition_variable>
 #include <dlfcn.h>
+#include <mutex>
+#include <thread>
 #include <math.h>
 #include <nccl.h>
 #include "common.cuh"
@@ -81,6 +84,7 @@ using namespace cbgpu;
 struct cbgpu_comm {
   cbgpu_grid grid;
   ncclComm_t world = nullptr, row = nullptr, col = nullptr, fiber = nullptr;
+  cbgpu_ctx *ctx2 = nullptr; // second context (own stream) for the fiber stage of the pipelined phased driver
 };
 
 extern "C" {
@@ -174,6 +178,7 @@ int cbgpu_comm_create(cbgpu_ctx *ctx, const cbgpu_grid *grid, const void *id128,
 
 int cbgpu_comm_destroy(cbgpu_comm *c) {
   if (!c) return CBGPU_OK;
+  if (c->ctx2) cbgpu_destroy(c->ctx2);
   if (nccl().ok) {
     if (c->row) nccl().CommDestroy(c->row);
     if (c->col) nccl().CommDestroy(c->col);
@@ -370,6 +375,107 @@ static int summa_layer(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
   return rc;
 }
 
+// The fiber stage of the 3D algorithm (ParFriends.h:3578-3642): cut this layer's partial product Cl (consumed) into L
+// column slabs, ship slab l to fiber rank l, merge what arrives with the own slab. Runs entirely on ctx's stream.
+static int fiber_reduce(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cbgpu_mat *Cl, cbgpu_mat **C, cbgpu_dist_stats *ds) {
+  const cbgpu_grid &g = comm->grid;
+  const int L = g.layers;
+  Timer tm(ctx->stream);
+  int rc = CBGPU_OK;
+  // ---- cut the layer result into L column slabs (CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576-609;
+  //      send ranges ParFriends->h:3578-3600); slab l belongs to fiber rank l
+  tm.start();
+  std::vector<cbgpu_mat *> slab(L, nullptr), recv(L, nullptr);
+  for (int l = 0; l < L && rc == CBGPU_OK; ++l) {
+    int64_t c0, c1;
+    cbgpu_block_range(Cl->n, L, l, &c0, &c1);
+    rc = mat_colslice(ctx, Cl, c0, c1, &slab[l]);
+  }
+  mat_release(ctx, Cl);
+  // ---- sizes: every rank tells every fiber peer {nnz, nzc} of the slab it will send (ParFriends->h:3602)
+  std::vector<int64_t> sizes((size_t)2 * L * L, 0);
+  if (rc == CBGPU_OK) {
+    std::vector<int64_t> mine((size_t)2 * L);
+    for (int l = 0; l < L; ++l) { mine[2 * l] = slab[l]->nnz; mine[2 * l + 1] = slab[l]->nzc; }
+    int64_t *d = nullptr;
+    rc = dev_alloc_t(ctx, &d, (size_t)2 * L * (L + 1));
+    if (rc == CBGPU_OK) {
+      cudaMemcpyAsync(d, mine.data(), sizeof(int64_t) * 2 * L, cudaMemcpyHostToDevice, ctx->stream);
+      ncclResult_t r = nccl().AllGather(d, d + 2 * L, (size_t)2 * L, ncclInt64, comm->fiber, ctx->stream);
+      if (r != ncclSuccess) rc = set_error(ctx, CBGPU_ERR_NCCL, "fiber allgather failed: %s", nccl().GetErrorString(r));
+      cudaMemcpyAsync(sizes.data(), d + 2 * L, sizeof(int64_t) * 2 * L * L, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      dev_free(ctx, d);
+    }
+  }
+  // ---- exchange (ParFriends->h:3612): grouped send/recv of the four arrays per peer
+  const int me = g.my_layer;
+  int tc = slab[0] ? slab[0]->dtype : CBGPU_F64;
+  const size_t vb = dtype_size(tc);
+  if (rc == CBGPU_OK) {
+    for (int p = 0; p < L && rc == CBGPU_OK; ++p) {
+      if (p == me) continue;
+      int64_t nnz = sizes[(size_t)2 * L * p + 2 * me], nzc = sizes[(size_t)2 * L * p + 2 * me + 1];
+      rc = mat_alloc(ctx, slab[me]->m, slab[me]->n, nnz, nzc, tc, &recv[p]);
+      if (rc == CBGPU_OK && nzc == 0) cudaMemsetAsync(recv[p]->cp, 0, 8, ctx->stream);
+    }
+  }
+  if (rc == CBGPU_OK) {
+    ncclResult_t r = nccl().GroupStart();
+    for (int p = 0; p < L && r == ncclSuccess; ++p) {
+      if (p == me) continue;
+      cbgpu_mat *S = slab[p], *R = recv[p];
+      if (S->nnz > 0) {
+        r = nccl().Send(S->jc, (size_t)S->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Send(S->cp, (size_t)(S->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Send(S->ir, (size_t)S->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Send(S->numx, (size_t)S->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+        ds->bytes_fiber += S->nzc * 16 + 8 + S->nnz * (4 + (int64_t)vb);
+      }
+      if (r == ncclSuccess && R->nnz > 0) {
+        r = nccl().Recv(R->jc, (size_t)R->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Recv(R->cp, (size_t)(R->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Recv(R->ir, (size_t)R->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
+        if (r == ncclSuccess) r = nccl().Recv(R->numx, (size_t)R->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+      }
+    }
+    ncclResult_t r2 = nccl().GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess)
+      rc = set_error(ctx, CBGPU_ERR_NCCL, "fiber exchange failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
+  }
+  ds->ms_fiber_exchange += tm.stop();
+  // ---- merge what arrived with my own slab (ParFriends->h:3642)
+  if (rc == CBGPU_OK) {
+    tm.start();
+    std::vector<cbgpu_mat *> lists;
+    for (int p = 0; p < L; ++p) {
+      cbgpu_mat *M = (p == me) ? slab[me] : recv[p];
+      if (M && M->nnz > 0) lists.push_back(M);
+    }
+    if (lists.empty()) {
+      *C = slab[me];
+      slab[me] = nullptr;
+    } else if (lists.size() == 1) {
+      *C = lists[0];
+      for (int p = 0; p < L; ++p) {
+        if (slab[p] == lists[0]) slab[p] = nullptr;
+        if (recv[p] == lists[0]) recv[p] = nullptr;
+      }
+    } else {
+      cbgpu_stats st;
+      memset(&st, 0, sizeof(st));
+      rc = cbgpu_merge(ctx, semiring, (int)lists.size(), lists.data(), C, &st);
+      ds->local.kernel_launches += st.kernel_launches;
+    }
+    ds->ms_fiber_merge += tm.stop();
+  }
+  for (int p = 0; p < L; ++p) {
+    mat_release(ctx, slab[p]);
+    mat_release(ctx, recv[p]);
+  }
+  return rc;
+}
+
 } // namespace cbgpu
 
 extern "C" {
@@ -393,112 +499,128 @@ int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
                   cbgpu_dist_stats *stats) {
   if (!ctx || !comm || !A || !B || !C) return CBGPU_ERR_INVALID;
   CB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const cbgpu_grid &g = comm->grid;
-  const int L = g.layers;
   cbgpu_dist_stats ds;
   memset(&ds, 0, sizeof(ds));
-  Timer all(ctx->stream), tm(ctx->stream);
+  Timer all(ctx->stream);
   all.start();
   cbgpu_mat *Cl = nullptr; // this layer's partial product: full block shape
   CB_TRY(summa_layer(ctx, comm, semiring, A, B, &Cl, &ds));
-  if (L == 1) {
-    *C = Cl;
-    ds.ms_total = all.stop();
-    if (stats) *stats = ds;
-    return CBGPU_OK;
-  }
-  // ---- cut the layer result into L column slabs (CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576-609;
-  //      send ranges ParFriends.h:3578-3600); slab l belongs to fiber rank l
   int rc = CBGPU_OK;
-  tm.start();
-  std::vector<cbgpu_mat *> slab(L, nullptr), recv(L, nullptr);
-  for (int l = 0; l < L && rc == CBGPU_OK; ++l) {
-    int64_t c0, c1;
-    cbgpu_block_range(Cl->n, L, l, &c0, &c1);
-    rc = mat_colslice(ctx, Cl, c0, c1, &slab[l]);
+  if (comm->grid.layers == 1) *C = Cl;
+  else rc = fiber_reduce(ctx, comm, semiring, Cl, C, &ds);
+  ds.ms_total = all.stop();
+  if (stats) *stats = ds;
+  return rc;
+}
+
+// Phased distributed multiply (MemEfficientSpGEMM ParFriends.h:453-777, MemEfficientSpGEMM3D :3674-4170): B's local columns
+// are cut into `phases` slabs (ColSplit rule) and one SUMMA runs per slab, so that C never has to exist as a whole.
+// With several layers the two halves of a phase are PIPELINED: a second host thread with its own context and stream
+// runs the fiber exchange + merge of slab p (NVLink traffic, few SMs) while this thread already multiplies slab p+1.
+int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                       int want_checksum, cbgpu_mat **slabs, cbgpu_slab_result *results, cbgpu_dist_stats *stats) {
+  if (!ctx || !comm || !A || !B || phases < 1 || !results) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = comm->grid.layers;
+  cbgpu_dist_stats ds;
+  memset(&ds, 0, sizeof(ds));
+  Timer all(ctx->stream);
+  all.start();
+  std::vector<cbgpu_mat *> Bs(phases, nullptr);
+  if (phases == 1) Bs[0] = const_cast<cbgpu_mat *>(B);
+  else CB_TRY(cbgpu_mat_colsplit(ctx, B, phases, Bs.data()));
+  if (L > 1 && !comm->ctx2) {
+    int rc2 = cbgpu_create(ctx->device, nullptr, &comm->ctx2);
+    if (rc2 != CBGPU_OK) return set_error(ctx, rc2, "could not create the second context of the pipeline");
+    comm->ctx2->opt = ctx->opt;
   }
-  mat_release(ctx, Cl);
-  // ---- sizes: every rank tells every fiber peer {nnz, nzc} of the slab it will send (ParFriends.h:3602)
-  std::vector<int64_t> sizes((size_t)2 * L * L, 0);
-  if (rc == CBGPU_OK) {
-    std::vector<int64_t> mine((size_t)2 * L);
-    for (int l = 0; l < L; ++l) { mine[2 * l] = slab[l]->nnz; mine[2 * l + 1] = slab[l]->nzc; }
-    int64_t *d = nullptr;
-    rc = dev_alloc_t(ctx, &d, (size_t)2 * L * (L + 1));
-    if (rc == CBGPU_OK) {
-      cudaMemcpyAsync(d, mine.data(), sizeof(int64_t) * 2 * L, cudaMemcpyHostToDevice, ctx->stream);
-      ncclResult_t r = nccl().AllGather(d, d + 2 * L, (size_t)2 * L, ncclInt64, comm->fiber, ctx->stream);
-      if (r != ncclSuccess) rc = set_error(ctx, CBGPU_ERR_NCCL, "fiber allgather failed: %s", nccl().GetErrorString(r));
-      cudaMemcpyAsync(sizes.data(), d + 2 * L, sizeof(int64_t) * 2 * L * L, cudaMemcpyDeviceToHost, ctx->stream);
-      cudaStreamSynchronize(ctx->stream);
-      dev_free(ctx, d);
-    }
-  }
-  // ---- exchange (ParFriends.h:3612): grouped send/recv of the four arrays per peer
-  const int me = g.my_layer;
-  int tc = slab[0] ? slab[0]->dtype : CBGPU_F64;
-  const size_t vb = dtype_size(tc);
-  if (rc == CBGPU_OK) {
-    for (int p = 0; p < L && rc == CBGPU_OK; ++p) {
-      if (p == me) continue;
-      int64_t nnz = sizes[(size_t)2 * L * p + 2 * me], nzc = sizes[(size_t)2 * L * p + 2 * me + 1];
-      rc = mat_alloc(ctx, slab[me]->m, slab[me]->n, nnz, nzc, tc, &recv[p]);
-      if (rc == CBGPU_OK && nzc == 0) cudaMemsetAsync(recv[p]->cp, 0, 8, ctx->stream);
-    }
-  }
-  if (rc == CBGPU_OK) {
-    ncclResult_t r = nccl().GroupStart();
-    for (int p = 0; p < L && r == ncclSuccess; ++p) {
-      if (p == me) continue;
-      cbgpu_mat *S = slab[p], *R = recv[p];
-      if (S->nnz > 0) {
-        r = nccl().Send(S->jc, (size_t)S->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-        if (r == ncclSuccess) r = nccl().Send(S->cp, (size_t)(S->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-        if (r == ncclSuccess) r = nccl().Send(S->ir, (size_t)S->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
-        if (r == ncclSuccess) r = nccl().Send(S->numx, (size_t)S->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
-        ds.bytes_fiber += S->nzc * 16 + 8 + S->nnz * (4 + (int64_t)vb);
+  struct Item { cbgpu_mat *Cl; cudaEvent_t ready; };
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<Item> queue((size_t)phases, Item{nullptr, nullptr});
+  int produced = 0, consumed = 0;
+  bool producer_failed = false;
+  int worker_rc = CBGPU_OK;
+  cbgpu_dist_stats wds;
+  memset(&wds, 0, sizeof(wds));
+  auto finish_slab = [&](cbgpu_ctx *c, int p, cbgpu_mat *Cp) -> int {
+    results[p].nnz = Cp->nnz;
+    results[p].nzc = Cp->nzc;
+    results[p].pattern_sum = results[p].value_sum = 0;
+    int rc = CBGPU_OK;
+    if (want_checksum) rc = cbgpu_mat_checksum(c, Cp, &results[p].pattern_sum, &results[p].value_sum);
+    if (slabs) slabs[p] = Cp;
+    else mat_release(c, Cp);
+    return rc;
+  };
+  std::thread worker;
+  if (L > 1) {
+    worker = std::thread([&]() {
+      cbgpu_ctx *c2 = comm->ctx2;
+      cudaSetDevice(c2->device);
+      for (int p = 0; p < phases; ++p) {
+        Item it;
+        {
+          std::unique_lock<std::mutex> lock(mu);
+          cv.wait(lock, [&] { return produced > p || producer_failed; });
+          if (produced <= p) return; // the producer gave up
+          it = queue[p];
+        }
+        cudaStreamWaitEvent(c2->stream, it.ready, 0);
+        cbgpu_mat *Cp = nullptr;
+        int rc = fiber_reduce(c2, comm, semiring, it.Cl, &Cp, &wds);
+        if (rc == CBGPU_OK) rc = finish_slab(c2, p, Cp);
+        cudaStreamSynchronize(c2->stream);
+        cudaEventDestroy(it.ready);
+        {
+          std::lock_guard<std::mutex> lock(mu);
+          consumed = p + 1;
+          if (rc != CBGPU_OK && worker_rc == CBGPU_OK) worker_rc = rc;
+        }
+        cv.notify_all();
+        if (rc != CBGPU_OK) return;
       }
-      if (r == ncclSuccess && R->nnz > 0) {
-        r = nccl().Recv(R->jc, (size_t)R->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-        if (r == ncclSuccess) r = nccl().Recv(R->cp, (size_t)(R->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-        if (r == ncclSuccess) r = nccl().Recv(R->ir, (size_t)R->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
-        if (r == ncclSuccess) r = nccl().Recv(R->numx, (size_t)R->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
-      }
-    }
-    ncclResult_t r2 = nccl().GroupEnd();
-    if (r != ncclSuccess || r2 != ncclSuccess)
-      rc = set_error(ctx, CBGPU_ERR_NCCL, "fiber exchange failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
+    });
   }
-  ds.ms_fiber_exchange = tm.stop();
-  // ---- merge what arrived with my own slab (ParFriends.h:3642)
-  if (rc == CBGPU_OK) {
-    tm.start();
-    std::vector<cbgpu_mat *> lists;
-    for (int p = 0; p < L; ++p) {
-      cbgpu_mat *M = (p == me) ? slab[me] : recv[p];
-      if (M && M->nnz > 0) lists.push_back(M);
+  int rc = CBGPU_OK;
+  for (int p = 0; p < phases && rc == CBGPU_OK; ++p) {
+    cbgpu_mat *Cl = nullptr;
+    rc = summa_layer(ctx, comm, semiring, A, Bs[p], &Cl, &ds);
+    if (rc != CBGPU_OK) break;
+    if (L == 1) {
+      rc = finish_slab(ctx, p, Cl);
+      continue;
     }
-    if (lists.empty()) {
-      *C = slab[me];
-      slab[me] = nullptr;
-    } else if (lists.size() == 1) {
-      *C = lists[0];
-      for (int p = 0; p < L; ++p) {
-        if (slab[p] == lists[0]) slab[p] = nullptr;
-        if (recv[p] == lists[0]) recv[p] = nullptr;
-      }
-    } else {
-      cbgpu_stats st;
-      memset(&st, 0, sizeof(st));
-      rc = cbgpu_merge(ctx, semiring, (int)lists.size(), lists.data(), C, &st);
-      ds.local.kernel_launches += st.kernel_launches;
+    Item it{Cl, nullptr};
+    cudaEventCreateWithFlags(&it.ready, cudaEventDisableTiming);
+    cudaEventRecord(it.ready, ctx->stream);
+    {
+      std::unique_lock<std::mutex> lock(mu);
+      queue[p] = it;
+      produced = p + 1;
+      cv.notify_all();
+      // keep at most one finished layer result waiting (memory) and stop early when the consumer failed
+      cv.wait(lock, [&] { return consumed >= p || worker_rc != CBGPU_OK; });
+      if (worker_rc != CBGPU_OK) rc = worker_rc;
     }
-    ds.ms_fiber_merge = tm.stop();
   }
-  for (int p = 0; p < L; ++p) {
-    mat_release(ctx, slab[p]);
-    mat_release(ctx, recv[p]);
+  if (L > 1) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (rc != CBGPU_OK) producer_failed = true;
+    }
+    cv.notify_all();
+    worker.join();
+    if (rc == CBGPU_OK) rc = worker_rc;
+    if (worker_rc != CBGPU_OK) ctx->last_error = comm->ctx2->last_error;
+    ds.ms_fiber_exchange = wds.ms_fiber_exchange;
+    ds.ms_fiber_merge = wds.ms_fiber_merge;
+    ds.bytes_fiber = wds.bytes_fiber;
+    ds.local.kernel_launches += wds.local.kernel_launches + comm->ctx2->launches;
+    comm->ctx2->launches = 0;
   }
+  if (phases > 1)
+    for (int p = 0; p < phases; ++p) mat_release(ctx, Bs[p]);
   ds.ms_total = all.stop();
   if (stats) *stats = ds;
   return rc;

@@ -1,6 +1,7 @@
 // Device-wide helper kernels: scan, task binning, dense column index, row-window table, column compaction.
 // Hand-written (no CUB/Thrust) so every launch on the hot path is ours and counted.
 #include <stdarg.h>
+#include <mutex>
 #include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 #include "util.cuh"
@@ -18,30 +19,52 @@ int set_error(cbgpu_ctx_impl *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
-constexpr size_t kBigBlock = (size_t)64 << 20; // blocks from 64 MiB are cached by the context
+constexpr size_t kBigBlock = (size_t)64 << 20; // blocks from 64 MiB are cached per device
+
+// Large-block cache in front of the stream-ordered pool: result arrays of tens of GB are recycled between multiplies
+// (and between the column slabs of a phased multiply) without going back to the driver. The cache is per device and
+// shared by all contexts (the pipelined 3D driver runs two contexts on two host threads); every cached block carries
+// an event recorded on the stream that released it, and the stream that takes it waits on that event.
+struct BigCache {
+  std::mutex mu;
+  std::map<void *, size_t> live;
+  struct Entry { void *p; cudaEvent_t ev; };
+  std::multimap<size_t, Entry> free_blocks;
+};
+static BigCache &big_cache(int device) {
+  static BigCache caches[64];
+  return caches[device & 63];
+}
 
 static void flush_big_cache(cbgpu_ctx_impl *ctx) {
-  for (auto &kv : ctx->big_free) cudaFreeAsync(kv.second, ctx->stream);
-  ctx->big_free.clear();
-  ctx->big_free_bytes = 0;
+  BigCache &bc = big_cache(ctx->device);
+  std::lock_guard<std::mutex> lock(bc.mu);
+  for (auto &kv : bc.free_blocks) {
+    cudaStreamWaitEvent(ctx->stream, kv.second.ev, 0);
+    cudaFreeAsync(kv.second.p, ctx->stream);
+    cudaEventDestroy(kv.second.ev);
+  }
+  bc.free_blocks.clear();
 }
 
 int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
+  BigCache &bc = big_cache(ctx->device);
   if (bytes >= kBigBlock) {
-    // smallest cached block that fits and wastes at most a quarter
-    auto it = ctx->big_free.lower_bound(bytes);
-    if (it != ctx->big_free.end() && it->first <= bytes + bytes / 4) {
-      *p = it->second;
-      ctx->big_live[*p] = it->first;
-      ctx->big_free_bytes -= it->first;
-      ctx->big_free.erase(it);
+    std::lock_guard<std::mutex> lock(bc.mu);
+    auto it = bc.free_blocks.lower_bound(bytes); // smallest cached block that fits and wastes at most a quarter
+    if (it != bc.free_blocks.end() && it->first <= bytes + bytes / 4) {
+      *p = it->second.p;
+      cudaStreamWaitEvent(ctx->stream, it->second.ev, 0);
+      cudaEventDestroy(it->second.ev);
+      bc.live[*p] = it->first;
+      bc.free_blocks.erase(it);
       return CBGPU_OK;
     }
   }
   cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
-  if (e != cudaSuccess && !ctx->big_free.empty()) { // give the cached blocks back and try once more
+  if (e != cudaSuccess) { // give the cached blocks back and try once more
     cudaGetLastError();
     flush_big_cache(ctx);
     cudaStreamSynchronize(ctx->stream);
@@ -52,19 +75,27 @@ int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes) {
     return set_error(ctx, e == cudaErrorMemoryAllocation ? CBGPU_ERR_NOMEM : CBGPU_ERR_CUDA,
                      "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
   }
-  if (bytes >= kBigBlock) ctx->big_live[*p] = bytes;
+  if (bytes >= kBigBlock) {
+    std::lock_guard<std::mutex> lock(bc.mu);
+    bc.live[*p] = bytes;
+  }
   return CBGPU_OK;
 }
 
 int dev_free(cbgpu_ctx_impl *ctx, void *p) {
   if (!p) return CBGPU_OK;
-  auto it = ctx->big_live.find(p);
-  if (it != ctx->big_live.end()) {
-    // stream order makes the reuse safe: every consumer of this block was enqueued on ctx->stream before now
-    ctx->big_free.emplace(it->second, p);
-    ctx->big_free_bytes += it->second;
-    ctx->big_live.erase(it);
-    return CBGPU_OK;
+  BigCache &bc = big_cache(ctx->device);
+  {
+    std::lock_guard<std::mutex> lock(bc.mu);
+    auto it = bc.live.find(p);
+    if (it != bc.live.end()) {
+      BigCache::Entry e{p, nullptr};
+      cudaEventCreateWithFlags(&e.ev, cudaEventDisableTiming);
+      cudaEventRecord(e.ev, ctx->stream); // every consumer of this block was enqueued on ctx->stream before now
+      bc.free_blocks.emplace(it->second, e);
+      bc.live.erase(it);
+      return CBGPU_OK;
+    }
   }
   CB_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
   return CBGPU_OK;

@@ -69,6 +69,10 @@ class DistStats(C.Structure):
         return d
 
 
+class SlabResult(C.Structure):
+    _fields_ = [("nnz", C.c_int64), ("nzc", C.c_int64), ("pattern_sum", C.c_uint64), ("value_sum", C.c_uint64)]
+
+
 class Grid(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("layers", C.c_int), ("grid_rows", C.c_int),
                 ("grid_cols", C.c_int), ("my_layer", C.c_int), ("my_row", C.c_int), ("my_col", C.c_int)]
@@ -113,6 +117,7 @@ SIGNATURES = {
     "cbgpu_comm_destroy": (C.c_int, [_P]),
     "cbgpu_summa2d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
     "cbgpu_summa3d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
+    "cbgpu_summa_phased": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(SlabResult), C.POINTER(DistStats)]),
     "cbgpu_rmat_edges_host": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, _P, _P]),
     "cbgpu_gen_rmat": (C.c_int, [_P, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.c_int, C.POINTER(_P)]),
@@ -369,6 +374,16 @@ class Comm:
         st = DistStats()
         self.ctx._check(self.ctx.lib.cbgpu_summa3d(self.ctx.handle, self.handle, sr, A.handle, B.handle, C.byref(h), C.byref(st)))
         return DeviceMatrix(self.ctx, h), st
+
+    def summa_phased(self, sr, A: DeviceMatrix, B: DeviceMatrix, phases: int, want_checksum=False, keep=False):
+        """MemEfficientSpGEMM[3D]-style phased multiply; returns (slab results, kept slabs or None, stats)."""
+        res = (SlabResult * phases)()
+        st = DistStats()
+        arr = (_P * phases)() if keep else None
+        self.ctx._check(self.ctx.lib.cbgpu_summa_phased(self.ctx.handle, self.handle, sr, A.handle, B.handle, phases,
+                                                        int(want_checksum), arr, res, C.byref(st)))
+        kept = [DeviceMatrix(self.ctx, _P(arr[i])) for i in range(phases)] if keep else None
+        return list(res), kept, st
 
     def destroy(self):
         if self.handle is not None:

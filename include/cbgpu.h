@@ -211,6 +211,18 @@ int cbgpu_summa2d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
 int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B,
                   cbgpu_mat **C, cbgpu_dist_stats *stats);
 
+/* Phased distributed multiply: replaces MemEfficientSpGEMM (ParFriends.h:453-777; without the pruning, which stays with
+ * the caller) and MemEfficientSpGEMM3D (:3674-4170). B's local columns are cut into `phases` slabs (ColSplit rule), one
+ * SUMMA per slab. With several layers the fiber exchange + merge of slab p overlaps the multiply of slab p+1 (second
+ * host thread, second stream). results[p] receives the essentials (and, if asked, the order-independent checksums) of
+ * slab p; slabs == NULL means every slab is consumed (freed) as soon as it is finished, otherwise slabs[p] is handed out. */
+typedef struct {
+  int64_t nnz, nzc;
+  uint64_t pattern_sum, value_sum;
+} cbgpu_slab_result;
+int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                       int want_checksum, cbgpu_mat **slabs, cbgpu_slab_result *results, cbgpu_dist_stats *stats);
+
 /* ---------------------------------------------------------------- synthetic inputs (own seeded generators)
  * R-MAT (Graph500 initiator a,b,c,d as in 3DSpGEMM/mpipspgemm.cpp:126-133), duplicates summed into the value
  * (SpTuples.cpp:70-124 semantics), vertex scramble by a seeded bijection. Device generation; the identical

@@ -140,10 +140,16 @@ def main():
         tot = torch.tensor([sum(p.nnz for p in pieces), whole.nnz], device="cuda")
         dist.all_reduce(tot)
         same = int(tot[0].item()) == int(tot[1].item())
+    # the C-level phased driver (pipelined fiber stage when layers > 1) must reproduce the slab-by-slab results
+    res, kept, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=True)
+    for r, kp, pc in zip(res, kept, pieces):
+        same = same and r.nnz == pc.nnz and r.pattern_sum == ctx.checksum(pc)[0] and ctx.checksum(kp) == ctx.checksum(pc)
+    res2, _, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=False)
+    same = same and [(r.nnz, r.pattern_sum) for r in res2] == [(r.nnz, r.pattern_sum) for r in res]
     t = torch.tensor([0 if same else 1], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} phased expansion (3 slabs) nnz={whole.nnz}", flush=True)
+        print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} phased expansion (3 slabs, staged + pipelined driver) nnz={whole.nnz}", flush=True)
     failures += int(t.item())
     comm.destroy()
     dist.barrier()
