@@ -62,16 +62,30 @@ struct SharedRows {
   __device__ __forceinline__ int operator[](int i) const { return p[i]; }
 };
 
+// merge-path start of every tile, one thread per tile: the dependent global-memory binary search is paid once, in
+// parallel over all tiles, instead of as a serial latency chain at the head of every merge CTA (and it serves both passes)
+static __global__ void merge_partition_kernel(MergeCols m, const int32_t *tile_col, const int64_t *first, int64_t ntiles,
+                                              int2 *tile_start) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int col = tile_col[t];
+  const int tl = (int)(t - first[col]);
+  const int64_t xb = m.xcp[col], yb = m.ycp[col];
+  const int nx = (int)(m.xcp[col + 1] - xb), ny = (int)(m.ycp[col + 1] - yb);
+  int i, j;
+  merge_partition(GlobalRows{m.xir + xb}, nx, GlobalRows{m.yir + yb}, ny, min(nx + ny, tl * kTile), i, j);
+  tile_start[t] = make_int2(i, j);
+}
+
 // WRITE == false: count the distinct rows of every tile. WRITE == true: emit rows and values at tile_base[t].
 template <class SR, bool WRITE>
 __global__ void __launch_bounds__(kMergeThreads)
 merge2_kernel(MergeCols m, const typename SR::out_t *xval, const typename SR::out_t *yval, const int32_t *tile_col,
-              const int64_t *first, int64_t ntiles, int64_t *tile_count, const int64_t *tile_base, int32_t *cir,
-              typename SR::out_t *cval) {
+              const int64_t *first, const int2 *tile_start, int64_t ntiles, int64_t *tile_count, const int64_t *tile_base,
+              int32_t *cir, typename SR::out_t *cval) {
   typedef typename SR::out_t out_t;
   __shared__ int srow[kTile + 2]; // cx + cy <= kTile + 1 elements: X part first, then the Y part
   __shared__ out_t sval[WRITE ? kTile + 2 : 1];
-  __shared__ int part[4];
   __shared__ int warp_sums[32];
   __shared__ int total_s;
   const int64_t t = blockIdx.x;
@@ -79,15 +93,11 @@ merge2_kernel(MergeCols m, const typename SR::out_t *xval, const typename SR::ou
   const int tl = (int)(t - first[col]);
   const int64_t xb = m.xcp[col], yb = m.ycp[col];
   const int nx = (int)(m.xcp[col + 1] - xb), ny = (int)(m.ycp[col + 1] - yb);
-  if (threadIdx.x < 2) {
-    int d = min(nx + ny, (tl + (int)threadIdx.x) * kTile);
-    int i, j;
-    merge_partition(GlobalRows{m.xir + xb}, nx, GlobalRows{m.yir + yb}, ny, d, i, j);
-    part[2 * threadIdx.x] = i;
-    part[2 * threadIdx.x + 1] = j;
-  }
-  __syncthreads();
-  const int i0 = part[0], j0 = part[1], cx = part[2] - i0, cy = part[3] - j0; // cx + cy <= kTile + 1
+  const bool last_tile = (t + 1 == first[col + 1]);
+  const int2 p0 = tile_start[t];
+  const int2 p1 = last_tile ? make_int2(nx, ny) : tile_start[t + 1];
+  (void)tl;
+  const int i0 = p0.x, j0 = p0.y, cx = p1.x - i0, cy = p1.y - j0; // cx + cy <= kTile + 1
   int *sx = srow, *sy = srow + cx;
   for (int q = threadIdx.x; q < cx; q += kMergeThreads) {
     sx[q] = m.xir[xb + i0 + q];
@@ -196,10 +206,16 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
   CB_TRY(dev_alloc_t(ctx, &tile_base, (size_t)ntiles + 2));
   merge_fill_tile_cols<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(first, n, tile_col);
   CB_LAUNCH_CHECK(ctx);
+  int2 *tile_start = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &tile_start, (size_t)ntiles + 1));
+  if (ntiles > 0) {
+    merge_partition_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(m, tile_col, first, ntiles, tile_start);
+    CB_LAUNCH_CHECK(ctx);
+  }
   cudaEventRecord(ctx->ev[1], st);
   if (ntiles > 0) {
-    merge2_kernel<SR, false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(m, nullptr, nullptr, tile_col, first, ntiles, tile_count,
-                                                                        nullptr, nullptr, nullptr);
+    merge2_kernel<SR, false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(m, nullptr, nullptr, tile_col, first, tile_start, ntiles,
+                                                                        tile_count, nullptr, nullptr, nullptr);
     CB_LAUNCH_CHECK(ctx);
   }
   CB_TRY(exclusive_scan_i64(ctx, tile_count, tile_base, ntiles));
@@ -211,8 +227,8 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
   CB_TRY(mat_alloc(ctx, X->m, n, nnz, -1, X->dtype, &C));
   if (ntiles > 0) {
     merge2_kernel<SR, true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(
-        m, reinterpret_cast<const out_t *>(X->numx), reinterpret_cast<const out_t *>(Y->numx), tile_col, first, ntiles, nullptr,
-        tile_base, C->ir, reinterpret_cast<out_t *>(C->numx));
+        m, reinterpret_cast<const out_t *>(X->numx), reinterpret_cast<const out_t *>(Y->numx), tile_col, first, tile_start, ntiles,
+        nullptr, tile_base, C->ir, reinterpret_cast<out_t *>(C->numx));
     CB_LAUNCH_CHECK(ctx);
   }
   int64_t *colptr = nullptr;
@@ -225,6 +241,7 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
   dev_free(ctx, ntiles_col);
   dev_free(ctx, first);
   dev_free(ctx, tile_col);
+  dev_free(ctx, tile_start);
   dev_free(ctx, tile_count);
   dev_free(ctx, tile_base);
   if (rc != CBGPU_OK) {
