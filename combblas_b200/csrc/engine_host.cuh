@@ -118,7 +118,7 @@ struct EngineIO {
 
 // symbolic kernel classes (launch order) and numeric kernel classes
 enum { SYM_BM_L = 0, SYM_BM_S = 1, SYM_H_CTA = 2, SYM_H_WARP = 3, SYM_H_WARP_S = 4 };
-enum { NUM_BM_G = 0, NUM_BM_L = 1, NUM_BM_S = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_M = 5, NUM_H_WARP_S = 6 };
+enum { NUM_BM_G = 0, NUM_BM_L = 1, NUM_BM_S = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_M2 = 5, NUM_H_WARP_M = 6, NUM_H_WARP_S = 7 };
 
 // src must arrive with Air/Aval (whole columns) and, when the block has several row windows, T2/Wir/Wval set.
 template <class SR, bool MERGE>
@@ -153,8 +153,10 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   int64_t *colflop = nullptr;
   CB_TRY(dev_alloc_t(ctx, &colflop, (size_t)ncol + 1));
   if (ncol > 0) {
+    CB_KBEGIN(CBGPU_K_FLOP);
     task_flop_kernel<SR, MERGE><<<(unsigned)((ncol + 7) / 8), 256, 0, st>>>(src, ncol, colflop);
     CB_LAUNCH_CHECK(ctx);
+    CB_KEND(CBGPU_K_FLOP);
   }
   int64_t ntask = ncol;
   int64_t *taskflop = colflop;
@@ -295,7 +297,8 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       uint8_t c = 15;
       if (b >= 1 && b <= 6) c = NUM_H_WARP_S;
       else if (b == 7) c = NUM_H_WARP_M;
-      else if (b >= 8 && b <= 9) c = NUM_H_WARP;
+      else if (b == 8) c = NUM_H_WARP_M2;
+      else if (b == 9) c = NUM_H_WARP;
       else if (b >= 10 && b <= 39) c = NUM_H_CTA;
       else if (b >= 41 && b <= 52) c = NUM_BM_S;
       else if (b >= 53 && b <= 79) c = NUM_BM_L;
@@ -378,15 +381,28 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       stats.nnz_hash_warp += class_weight(nb, num_class, NUM_H_WARP, true);
     }
     // hash per warp: 33..64 outputs (128 slots: the Erdos-Renyi regime, d^2 = 64 products per column)
-    if (nc.count[NUM_H_WARP_M] > 0) {
+    if (nc.count[NUM_H_WARP_M] + nc.count[NUM_H_WARP_M2] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 7>;
       size_t sm = 8 * ((size_t)1 << 7) * (8 + sizeof(acc_t) + 4) + 64;
       CB_TRY(optin_smem(ctx, kern, sm));
-      CB_KBEGIN(CBGPU_K_NUM_HASH_WARP);
-      kern<<<(unsigned)((nc.count[NUM_H_WARP_M] + 7) / 8), 256, sm, st>>>(src, order + nc.begin[NUM_H_WARP_M], nc.count[NUM_H_WARP_M],
-                                                                         taskptr, Cm->ir, Cval);
-      CB_LAUNCH_CHECK(ctx);
-      CB_KEND(CBGPU_K_NUM_HASH_WARP);
+      CB_KBEGIN(CBGPU_K_NUM_HASH_WARP_M);
+      if (nc.count[NUM_H_WARP_M] > 0) {
+        kern<<<(unsigned)((nc.count[NUM_H_WARP_M] + 7) / 8), 256, sm, st>>>(src, order + nc.begin[NUM_H_WARP_M], nc.count[NUM_H_WARP_M],
+                                                                           taskptr, Cm->ir, Cval);
+        CB_LAUNCH_CHECK(ctx);
+      }
+      if (nc.count[NUM_H_WARP_M2] > 0) { // 65..128 outputs: 256 slots
+        auto kern2 = num_hash_kernel<SR, MERGE, 1, 8>;
+        size_t sm2 = 8 * ((size_t)1 << 8) * (8 + sizeof(acc_t) + 4) + 64;
+        CB_TRY(optin_smem(ctx, kern2, sm2));
+        kern2<<<(unsigned)((nc.count[NUM_H_WARP_M2] + 7) / 8), 256, sm2, st>>>(src, order + nc.begin[NUM_H_WARP_M2], nc.count[NUM_H_WARP_M2],
+                                                                              taskptr, Cm->ir, Cval);
+        CB_LAUNCH_CHECK(ctx);
+        stats.tasks_hash_warp += nc.count[NUM_H_WARP_M2];
+        stats.flops_hash_warp += class_weight(nb, num_class, NUM_H_WARP_M2, false);
+        stats.nnz_hash_warp += class_weight(nb, num_class, NUM_H_WARP_M2, true);
+      }
+      CB_KEND(CBGPU_K_NUM_HASH_WARP_M);
       stats.tasks_hash_warp += nc.count[NUM_H_WARP_M];
       stats.flops_hash_warp += class_weight(nb, num_class, NUM_H_WARP_M, false);
       stats.nnz_hash_warp += class_weight(nb, num_class, NUM_H_WARP_M, true);

@@ -49,7 +49,8 @@ class Stats(C.Structure):
                 ("nnz_bitmap_gmem", C.c_int64), ("ms_kernel", C.c_float * 12), ("flops_sym", C.c_int64 * 5)]
 
     KERNELS = ["sym_bitmap", "sym_hash_cta_large", "sym_hash_cta", "sym_hash_warp", "sym_hash_warp_small",
-               "num_bitmap_gmem", "num_bitmap_smem", "num_hash_cta", "num_hash_warp", "num_hash_warp_small", "flop", "-"]
+               "num_bitmap_gmem", "num_bitmap_smem", "num_hash_cta", "num_hash_warp", "num_hash_warp_small", "flop",
+               "num_hash_warp_mid"]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_kernel", "flops_sym")}

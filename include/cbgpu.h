@@ -105,7 +105,8 @@ typedef struct {
 enum {
   CBGPU_K_SYM_BITMAP = 0, CBGPU_K_SYM_HASH_CTA_L = 1, CBGPU_K_SYM_HASH_CTA = 2, CBGPU_K_SYM_HASH_WARP = 3,
   CBGPU_K_SYM_HASH_WARP_S = 4, CBGPU_K_NUM_BITMAP_GMEM = 5, CBGPU_K_NUM_BITMAP_SMEM = 6, CBGPU_K_NUM_HASH_CTA = 7,
-  CBGPU_K_NUM_HASH_WARP = 8, CBGPU_K_NUM_HASH_WARP_S = 9, CBGPU_K_FLOP = 10, CBGPU_K_COUNT = 12
+  CBGPU_K_NUM_HASH_WARP = 8, CBGPU_K_NUM_HASH_WARP_S = 9, CBGPU_K_FLOP = 10, CBGPU_K_NUM_HASH_WARP_M = 11,
+  CBGPU_K_COUNT = 12
 };
 
 /* ---------------------------------------------------------------- lifecycle */
