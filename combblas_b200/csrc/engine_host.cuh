@@ -306,7 +306,8 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       num_class[b] = c;
     }
     if (ntask > 0) {
-      int64_t auto_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 2048, 32), 2048);
+      // below this many outputs a task is cheaper in the per-warp hash classes than with a window-sized bitmap
+      int64_t auto_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 512, 32), 256);
       int64_t bmin = opt.bitmap_min_nnz > 0 ? opt.bitmap_min_nnz : auto_min;
       num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048,
                                                                         opt.bitmap_smem_acc, (int)opt.force_path, bucket);
