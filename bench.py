@@ -160,6 +160,22 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(scale):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same workload (profiles/r1_ncu_summary_s<scale>_dominant.txt); None otherwise."""
+    p = os.path.join(ROOT, "profiles", f"r1_ncu_summary_s{scale}_dominant.txt")
+    if not os.path.exists(p):
+        return None
+    rd = wr = None
+    for line in open(p):
+        f = line.split()
+        if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
+            rd = float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(f[2], 1)
+        if len(f) >= 3 and f[0] == "dram__bytes_write.sum":
+            wr = float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(f[2], 1)
+    return None if rd is None or wr is None else rd + wr
+
+
 def bytes_alg(nnzA, nzcA, nnzB, nzcB, nnzC, nzcC, sv=8):
     """each operand read once, result written once, compressed-column form. Device layout:
     row ids 4 B (SpDCCols<int32_t,...> local indices), values sv B, jc+cp 16 B per non-empty column."""
@@ -372,7 +388,9 @@ def main():
         share = sd[kf] / max(1, mults_local)
         dom_bytes = sd[kn] * 12 + share * ((ainfo.nnz + binfo.nnz) * 12 + (ainfo.nzc + binfo.nzc) * 16)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "scope": "one cbgpu_spgemm_local call (all kernel classes)",
+                "traffic": ncu_traffic(scale) if world == 1 else None,
+                "traffic_note": "DRAM bytes of ONE launch of num_bitmap_kernel<...,512> (one of the column slabs), ncu --set full, "
+                                "profiles/r1_ncu_summary_s%d_dominant.txt" % scale, "peak_source": peak_src, "scope": "one cbgpu_spgemm_local call (all kernel classes)",
                 "algorithmic_bytes": balg, "kernel_ms": {k: round(v, 4) for k, v in sorted(kernel_ms.items())},
                 "dominant_kernel": dominant[0], "dominant_kernel_ms": round(dominant[1], 4)}
     if dom_bytes is not None and dominant[1] > 0:
