@@ -460,6 +460,8 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "bitmap_window_log2")) return &o.bitmap_window_log2;
   if (!strcmp(name, "bitmap_min_nnz")) return &o.bitmap_min_nnz;
   if (!strcmp(name, "bitmap_smem_acc")) return &o.bitmap_smem_acc;
+  if (!strcmp(name, "bitmap_cta_threads")) return &o.bitmap_cta_threads;
+  if (!strcmp(name, "bitmap_small_threads")) return &o.bitmap_small_threads;
   if (!strcmp(name, "force_path")) return &o.force_path;
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
@@ -471,6 +473,10 @@ int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {
   if (!s) return set_error(ctx, CBGPU_ERR_INVALID, "unknown option %s", name);
   if (!strcmp(name, "bitmap_smem_acc") && (value < 256 || value > 16384))
     return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_smem_acc must be in [256, 16384]");
+  if (!strcmp(name, "bitmap_cta_threads") && value != 256 && value != 512)
+    return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_cta_threads must be 256 or 512");
+  if (!strcmp(name, "bitmap_small_threads") && value != 128 && value != 256)
+    return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_small_threads must be 128 or 256");
   *s = value;
   return CBGPU_OK;
 }

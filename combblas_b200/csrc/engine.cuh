@@ -96,17 +96,17 @@ __device__ __forceinline__ void task_segments(const Source<SR, MERGE> &s, Task &
   k.vals = whole ? (const void *)s.Aval : (const void *)s.Wval;
 }
 
-// segment p of task k: [beg, beg+len) in Air/Aval, with its multiplier
+// segment p of task k, first half: the column of A (or of the stacked merge lists) it reads, and its multiplier
 template <class SR, bool MERGE, bool NEED_MULT>
-__device__ __forceinline__ void load_segment(const Source<SR, MERGE> &s, const Task &k, int64_t p, int64_t &beg, int &len,
-                                             typename SR::b_t &mult) {
-  int64_t col;
-  if (MERGE) {
-    col = p * s.n + k.col;
-  } else {
-    col = s.Bir[p];
-    if (NEED_MULT) mult = s.Bval[p];
-  }
+__device__ __forceinline__ int64_t segment_column(const Source<SR, MERGE> &s, const Task &k, int64_t p, typename SR::b_t &mult) {
+  if (MERGE) return p * s.n + k.col;
+  if (NEED_MULT) mult = s.Bval[p];
+  return s.Bir[p];
+}
+
+// second half: the run [beg, beg+len) of that column inside the task's row window(s)
+template <class SR, bool MERGE>
+__device__ __forceinline__ void segment_range(const Source<SR, MERGE> &s, const Task &k, int64_t col, int64_t &beg, int &len) {
   if ((k.whi - k.wlo) == s.nwin) {
     beg = s.T[col];
     len = (int)(s.T[col + 1] - beg);
@@ -133,6 +133,14 @@ __device__ __forceinline__ void load_segment(const Source<SR, MERGE> &s, const T
     }
     len = (int)(a - beg);
   }
+}
+
+// segment p of task k: [beg, beg+len) in Air/Aval, with its multiplier
+template <class SR, bool MERGE, bool NEED_MULT>
+__device__ __forceinline__ void load_segment(const Source<SR, MERGE> &s, const Task &k, int64_t p, int64_t &beg, int &len,
+                                             typename SR::b_t &mult) {
+  const int64_t col = segment_column<SR, MERGE, NEED_MULT>(s, k, p, mult);
+  segment_range<SR, MERGE>(s, k, col, beg, len);
 }
 
 // ------------------------------------------------------------------------------------------------ product walk
@@ -259,14 +267,25 @@ __device__ __forceinline__ void warp_walk(const Source<SR, MERGE> &s, const Task
 template <class SR, bool MERGE, bool NEED_MULT, int CH, class LD, class USE>
 __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<CH> *q, LD &&ld, USE &&use) {
   typedef typename SR::b_t mult_t;
-  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = CH >> 5; // blockDim.x == CH
+  constexpr int nwarp = CH >> 5; // blockDim.x == CH
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  // The segment descriptors are two dependent loads (B's row id, then A's column range): the first half of the next
+  // chunk is fetched while the current chunk is processed, so only one of the two latencies is exposed per chunk.
+  int64_t col_next = -1;
+  mult_t mult_next = mult_t();
+  if (k.seg_begin + threadIdx.x < k.seg_end)
+    col_next = segment_column<SR, MERGE, NEED_MULT>(s, k, k.seg_begin + threadIdx.x, mult_next);
   for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
     __syncthreads(); // previous chunk fully consumed
     const int nseg = (int)min((int64_t)CH, k.seg_end - cbase);
     int64_t beg = 0;
     int len = 0;
-    mult_t mult = mult_t();
-    if ((int)threadIdx.x < nseg) load_segment<SR, MERGE, NEED_MULT>(s, k, cbase + threadIdx.x, beg, len, mult);
+    const int64_t col = col_next;
+    mult_t mult = mult_next;
+    if ((int)threadIdx.x < nseg) segment_range<SR, MERGE>(s, k, col, beg, len);
+    col_next = -1;
+    if (cbase + CH + threadIdx.x < k.seg_end)
+      col_next = segment_column<SR, MERGE, NEED_MULT>(s, k, cbase + CH + threadIdx.x, mult_next);
     // block-wide exclusive scan of len (64-bit)
     long long incl = len;
 #pragma unroll
@@ -276,12 +295,15 @@ __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task 
     }
     if (lane == 31) q->warp_sums[warp] = incl;
     __syncthreads();
-    long long woff = 0, total = 0;
-    for (int w = 0; w < nwarp; ++w) {
-      long long v = q->warp_sums[w];
-      if (w < warp) woff += v;
-      total += v;
+    // offsets of the warps' segment groups: inclusive scan of the per-warp sums by the first nwarp lanes of every warp
+    long long wv = lane < nwarp ? q->warp_sums[lane] : 0, winc = wv;
+#pragma unroll
+    for (int d = 1; d < nwarp; d <<= 1) {
+      long long x = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+      if (lane >= d) winc += x;
     }
+    const long long total = __shfl_sync(0xFFFFFFFFu, winc, nwarp - 1);
+    const long long woff = __shfl_sync(0xFFFFFFFFu, winc - wv, warp);
     if ((int)threadIdx.x < CH) {
       q->pre[threadIdx.x] = woff + incl - len;
       q->beg[threadIdx.x] = beg;
@@ -608,20 +630,22 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   const int nnz = total;
   for (int c = c0; c < c1; ++c) {
     pre[c] = (unsigned)run;
-    unsigned lo = bm[2 * c], hi = bm[2 * c + 1];
-    int rowbase = rbase + (c << 6);
-    while (lo) {
-      int b = __ffs(lo) - 1;
-      lo &= lo - 1;
-      if (s.debug != 2) Cir[obase + run] = rowbase + b;
-      ++run;
-    }
-    rowbase += 32;
-    while (hi) {
-      int b = __ffs(hi) - 1;
-      hi &= hi - 1;
-      if (s.debug != 2) Cir[obase + run] = rowbase + b;
-      ++run;
+    run += __popc(bm[2 * c]) + __popc(bm[2 * c + 1]);
+  }
+  __syncthreads();
+  // Row emission with neighbouring lanes on neighbouring cells: the ranks of adjacent cells are adjacent, so the stores
+  // of one warp instruction fall into a few sectors of Cir (one thread per run of cells scattered them over 32 sectors).
+  if (s.debug != 2) {
+    const unsigned long long *bm64 = reinterpret_cast<const unsigned long long *>(bm);
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+      unsigned long long w = bm64[c];
+      if (w == 0) continue;
+      int32_t *o = Cir + obase + pre[c];
+      const int rowbase = rbase + (c << 6);
+      while (w) {
+        *o++ = rowbase + (__ffsll((long long)w) - 1);
+        w &= w - 1;
+      }
     }
   }
   if (s.debug == 4) return; // mark + scan + row emission only
@@ -637,10 +661,8 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   auto use = [&](const RowVal<aval_t> &x, typename SR::b_t mu) {
     unsigned r = (unsigned)(x.row - rbase);
     unsigned cell = r >> 6, bit = r & 63;
-    uint2 w = reinterpret_cast<const uint2 *>(bm)[cell];
-    unsigned rank = pre[cell];
-    if (bit >= 32) rank += __popc(w.x) + __popc(w.y & ((1u << (bit - 32)) - 1u));
-    else rank += __popc(w.x & ((1u << bit) - 1u));
+    const unsigned long long w = reinterpret_cast<const unsigned long long *>(bm)[cell];
+    const unsigned rank = pre[cell] + (unsigned)__popcll(w & ((1ull << bit) - 1ull));
     acc_t v;
     if (MERGE) v = SR::from_out((out_t)x.val);
     else v = SR::mul((typename SR::a_t)x.val, mu);

@@ -231,15 +231,27 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   if (sc.count[SYM_BM_L] + sc.count[SYM_BM_S] > 0) {
     CB_KBEGIN(CBGPU_K_SYM_BITMAP);
     if (sc.count[SYM_BM_L] > 0) {
-      auto kern = sym_bitmap_kernel<SR, MERGE, 512>;
-      CB_TRY(optin_smem(ctx, kern, bm_bytes));
-      kern<<<(unsigned)sc.count[SYM_BM_L], 512, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
+      if (opt.bitmap_cta_threads == 256) {
+        auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
+        CB_TRY(optin_smem(ctx, kern, bm_bytes));
+        kern<<<(unsigned)sc.count[SYM_BM_L], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
+      } else {
+        auto kern = sym_bitmap_kernel<SR, MERGE, 512>;
+        CB_TRY(optin_smem(ctx, kern, bm_bytes));
+        kern<<<(unsigned)sc.count[SYM_BM_L], 512, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
+      }
       CB_LAUNCH_CHECK(ctx);
     }
     if (sc.count[SYM_BM_S] > 0) {
-      auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
-      CB_TRY(optin_smem(ctx, kern, bm_bytes));
-      kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
+      if (opt.bitmap_small_threads == 256) {
+        auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
+        CB_TRY(optin_smem(ctx, kern, bm_bytes));
+        kern<<<(unsigned)sc.count[SYM_BM_S], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
+      } else {
+        auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
+        CB_TRY(optin_smem(ctx, kern, bm_bytes));
+        kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
+      }
       CB_LAUNCH_CHECK(ctx);
     }
     CB_KEND(CBGPU_K_SYM_BITMAP);
@@ -322,17 +334,31 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       size_t sm = bm_bytes + (size_t)max_cells * 4 + 16;
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
       if (nc.count[NUM_BM_G] > 0) {
-        auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
-        CB_TRY(optin_smem(ctx, kern, sm));
-        kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                           taskptr, Cm->ir, Cval);
+        if (opt.bitmap_cta_threads == 256) {
+          auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
+          CB_TRY(optin_smem(ctx, kern, sm));
+          kern<<<(unsigned)nc.count[NUM_BM_G], 256, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
+                                                             taskptr, Cm->ir, Cval);
+        } else {
+          auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
+          CB_TRY(optin_smem(ctx, kern, sm));
+          kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
+                                                             taskptr, Cm->ir, Cval);
+        }
         CB_LAUNCH_CHECK(ctx);
       }
       if (nc.count[NUM_BM_S] > 0) {
-        auto kern = num_bitmap_kernel<SR, MERGE, true, 128>;
-        CB_TRY(optin_smem(ctx, kern, sm));
-        kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                           taskptr, Cm->ir, Cval);
+        if (opt.bitmap_small_threads == 256) {
+          auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
+          CB_TRY(optin_smem(ctx, kern, sm));
+          kern<<<(unsigned)nc.count[NUM_BM_S], 256, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
+                                                             taskptr, Cm->ir, Cval);
+        } else {
+          auto kern = num_bitmap_kernel<SR, MERGE, true, 128>;
+          CB_TRY(optin_smem(ctx, kern, sm));
+          kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
+                                                             taskptr, Cm->ir, Cval);
+        }
         CB_LAUNCH_CHECK(ctx);
       }
       CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
