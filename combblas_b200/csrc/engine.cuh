@@ -25,7 +25,7 @@
 
 namespace cbgpu {
 
-constexpr int kWarpLong = 48;    // segments at least this long are walked by a whole warp
+constexpr int kWarpLong = 128;   // segments are walked by a whole warp in groups of this many products (4 loads per lane)
 constexpr int kBitmapThreads = 512;
 constexpr int kLightMax = 256;   // with several row windows, columns up to this many products stay one task (warp hash)
 
@@ -190,16 +190,17 @@ struct RowVal {
 template <class mult_t, bool NEED_MULT, class LD, class USE>
 __device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult, LD &&ld, USE &&use) {
   const int lane = lane_id();
+  // long segments: whole groups of kWarpLong products, strided by the warp (coalesced), four loads in flight per lane
   unsigned longmask = __ballot_sync(0xFFFFFFFFu, len >= kWarpLong);
   while (longmask) {
     int src = __ffs(longmask) - 1;
     longmask &= longmask - 1;
     int64_t b = __shfl_sync(0xFFFFFFFFu, beg, src);
-    int l = __shfl_sync(0xFFFFFFFFu, len, src);
+    int l = __shfl_sync(0xFFFFFFFFu, len, src) & ~(kWarpLong - 1);
     mult_t mu = mult_t();
     if (NEED_MULT) mu = shfl_mult<mult_t>(mult, src);
-    int i = lane;
-    for (; i + 96 < l; i += 128) {
+#pragma unroll 1
+    for (int i = lane; i < l; i += 128) {
       auto x0 = ld(b + i);
       auto x1 = ld(b + i + 32);
       auto x2 = ld(b + i + 64);
@@ -209,9 +210,14 @@ __device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult
       use(x2, mu);
       use(x3, mu);
     }
-    for (; i < l; i += 32) use(ld(b + i), mu);
   }
-  int slen = (len >= kWarpLong) ? 0 : len;
+  // what is left of a long segment (< kWarpLong products) joins the short ones
+  if (len >= kWarpLong) {
+    const int done = len & ~(kWarpLong - 1);
+    beg += done;
+    len -= done;
+  }
+  int slen = len;
   int incl = slen;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -269,23 +275,13 @@ __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task 
   typedef typename SR::b_t mult_t;
   constexpr int nwarp = CH >> 5; // blockDim.x == CH
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  // The segment descriptors are two dependent loads (B's row id, then A's column range): the first half of the next
-  // chunk is fetched while the current chunk is processed, so only one of the two latencies is exposed per chunk.
-  int64_t col_next = -1;
-  mult_t mult_next = mult_t();
-  if (k.seg_begin + threadIdx.x < k.seg_end)
-    col_next = segment_column<SR, MERGE, NEED_MULT>(s, k, k.seg_begin + threadIdx.x, mult_next);
   for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
     __syncthreads(); // previous chunk fully consumed
     const int nseg = (int)min((int64_t)CH, k.seg_end - cbase);
     int64_t beg = 0;
     int len = 0;
-    const int64_t col = col_next;
-    mult_t mult = mult_next;
-    if ((int)threadIdx.x < nseg) segment_range<SR, MERGE>(s, k, col, beg, len);
-    col_next = -1;
-    if (cbase + CH + threadIdx.x < k.seg_end)
-      col_next = segment_column<SR, MERGE, NEED_MULT>(s, k, cbase + CH + threadIdx.x, mult_next);
+    mult_t mult = mult_t();
+    if ((int)threadIdx.x < nseg) load_segment<SR, MERGE, NEED_MULT>(s, k, cbase + threadIdx.x, beg, len, mult);
     // block-wide exclusive scan of len (64-bit)
     long long incl = len;
 #pragma unroll
@@ -531,6 +527,17 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
 }
 
 // ------------------------------------------------------------------------------------------------ bitmap path
+// The presence bitmap of a row window is an array of 64-bit CELLS in shared memory: the low kCellRows bits mark the
+// rows of the cell that occur in the task, the high kRankBits bits hold (after the scan) the number of present rows in
+// all earlier cells. One 8-byte shared-memory load therefore gives a product both halves of its output rank,
+//     rank(row) = cell >> kCellRows  +  popc(cell & ((1 << bit) - 1)),
+// and a cell array that the symbolic pass stores to HBM lets the numeric pass skip its own mark walk and scan.
+constexpr int kCellRows = 45;
+constexpr int kRankBits = 64 - kCellRows; // 19: row windows of up to 2^19 rows
+constexpr unsigned long long kCellMask = (1ull << kCellRows) - 1ull;
+
+__host__ __device__ __forceinline__ int cells_of_rows(int64_t rows) { return (int)((rows + kCellRows - 1) / kCellRows); }
+
 // block-wide exclusive scan of one int per thread (blockDim <= 1024); returns exclusive prefix, total in *total
 __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /*[32]*/, int *total) {
   const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -557,94 +564,138 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /*[32]
   return warp_sums[warp] + incl - v;
 }
 
+// the row window of a task
+struct Window {
+  int rbase, wrows, ncell;
+};
+template <class Src>
+__device__ __forceinline__ Window task_window(const Src &s, const Task &k, int64_t m) {
+  const int64_t rbase64 = (int64_t)k.wlo << s.wlog2;
+  const int64_t rend = (k.whi == s.nwin) ? m : ((int64_t)k.whi << s.wlog2);
+  Window w;
+  w.rbase = (int)rbase64;
+  w.wrows = (int)(rend - rbase64);
+  w.ncell = cells_of_rows(w.wrows);
+  return w;
+}
+
+// clear the cells, then set the bit of every row that occurs in the task
 template <class SR, bool MERGE, int THREADS>
-__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<THREADS> *q, unsigned *bm,
-                                            int ncell, int rbase) {
-  uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
+__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<THREADS> *q,
+                                            unsigned long long *cells, int ncell, int rbase) {
+  uint4 *c4 = reinterpret_cast<uint4 *>(cells);
   const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) bm4[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) c4[i] = make_uint4(0, 0, 0, 0);
+  unsigned *words = reinterpret_cast<unsigned *>(cells);
   auto ld = [&](int64_t pos) { return k.rows[pos]; };
   auto use = [&](int row, typename SR::b_t) {
-    unsigned r = (unsigned)(row - rbase);
-    atomicOr(&bm[r >> 5], 1u << (r & 31));
+    const unsigned r = (unsigned)(row - rbase);
+    const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
+    atomicOr(&words[2 * cell + (bit >> 5)], 1u << (bit & 31));
   };
   cta_walk<SR, MERGE, false>(s, k, q, ld, use); // starts and ends with __syncthreads
 }
 
-// K2 (bitmap): rows of the window present in the task
+// number of present rows; with RANKS the exclusive prefix of every cell is written into its high bits.
+// Ends with __syncthreads (the cells are final afterwards).
+template <bool RANKS>
+__device__ __forceinline__ int bitmap_scan(unsigned long long *cells, int ncell, int *warp_sums, int *total) {
+  const int cpt = (ncell + blockDim.x - 1) / blockDim.x;
+  const int c0 = min(ncell, (int)threadIdx.x * cpt), c1 = min(ncell, c0 + cpt);
+  int mine = 0;
+  for (int c = c0; c < c1; ++c) mine += __popcll(cells[c]);
+  int run = block_exclusive_scan(mine, warp_sums, total);
+  if (RANKS) {
+    for (int c = c0; c < c1; ++c) {
+      const unsigned long long w = cells[c];
+      cells[c] = w | ((unsigned long long)run << kCellRows);
+      run += __popcll(w);
+    }
+    __syncthreads();
+  }
+  return *total;
+}
+
+// K2 (bitmap): rows of the window present in the task. The first `save_count` CTAs of the launch also rank their
+// cells and store them at saved + blockIdx.x * save_stride for the numeric pass (slot_of_task[t] = blockIdx.x).
 template <class SR, bool MERGE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int64_t *tasknnz) {
+sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int64_t *tasknnz,
+                  unsigned long long *saved, int64_t save_stride, int save_count, int32_t *slot_of_task) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned *bm = reinterpret_cast<unsigned *>(smem_raw);
+  unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
   __shared__ CtaQueueT<THREADS> queue;
   __shared__ int warp_sums[32];
   __shared__ int total;
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
   task_segments(s, k);
-  const int64_t rbase64 = (int64_t)k.wlo << s.wlog2;
-  int64_t rend = (k.whi == s.nwin) ? m : ((int64_t)k.whi << s.wlog2);
-  const int wrows = (int)(rend - rbase64);
-  const int ncell = (wrows + 63) >> 6;
-  bitmap_mark(s, k, &queue, bm, ncell, (int)rbase64);
-  int c = 0;
-  for (int i = threadIdx.x; i < ncell * 2; i += blockDim.x) c += __popc(bm[i]);
-  block_exclusive_scan(c, warp_sums, &total);
-  if (threadIdx.x == 0) tasknnz[t] = total;
+  const Window w = task_window(s, k, m);
+  bitmap_mark(s, k, &queue, cells, w.ncell, w.rbase);
+  if ((int)blockIdx.x < save_count) { // uniform per CTA
+    const int nnz = bitmap_scan<true>(cells, w.ncell, warp_sums, &total);
+    const uint4 *src = reinterpret_cast<const uint4 *>(cells);
+    uint4 *dst = reinterpret_cast<uint4 *>(saved + (int64_t)blockIdx.x * save_stride);
+    const int nvec = (w.ncell + 1) >> 1;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+      tasknnz[t] = nnz;
+      slot_of_task[t] = (int)blockIdx.x;
+    }
+  } else {
+    const int nnz = bitmap_scan<false>(cells, w.ncell, warp_sums, &total);
+    if (threadIdx.x == 0) tasknnz[t] = nnz;
+  }
 }
 
 // K4 (bitmap): rank every present row by popcount, accumulate values at their final sorted position.
 // GMEM_ACC == false: accumulators in shared memory, copied out at the end;
 // GMEM_ACC == true : accumulators are C's value array itself (atomics resolve in L2).
 template <class SR, bool MERGE, bool GMEM_ACC, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 3 : (THREADS == 256 ? 5 : 8))
 num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int max_cells,
-                  const int64_t *taskptr, int32_t *Cir, typename SR::out_t *Cval) {
+                  const int64_t *taskptr, int32_t *Cir, typename SR::out_t *Cval, const unsigned long long *saved,
+                  int64_t save_stride, const int32_t *slot_of_task) {
   typedef typename SR::acc_t acc_t;
   typedef typename SR::out_t out_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: bm[2*max_cells] u32 | pre[max_cells] u32 | acc[...] acc_t
-  unsigned *bm = reinterpret_cast<unsigned *>(smem_raw);
-  unsigned *pre = bm + 2 * (size_t)max_cells;
-  acc_t *acc = reinterpret_cast<acc_t *>(pre + max_cells + (max_cells & 1));
+  // layout: cells[max_cells] u64 | acc[...] acc_t
+  unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
+  acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
   __shared__ CtaQueueT<THREADS> queue;
   __shared__ int warp_sums[32];
   __shared__ int total;
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
   task_segments(s, k);
-  const int64_t rbase64 = (int64_t)k.wlo << s.wlog2;
-  int64_t rend = (k.whi == s.nwin) ? m : ((int64_t)k.whi << s.wlog2);
-  const int rbase = (int)rbase64;
-  const int wrows = (int)(rend - rbase64);
-  const int ncell = (wrows + 63) >> 6;
-  bitmap_mark(s, k, &queue, bm, ncell, rbase);
-  // rank index + sorted row ids
+  const Window w = task_window(s, k, m);
+  const int rbase = w.rbase, ncell = w.ncell;
   const int64_t obase = taskptr[t];
-  const int cpt = (ncell + blockDim.x - 1) / blockDim.x;
-  const int c0 = min(ncell, (int)threadIdx.x * cpt), c1 = min(ncell, c0 + cpt);
-  int mine = 0;
-  for (int c = c0; c < c1; ++c) mine += __popc(bm[2 * c]) + __popc(bm[2 * c + 1]);
-  int run = block_exclusive_scan(mine, warp_sums, &total);
-  const int nnz = total;
-  for (int c = c0; c < c1; ++c) {
-    pre[c] = (unsigned)run;
-    run += __popc(bm[2 * c]) + __popc(bm[2 * c + 1]);
+  const int nnz = (int)(taskptr[t + 1] - obase);
+  const int slot = slot_of_task ? slot_of_task[t] : -1;
+  if (slot >= 0) {
+    // the symbolic pass left the ranked cells of this task in HBM
+    const uint4 *src = reinterpret_cast<const uint4 *>(saved + (int64_t)slot * save_stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(cells);
+    const int nvec = (ncell + 1) >> 1;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  } else {
+    bitmap_mark(s, k, &queue, cells, ncell, rbase);
+    bitmap_scan<true>(cells, ncell, warp_sums, &total);
   }
-  __syncthreads();
   // Row emission with neighbouring lanes on neighbouring cells: the ranks of adjacent cells are adjacent, so the stores
-  // of one warp instruction fall into a few sectors of Cir (one thread per run of cells scattered them over 32 sectors).
+  // of one warp instruction fall into a few sectors of Cir.
   if (s.debug != 2) {
-    const unsigned long long *bm64 = reinterpret_cast<const unsigned long long *>(bm);
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
-      unsigned long long w = bm64[c];
-      if (w == 0) continue;
-      int32_t *o = Cir + obase + pre[c];
-      const int rowbase = rbase + (c << 6);
-      while (w) {
-        *o++ = rowbase + (__ffsll((long long)w) - 1);
-        w &= w - 1;
+      const unsigned long long cw = cells[c];
+      unsigned long long bits = cw & kCellMask;
+      if (bits == 0) continue;
+      int32_t *o = Cir + obase + (int64_t)(cw >> kCellRows);
+      const int rowbase = rbase + c * kCellRows;
+      while (bits) {
+        *o++ = rowbase + (__ffsll((long long)bits) - 1);
+        bits &= bits - 1;
       }
     }
   }
@@ -659,10 +710,10 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   auto ld = [&](int64_t pos) { return RowVal<aval_t>{k.rows[pos], ((const aval_t *)k.vals)[pos]}; };
   auto use = [&](const RowVal<aval_t> &x, typename SR::b_t mu) {
-    unsigned r = (unsigned)(x.row - rbase);
-    unsigned cell = r >> 6, bit = r & 63;
-    const unsigned long long w = reinterpret_cast<const unsigned long long *>(bm)[cell];
-    const unsigned rank = pre[cell] + (unsigned)__popcll(w & ((1ull << bit) - 1ull));
+    const unsigned r = (unsigned)(x.row - rbase);
+    const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
+    const unsigned long long cw = cells[cell];
+    const unsigned rank = (unsigned)(cw >> kCellRows) + (unsigned)__popcll(cw & ((1ull << bit) - 1ull));
     acc_t v;
     if (MERGE) v = SR::from_out((out_t)x.val);
     else v = SR::mul((typename SR::a_t)x.val, mu);

@@ -220,8 +220,22 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
 
   // ---- K2: symbolic kernels
-  const int max_cells = (int)((std::min<int64_t>(io.m, W) + 63) / 64 + 1) & ~1; // even, covers the uint4 clear
+  const int max_cells = (cells_of_rows(std::min<int64_t>(io.m, W)) + 1) & ~1; // even, covers the uint4 clear
   const size_t bm_bytes = (size_t)max_cells * 8;
+  // Ranked cells of the large symbolic tasks are kept in HBM for the numeric pass (which then needs no mark walk and no
+  // scan of its own): one slot of max_cells words per task, as many tasks as fit the budget.
+  unsigned long long *saved = nullptr;
+  int32_t *slot_of_task = nullptr;
+  int save_count = 0;
+  if (io.C && opt.bitmap_save_mb > 0 && sc.count[SYM_BM_L] > 0) {
+    const int64_t fit = (opt.bitmap_save_mb << 20) / (int64_t)bm_bytes;
+    save_count = (int)std::min<int64_t>(sc.count[SYM_BM_L], fit);
+    if (save_count > 0) {
+      CB_TRY(dev_alloc_t(ctx, &saved, (size_t)save_count * max_cells));
+      CB_TRY(dev_alloc_t(ctx, &slot_of_task, (size_t)ntask));
+      CB_CUDA(ctx, cudaMemsetAsync(slot_of_task, 0xFF, sizeof(int32_t) * (size_t)ntask, st));
+    }
+  }
   auto class_weight = [](const BinResult &r, const uint8_t *tab, int c, bool second) {
     int64_t s = 0;
     for (int b = 0; b < 256; ++b)
@@ -234,11 +248,13 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       if (opt.bitmap_cta_threads == 256) {
         auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
         CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_L], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
+        kern<<<(unsigned)sc.count[SYM_BM_L], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz,
+                                                                saved, max_cells, save_count, slot_of_task);
       } else {
         auto kern = sym_bitmap_kernel<SR, MERGE, 512>;
         CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_L], 512, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz);
+        kern<<<(unsigned)sc.count[SYM_BM_L], 512, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz,
+                                                                saved, max_cells, save_count, slot_of_task);
       }
       CB_LAUNCH_CHECK(ctx);
     }
@@ -246,11 +262,13 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       if (opt.bitmap_small_threads == 256) {
         auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
         CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_S], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
+        kern<<<(unsigned)sc.count[SYM_BM_S], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
+                                                                nullptr, 0, 0, nullptr);
       } else {
         auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
         CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz);
+        kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
+                                                                nullptr, 0, 0, nullptr);
       }
       CB_LAUNCH_CHECK(ctx);
     }
@@ -331,19 +349,19 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // Largest tasks by 512 threads; the many small ones (<= 2048 outputs) by 128 threads with a small shared-memory
     // footprint so that many of them are in flight per SM (their cost is dependent-load latency, not bandwidth).
     if (nc.count[NUM_BM_G] + nc.count[NUM_BM_S] > 0) {
-      size_t sm = bm_bytes + (size_t)max_cells * 4 + 16;
+      size_t sm = bm_bytes + 16;
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
       if (nc.count[NUM_BM_G] > 0) {
         if (opt.bitmap_cta_threads == 256) {
           auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
           CB_TRY(optin_smem(ctx, kern, sm));
           kern<<<(unsigned)nc.count[NUM_BM_G], 256, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval);
+                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
         } else {
           auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
           CB_TRY(optin_smem(ctx, kern, sm));
           kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval);
+                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
         }
         CB_LAUNCH_CHECK(ctx);
       }
@@ -352,12 +370,12 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
           auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
           CB_TRY(optin_smem(ctx, kern, sm));
           kern<<<(unsigned)nc.count[NUM_BM_S], 256, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval);
+                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
         } else {
           auto kern = num_bitmap_kernel<SR, MERGE, true, 128>;
           CB_TRY(optin_smem(ctx, kern, sm));
           kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval);
+                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
         }
         CB_LAUNCH_CHECK(ctx);
       }
@@ -369,11 +387,11 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // bitmap, accumulators in shared memory (2049 .. bitmap_smem_acc outputs; empty with the default options)
     if (nc.count[NUM_BM_L] > 0) {
       auto kern = num_bitmap_kernel<SR, MERGE, false, 512>;
-      size_t smL = bm_bytes + (size_t)max_cells * 4 + 16 + (size_t)std::max<int64_t>(opt.bitmap_smem_acc, 2048) * sizeof(acc_t);
+      size_t smL = bm_bytes + 16 + (size_t)std::max<int64_t>(opt.bitmap_smem_acc, 2048) * sizeof(acc_t);
       CB_TRY(optin_smem(ctx, kern, smL));
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
       kern<<<(unsigned)nc.count[NUM_BM_L], 512, smL, st>>>(src, order + nc.begin[NUM_BM_L], nc.count[NUM_BM_L], io.m, max_cells,
-                                                          taskptr, Cm->ir, Cval);
+                                                          taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
       CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
       stats.tasks_bitmap_smem = nc.count[NUM_BM_L];
@@ -472,6 +490,8 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   dev_free(ctx, order);
   dev_free(ctx, tasknnz);
   dev_free(ctx, taskptr);
+  dev_free(ctx, saved);
+  dev_free(ctx, slot_of_task);
   if (rc != CBGPU_OK) {
     mat_release(ctx, Cm);
     return rc;
