@@ -27,7 +27,6 @@ namespace cbgpu {
 
 constexpr int kWarpLong = 128;   // segments are walked by a whole warp in groups of this many products (4 loads per lane)
 constexpr int kBitmapThreads = 512;
-constexpr int kLightMax = 256;   // with several row windows, columns up to this many products stay one task (warp hash)
 
 // ------------------------------------------------------------------------------------------------ source
 template <class SR, bool MERGE>
@@ -456,7 +455,7 @@ __device__ __forceinline__ void group_bitonic(unsigned long long *a, int P, int 
 
 // K4 (hash): accumulate, compact, sort by row, emit.
 template <class SR, bool MERGE, int GROUP_WARPS, int LOG2T>
-__global__ void __launch_bounds__(GROUP_WARPS == 1 ? 256 : GROUP_WARPS * 32)
+__global__ void __launch_bounds__(GROUP_WARPS == 1 ? 256 : GROUP_WARPS * 32, GROUP_WARPS == 1 ? 6 : 1)
 num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const int64_t *taskptr, int32_t *Cir,
                 typename SR::out_t *Cval) {
   typedef typename SR::acc_t acc_t;
@@ -464,9 +463,10 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   constexpr int GROUPS = GROUP_WARPS == 1 ? 8 : 1;
   constexpr int GT = GROUP_WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout per CTA: sortbuf[GROUPS*T] u64 | acc[GROUPS*T] acc_t | keys[GROUPS*T] u32 | counters[GROUPS]
+  // layout per CTA: sortbuf[GROUPS*T/2] u64 | acc[GROUPS*T] acc_t | keys[GROUPS*T] u32 | counters[GROUPS]
+  // (a task of this class has at most T/2 outputs, so the sort buffer needs T/2 entries)
   unsigned long long *sort_all = reinterpret_cast<unsigned long long *>(smem_raw);
-  acc_t *acc_all = reinterpret_cast<acc_t *>(sort_all + GROUPS * T);
+  acc_t *acc_all = reinterpret_cast<acc_t *>(sort_all + GROUPS * (T / 2));
   unsigned *keys_all = reinterpret_cast<unsigned *>(acc_all + GROUPS * T);
   int *cnt_all = reinterpret_cast<int *>(keys_all + GROUPS * T);
   __shared__ typename std::conditional<GROUP_WARPS == 1, NoQueue, CtaQueueT<GROUP_WARPS * 32>>::type queue;
@@ -474,7 +474,7 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   const int gtid = GROUP_WARPS == 1 ? lane_id() : threadIdx.x;
   int64_t ti = (int64_t)blockIdx.x * GROUPS + group;
   if (GROUP_WARPS == 1 && ti >= count) return;
-  unsigned long long *sortbuf = sort_all + group * T;
+  unsigned long long *sortbuf = sort_all + group * (T / 2);
   acc_t *acc = acc_all + group * T;
   unsigned *keys = keys_all + group * T;
   int *cnt = cnt_all + group;
@@ -503,13 +503,23 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   } else {
     cta_walk<SR, MERGE, true>(s, k, reinterpret_cast<CtaQueueT<GROUP_WARPS * 32> *>(&queue), ld, use);
   }
-  // compact the occupied slots
-  for (int i = gtid; i < T; i += GT) {
-    unsigned key = keys[i];
-    if (key != kEmptyKey) {
-      int pos = atomicAdd(cnt, 1);
-      sortbuf[pos] = ((unsigned long long)key << 32) | (unsigned)i;
+  // compact the occupied slots (one warp: positions by ballot; a CTA: one shared counter bump per warp and round)
+  for (int i0 = 0; i0 < T; i0 += GT) {
+    const int i = i0 + gtid; // T is a multiple of GT
+    const unsigned key = keys[i];
+    const bool hit = key != kEmptyKey;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    int base = 0;
+    if (GROUP_WARPS == 1) {
+      base = *cnt;
+      __syncwarp();
+      if (lane_id() == 0) *cnt = base + __popc(m);
+      __syncwarp();
+    } else {
+      if (lane_id() == 0 && m) base = atomicAdd(cnt, __popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
     }
+    if (hit) sortbuf[base + __popc(m & ((1u << lane_id()) - 1u))] = ((unsigned long long)key << 32) | (unsigned)i;
   }
   group_sync<GROUP_WARPS>();
   const int n = *cnt;
@@ -597,23 +607,57 @@ __device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Ta
 }
 
 // number of present rows; with RANKS the exclusive prefix of every cell is written into its high bits.
-// Ends with __syncthreads (the cells are final afterwards).
+// Every warp sweeps one contiguous block of cell pairs with 16-byte loads, lanes on adjacent pairs (no bank conflicts);
+// prefixes inside the block come from warp scans, the block offsets from one exchange of the warp totals.
+// Ends with __syncthreads (the cells are final afterwards). blockDim.x is a multiple of 32, at most 1024.
 template <bool RANKS>
-__device__ __forceinline__ int bitmap_scan(unsigned long long *cells, int ncell, int *warp_sums, int *total) {
-  const int cpt = (ncell + blockDim.x - 1) / blockDim.x;
-  const int c0 = min(ncell, (int)threadIdx.x * cpt), c1 = min(ncell, c0 + cpt);
+__device__ __forceinline__ int bitmap_scan(unsigned long long *cells, int ncell, int *warp_sums) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int npair = (ncell + 1) >> 1; // a cell past ncell inside the last pair is zero
+  const int pw = (((npair + nwarp - 1) / nwarp) + 31) & ~31;
+  const int w0 = min(npair, warp * pw), w1 = min(npair, w0 + pw);
+  ulonglong2 *c2 = reinterpret_cast<ulonglong2 *>(cells);
   int mine = 0;
-  for (int c = c0; c < c1; ++c) mine += __popcll(cells[c]);
-  int run = block_exclusive_scan(mine, warp_sums, total);
-  if (RANKS) {
-    for (int c = c0; c < c1; ++c) {
-      const unsigned long long w = cells[c];
-      cells[c] = w | ((unsigned long long)run << kCellRows);
-      run += __popcll(w);
-    }
-    __syncthreads();
+  for (int p = w0 + lane; p < w1; p += 32) {
+    const ulonglong2 v = c2[p];
+    mine += __popcll(v.x) + __popcll(v.y);
   }
-  return *total;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+  if (lane == 0) warp_sums[warp] = mine;
+  __syncthreads();
+  const int wv = lane < nwarp ? warp_sums[lane] : 0;
+  int winc = wv;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int x = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+    if (lane >= d) winc += x;
+  }
+  const int total = __shfl_sync(0xFFFFFFFFu, winc, nwarp - 1);
+  if (RANKS) {
+    int run = __shfl_sync(0xFFFFFFFFu, winc - wv, warp);
+    for (int p0 = w0; p0 < w1; p0 += 32) { // warp-uniform
+      const int p = p0 + lane;
+      const bool valid = p < w1;
+      ulonglong2 v = valid ? c2[p] : make_ulonglong2(0ull, 0ull);
+      const int a = __popcll(v.x), sum = a + __popcll(v.y);
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += x;
+      }
+      const unsigned long long before = (unsigned long long)(run + incl - sum);
+      if (valid) {
+        v.x |= before << kCellRows;
+        v.y |= (before + (unsigned long long)a) << kCellRows;
+        c2[p] = v;
+      }
+      run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+  }
+  __syncthreads(); // also protects warp_sums against the next use
+  return total;
 }
 
 // K2 (bitmap): rows of the window present in the task. The first `save_count` CTAs of the launch also rank their
@@ -626,14 +670,13 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
   __shared__ CtaQueueT<THREADS> queue;
   __shared__ int warp_sums[32];
-  __shared__ int total;
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
   task_segments(s, k);
   const Window w = task_window(s, k, m);
   bitmap_mark(s, k, &queue, cells, w.ncell, w.rbase);
   if ((int)blockIdx.x < save_count) { // uniform per CTA
-    const int nnz = bitmap_scan<true>(cells, w.ncell, warp_sums, &total);
+    const int nnz = bitmap_scan<true>(cells, w.ncell, warp_sums);
     const uint4 *src = reinterpret_cast<const uint4 *>(cells);
     uint4 *dst = reinterpret_cast<uint4 *>(saved + (int64_t)blockIdx.x * save_stride);
     const int nvec = (w.ncell + 1) >> 1;
@@ -643,7 +686,7 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
       slot_of_task[t] = (int)blockIdx.x;
     }
   } else {
-    const int nnz = bitmap_scan<false>(cells, w.ncell, warp_sums, &total);
+    const int nnz = bitmap_scan<false>(cells, w.ncell, warp_sums);
     if (threadIdx.x == 0) tasknnz[t] = nnz;
   }
 }
@@ -651,8 +694,8 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
 // K4 (bitmap): rank every present row by popcount, accumulate values at their final sorted position.
 // GMEM_ACC == false: accumulators in shared memory, copied out at the end;
 // GMEM_ACC == true : accumulators are C's value array itself (atomics resolve in L2).
-template <class SR, bool MERGE, bool GMEM_ACC, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 3 : (THREADS == 256 ? 5 : 8))
+template <class SR, bool MERGE, bool GMEM_ACC, int THREADS, int MINB = (THREADS == 512 ? 3 : (THREADS == 256 ? 5 : 8))>
+__global__ void __launch_bounds__(THREADS, MINB)
 num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int max_cells,
                   const int64_t *taskptr, int32_t *Cir, typename SR::out_t *Cval, const unsigned long long *saved,
                   int64_t save_stride, const int32_t *slot_of_task) {
@@ -664,7 +707,6 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
   __shared__ CtaQueueT<THREADS> queue;
   __shared__ int warp_sums[32];
-  __shared__ int total;
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
   task_segments(s, k);
@@ -682,7 +724,7 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
     __syncthreads();
   } else {
     bitmap_mark(s, k, &queue, cells, ncell, rbase);
-    bitmap_scan<true>(cells, ncell, warp_sums, &total);
+    bitmap_scan<true>(cells, ncell, warp_sums);
   }
   // Row emission with neighbouring lanes on neighbouring cells: the ranks of adjacent cells are adjacent, so the stores
   // of one warp instruction fall into a few sectors of Cir.

@@ -167,7 +167,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     int64_t *cnt = nullptr;
     CB_TRY(dev_alloc_t(ctx, &cnt, (size_t)ncol));
     CB_TRY(dev_alloc_t(ctx, &first, (size_t)ncol + 1));
-    col_task_count_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(colflop, ncol, nwin, kLightMax, cnt);
+    col_task_count_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(colflop, ncol, nwin, std::min<int64_t>(std::max<int64_t>(opt.light_max, 1), 2048), cnt);
     CB_LAUNCH_CHECK(ctx);
     CB_TRY(exclusive_scan_i64(ctx, cnt, first, ncol));
     CB_CUDA(ctx, cudaMemcpyAsync(&ntask, first + ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -371,6 +371,11 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
           CB_TRY(optin_smem(ctx, kern, sm));
           kern<<<(unsigned)nc.count[NUM_BM_S], 256, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
                                                              taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
+        } else if (opt.bitmap_small_minblocks == 12) {
+          auto kern = num_bitmap_kernel<SR, MERGE, true, 128, 12>;
+          CB_TRY(optin_smem(ctx, kern, sm));
+          kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
+                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
         } else {
           auto kern = num_bitmap_kernel<SR, MERGE, true, 128>;
           CB_TRY(optin_smem(ctx, kern, sm));
@@ -401,7 +406,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // hash per CTA: 257..2048 outputs
     if (nc.count[NUM_H_CTA] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 8, 12>;
-      size_t sm = ((size_t)1 << 12) * (8 + sizeof(acc_t) + 4) + 16;
+      size_t sm = ((size_t)1 << 12) * (4 + sizeof(acc_t) + 4) + 16;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_CTA);
       kern<<<(unsigned)nc.count[NUM_H_CTA], 256, sm, st>>>(src, order + nc.begin[NUM_H_CTA], nc.count[NUM_H_CTA], taskptr, Cm->ir, Cval);
@@ -414,7 +419,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // hash per warp: 33..256 outputs
     if (nc.count[NUM_H_WARP] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 9>;
-      size_t sm = 8 * ((size_t)1 << 9) * (8 + sizeof(acc_t) + 4) + 64;
+      size_t sm = 8 * ((size_t)1 << 9) * (4 + sizeof(acc_t) + 4) + 64;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_WARP);
       kern<<<(unsigned)((nc.count[NUM_H_WARP] + 7) / 8), 256, sm, st>>>(src, order + nc.begin[NUM_H_WARP], nc.count[NUM_H_WARP], taskptr,
@@ -428,7 +433,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // hash per warp: 33..64 outputs (128 slots: the Erdos-Renyi regime, d^2 = 64 products per column)
     if (nc.count[NUM_H_WARP_M] + nc.count[NUM_H_WARP_M2] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 7>;
-      size_t sm = 8 * ((size_t)1 << 7) * (8 + sizeof(acc_t) + 4) + 64;
+      size_t sm = 8 * ((size_t)1 << 7) * (4 + sizeof(acc_t) + 4) + 64;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_WARP_M);
       if (nc.count[NUM_H_WARP_M] > 0) {
@@ -438,7 +443,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       }
       if (nc.count[NUM_H_WARP_M2] > 0) { // 65..128 outputs: 256 slots
         auto kern2 = num_hash_kernel<SR, MERGE, 1, 8>;
-        size_t sm2 = 8 * ((size_t)1 << 8) * (8 + sizeof(acc_t) + 4) + 64;
+        size_t sm2 = 8 * ((size_t)1 << 8) * (4 + sizeof(acc_t) + 4) + 64;
         CB_TRY(optin_smem(ctx, kern2, sm2));
         kern2<<<(unsigned)((nc.count[NUM_H_WARP_M2] + 7) / 8), 256, sm2, st>>>(src, order + nc.begin[NUM_H_WARP_M2], nc.count[NUM_H_WARP_M2],
                                                                               taskptr, Cm->ir, Cval);
@@ -455,7 +460,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // hash per warp: <= 32 outputs
     if (nc.count[NUM_H_WARP_S] > 0) {
       auto kern = num_hash_kernel<SR, MERGE, 1, 6>;
-      size_t sm = 8 * ((size_t)1 << 6) * (8 + sizeof(acc_t) + 4) + 64;
+      size_t sm = 8 * ((size_t)1 << 6) * (4 + sizeof(acc_t) + 4) + 64;
       CB_TRY(optin_smem(ctx, kern, sm));
       CB_KBEGIN(CBGPU_K_NUM_HASH_WARP_S);
       kern<<<(unsigned)((nc.count[NUM_H_WARP_S] + 7) / 8), 256, sm, st>>>(src, order + nc.begin[NUM_H_WARP_S], nc.count[NUM_H_WARP_S],
