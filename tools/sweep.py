@@ -11,6 +11,7 @@ ap.add_argument("--scale", type=int, action="append", default=[])
 ap.add_argument("--set", action="append", default=[], help="comma separated name=value list ('' = defaults)")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--sr", type=int, default=0)
+ap.add_argument("--phases", type=int, default=0, help="column slabs (0 = as bench.py: 48 GB of C per slab)")
 a = ap.parse_args()
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
@@ -19,7 +20,7 @@ defaults = {}
 for scale in a.scale or [20]:
     G = ctx.gen_rmat(scale, 16 << scale, 1, 0.57, 0.19, 0.19, True, cb.F64, 0)
     f_sym, nnz_sym = ctx.symbolic(G, G)
-    phases = max(1, int(np.ceil(nnz_sym * 12 / 48e9)))
+    phases = a.phases if a.phases > 0 else max(1, int(np.ceil(nnz_sym * 12 / 48e9)))
     slabs = ctx.colsplit(G, phases) if phases > 1 else [G]
     for oset in a.set or [""]:
         opts = dict(kv.split("=") for kv in oset.split(",") if kv)
@@ -40,7 +41,7 @@ for scale in a.scale or [20]:
             torch.cuda.synchronize()
             if rep > 0:
                 times.append(e0.elapsed_time(e1))
-        ms = min(times)
+        ms = min(times) if times else float('nan')
         print(f"s{scale} [{oset or 'defaults'}] {2 * f_sym / ms / 1e6:.1f} GFLOP/s  ms={[round(t, 1) for t in times]} slabs={phases} {kms}", flush=True)
         for k, v in defaults.items():
             ctx.set_option(k, v)
