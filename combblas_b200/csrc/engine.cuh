@@ -210,12 +210,35 @@ __device__ __forceinline__ void warp_process32(int64_t beg, int len, mult_t mult
       use(x3, mu);
     }
   }
-  // what is left of a long segment (< kWarpLong products) joins the short ones
   if (len >= kWarpLong) {
     const int done = len & ~(kWarpLong - 1);
     beg += done;
     len -= done;
   }
+  // what is left (< kWarpLong products per segment): whole groups of 32 are still strided by the warp, one to three
+  // loads in flight; this costs a third of the instructions of the flattened path below
+  unsigned midmask = __ballot_sync(0xFFFFFFFFu, len >= 32);
+  while (midmask) {
+    int src = __ffs(midmask) - 1;
+    midmask &= midmask - 1;
+    const int64_t b = __shfl_sync(0xFFFFFFFFu, beg, src) + lane;
+    const int n = __shfl_sync(0xFFFFFFFFu, len, src) >> 5; // 1..3, warp-uniform
+    mult_t mu = mult_t();
+    if (NEED_MULT) mu = shfl_mult<mult_t>(mult, src);
+    auto x0 = ld(b);
+    decltype(x0) x1{}, x2{};
+    if (n > 1) x1 = ld(b + 32);
+    if (n > 2) x2 = ld(b + 64);
+    use(x0, mu);
+    if (n > 1) use(x1, mu);
+    if (n > 2) use(x2, mu);
+  }
+  if (len >= 32) {
+    const int done = len & ~31;
+    beg += done;
+    len -= done;
+  }
+  // the tails (< 32 products per segment) are flattened over the lanes
   int slen = len;
   int incl = slen;
 #pragma unroll
@@ -607,56 +630,23 @@ __device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Ta
 }
 
 // number of present rows; with RANKS the exclusive prefix of every cell is written into its high bits.
-// Every warp sweeps one contiguous block of cell pairs with 16-byte loads, lanes on adjacent pairs (no bank conflicts);
-// prefixes inside the block come from warp scans, the block offsets from one exchange of the warp totals.
-// Ends with __syncthreads (the cells are final afterwards). blockDim.x is a multiple of 32, at most 1024.
+// Ends with __syncthreads (the cells are final afterwards). warp_sums has 33 entries.
 template <bool RANKS>
 __device__ __forceinline__ int bitmap_scan(unsigned long long *cells, int ncell, int *warp_sums) {
-  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int npair = (ncell + 1) >> 1; // a cell past ncell inside the last pair is zero
-  const int pw = (((npair + nwarp - 1) / nwarp) + 31) & ~31;
-  const int w0 = min(npair, warp * pw), w1 = min(npair, w0 + pw);
-  ulonglong2 *c2 = reinterpret_cast<ulonglong2 *>(cells);
+  const int cpt = (ncell + blockDim.x - 1) / blockDim.x;
+  const int c0 = min(ncell, (int)threadIdx.x * cpt), c1 = min(ncell, c0 + cpt);
   int mine = 0;
-  for (int p = w0 + lane; p < w1; p += 32) {
-    const ulonglong2 v = c2[p];
-    mine += __popcll(v.x) + __popcll(v.y);
-  }
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
-  if (lane == 0) warp_sums[warp] = mine;
-  __syncthreads();
-  const int wv = lane < nwarp ? warp_sums[lane] : 0;
-  int winc = wv;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int x = __shfl_up_sync(0xFFFFFFFFu, winc, d);
-    if (lane >= d) winc += x;
-  }
-  const int total = __shfl_sync(0xFFFFFFFFu, winc, nwarp - 1);
+  for (int c = c0; c < c1; ++c) mine += __popcll(cells[c]);
+  int run = block_exclusive_scan(mine, warp_sums, warp_sums + 32);
+  const int total = warp_sums[32];
   if (RANKS) {
-    int run = __shfl_sync(0xFFFFFFFFu, winc - wv, warp);
-    for (int p0 = w0; p0 < w1; p0 += 32) { // warp-uniform
-      const int p = p0 + lane;
-      const bool valid = p < w1;
-      ulonglong2 v = valid ? c2[p] : make_ulonglong2(0ull, 0ull);
-      const int a = __popcll(v.x), sum = a + __popcll(v.y);
-      int incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += x;
-      }
-      const unsigned long long before = (unsigned long long)(run + incl - sum);
-      if (valid) {
-        v.x |= before << kCellRows;
-        v.y |= (before + (unsigned long long)a) << kCellRows;
-        c2[p] = v;
-      }
-      run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (int c = c0; c < c1; ++c) {
+      const unsigned long long w = cells[c];
+      cells[c] = w | ((unsigned long long)run << kCellRows);
+      run += __popcll(w);
     }
   }
-  __syncthreads(); // also protects warp_sums against the next use
+  __syncthreads(); // cells final; warp_sums free for the next use
   return total;
 }
 
@@ -669,7 +659,7 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
   __shared__ CtaQueueT<THREADS> queue;
-  __shared__ int warp_sums[32];
+  __shared__ int warp_sums[33];
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
   task_segments(s, k);
@@ -706,7 +696,7 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
   acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
   __shared__ CtaQueueT<THREADS> queue;
-  __shared__ int warp_sums[32];
+  __shared__ int warp_sums[33];
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
   task_segments(s, k);
@@ -726,19 +716,34 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
     bitmap_mark(s, k, &queue, cells, ncell, rbase);
     bitmap_scan<true>(cells, ncell, warp_sums);
   }
-  // Row emission with neighbouring lanes on neighbouring cells: the ranks of adjacent cells are adjacent, so the stores
-  // of one warp instruction fall into a few sectors of Cir.
+  // Row emission: every lane walks its own cells (c, c + blockDim, ...) and emits one row per iteration, fetching its
+  // next cell when the current one is exhausted, so lanes whose cells hold few rows do not idle while a neighbour
+  // drains a full cell. Neighbouring lanes start on neighbouring cells, whose ranks are adjacent in Cir.
   if (s.debug != 2) {
-    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
-      const unsigned long long cw = cells[c];
-      unsigned long long bits = cw & kCellMask;
-      if (bits == 0) continue;
-      int32_t *o = Cir + obase + (int64_t)(cw >> kCellRows);
-      const int rowbase = rbase + c * kCellRows;
-      while (bits) {
-        *o++ = rowbase + (__ffsll((long long)bits) - 1);
-        bits &= bits - 1;
+    int c = threadIdx.x;
+    unsigned lo = 0, hi = 0;
+    int rowbase = 0;
+    int32_t *o = Cir;
+    while (true) {
+      if ((lo | hi) == 0) {
+        if (c >= ncell) break;
+        const unsigned long long cw = cells[c];
+        lo = (unsigned)cw;
+        hi = (unsigned)(cw >> 32) & ((1u << (kCellRows - 32)) - 1u);
+        o = Cir + obase + (int64_t)(cw >> kCellRows);
+        rowbase = rbase + c * kCellRows;
+        c += blockDim.x;
+        continue;
       }
+      int b;
+      if (lo) {
+        b = __ffs(lo) - 1;
+        lo &= lo - 1;
+      } else {
+        b = 31 + __ffs(hi);
+        hi &= hi - 1;
+      }
+      *o++ = rowbase + b;
     }
   }
   if (s.debug == 4) return; // mark + scan + row emission only
