@@ -15,6 +15,7 @@ from .lib import (  # noqa: F401
     DistStats,
     Grid,
     Comm,
+    SlabPipeline,
     lib_path,
     load_library,
     F64, F32, I64, I32, BOOL,

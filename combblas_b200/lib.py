@@ -337,6 +337,58 @@ class Context:
         return DeviceMatrix(self, h)
 
 
+OPTION_NAMES = ["bitmap_window_log2", "bitmap_min_nnz", "bitmap_smem_acc", "bitmap_cta_threads", "bitmap_small_threads",
+                "bitmap_small_minblocks", "bitmap_save_mb", "light_max", "force_path", "merge_engine", "summa_fused",
+                "debug_numeric"]
+
+
+class SlabPipeline:
+    """Phased multiply C(:, slab) = A x B(:, slab) (MemEfficientSpGEMM's column phases, ParFriends.h:553-772) with the
+    slabs spread over `nstreams` contexts of one GPU, each a host thread with its own CUDA stream. The slabs are
+    independent, so the symbolic pass of one (instruction bound) overlaps the numeric pass of another (bound by the
+    L2 reductions), and the host-side gaps of one stream (size read-backs, allocation) are covered by the other.
+    The first slab runs alone: it builds the per-operand caches of A (dense column index, window-major copy)."""
+
+    def __init__(self, ctx: Context, nstreams: int = 2):
+        self.ctxs = [ctx] + [Context(ctx.device) for _ in range(max(1, nstreams) - 1)]
+        self.sync_options()
+
+    def sync_options(self):
+        for name in OPTION_NAMES:
+            v = self.ctxs[0].get_option(name)
+            for c in self.ctxs[1:]:
+                c.set_option(name, v)
+
+    def launch_count(self) -> int:
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def run(self, sr: int, A: DeviceMatrix, slabs, consume):
+        """consume(index, C_slab, stats) is called on the worker thread that produced the slab and must free C_slab."""
+        import threading
+
+        self.ctxs[0].sync()  # everything the caller queued on the main stream (operands, L2 flush) is complete
+        errors = []
+
+        def work(ctx, items):
+            try:
+                for i in items:
+                    Cs, st = ctx.spgemm(sr, A, slabs[i], want_stats=True)
+                    consume(i, Cs, st)
+            except Exception as e:  # surfaced on the calling thread
+                errors.append(e)
+
+        work(self.ctxs[0], [0])
+        n = len(self.ctxs)
+        rest = list(range(1, len(slabs)))
+        threads = [threading.Thread(target=work, args=(self.ctxs[w], rest[w::n])) for w in range(n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+
 def make_grid(world: int, rank: int, layers: int = 1) -> Grid:
     g = Grid()
     rc = load_library().cbgpu_grid_make(world, rank, layers, C.byref(g))
