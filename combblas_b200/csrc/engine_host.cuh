@@ -231,9 +231,18 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     const int64_t fit = (opt.bitmap_save_mb << 20) / (int64_t)bm_bytes;
     save_count = (int)std::min<int64_t>(sc.count[SYM_BM_L], fit);
     if (save_count > 0) {
-      CB_TRY(dev_alloc_t(ctx, &saved, (size_t)save_count * max_cells));
-      CB_TRY(dev_alloc_t(ctx, &slot_of_task, (size_t)ntask));
-      CB_CUDA(ctx, cudaMemsetAsync(slot_of_task, 0xFF, sizeof(int32_t) * (size_t)ntask, st));
+      // an optimisation only: when HBM is too full for the hand-over buffer the numeric pass marks and ranks again
+      if (dev_alloc_t(ctx, &saved, (size_t)save_count * max_cells) != CBGPU_OK ||
+          dev_alloc_t(ctx, &slot_of_task, (size_t)ntask) != CBGPU_OK) {
+        dev_free(ctx, saved);
+        dev_free(ctx, slot_of_task);
+        saved = nullptr;
+        slot_of_task = nullptr;
+        save_count = 0;
+        ctx->last_error.clear();
+      } else {
+        CB_CUDA(ctx, cudaMemsetAsync(slot_of_task, 0xFF, sizeof(int32_t) * (size_t)ntask, st));
+      }
     }
   }
   auto class_weight = [](const BinResult &r, const uint8_t *tab, int c, bool second) {
