@@ -24,7 +24,7 @@ struct Options {
   int64_t num_warp_max = 256;    // warp table 512
   int64_t num_cta_max = 2048;    // CTA(256) table 4096
   // bitmap path
-  int64_t bitmap_window_log2 = 17; // rows per window (2^17 rows = 16 KiB bitmap + 8 KiB rank index)
+  int64_t bitmap_window_log2 = 17; // rows per window (2^17 rows = 23 KiB of ranked 45-row cells)
   int64_t bitmap_min_nnz = 0;      // 0 = automatic: clamp(window_rows/2048, 32, num_cta_max)
   int64_t bitmap_smem_acc = 2048;  // accumulators kept in shared memory up to this many outputs per task
   int64_t bitmap_cta_threads = 512; // CTA size of the large-task bitmap kernels (512 or 256)

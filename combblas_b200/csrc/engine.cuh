@@ -13,10 +13,10 @@
 // Per task the engine runs a symbolic pass (count distinct rows) and, after an exclusive scan over the
 // counts, a numeric pass that writes the column's rows ASCENDING together with the accumulated values:
 //   hash path   (small tasks) : shared-memory open addressing per warp or per CTA + bitonic sort of the hits
-//   bitmap path (large tasks) : shared-memory presence bitmap of the row window; popcount ranks give every row
-//                               its sorted output slot directly, so there is no sort and no probing;
-//                               values accumulate in shared memory, or straight into C in HBM (L2 atomics)
-//                               when the task has more outputs than fit.
+//   bitmap path (large tasks) : shared-memory presence bitmap of the row window in 64-bit cells (45 row bits + the
+//                               19-bit count of the rows in earlier cells): one load and a popcount give every row
+//                               its sorted output slot, so there is no sort and no probing; values accumulate
+//                               straight into C in HBM (L2 reductions), or in shared memory for tasks that fit.
 // No tensor cores: the work is irregular integer/atomic traffic; the levers are coalesced segment reads,
 // shared-memory atomics, and keeping every SM busy with size-ordered tasks.
 #pragma once
