@@ -16,6 +16,7 @@ from .lib import (  # noqa: F401
     Grid,
     Comm,
     SlabPipeline,
+    PruneStats,
     lib_path,
     load_library,
     F64, F32, I64, I32, BOOL,
@@ -29,6 +30,7 @@ from .host import (  # noqa: F401
     OrAndSRing_bool, PlusTimesSRing_bool_f64, PlusTimesSRing_i32, SelectMaxSRing_i64,
     semiring_types,
     LocalHybridSpGEMM, LocalSpGEMMHash, LocalSpGEMM, MultiwayMerge, MultiwayMergeHash, EstimateFLOP,
+    MCLPruneRecoverySelect, MemEfficientSpGEMM,
     block_range, block_owner, partition_2d, partition_3d,
 )
 

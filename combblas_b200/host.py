@@ -182,6 +182,48 @@ def LocalSpGEMM(ctx, SR: int, A: SpDCCols, B: SpDCCols, clearA=False, clearB=Fal
     return LocalHybridSpGEMM(ctx, SR, A, B, clearA, clearB)
 
 
+def MCLPruneRecoverySelect(ctx, A: SpDCCols, hardThreshold, selectNum: int, recoverNum: int, recoverPct,
+                           kselectVersion: int = 1) -> SpTuples:
+    """ParFriends.h:186-354 for a block holding whole columns (P = 1 / one rank per process column). Host block in,
+    pruned column-sorted tuples out. Both Kselect versions of the reference give the same thresholds, so
+    kselectVersion is accepted for signature parity only."""
+    dA = ctx.upload(A)
+    D = ctx.mcl_prune(dA, float(hardThreshold), int(selectNum), int(recoverNum), float(recoverPct))
+    out = _download_tuples(ctx, D)
+    D.free()
+    dA.free()
+    return out
+
+
+def MemEfficientSpGEMM(ctx, SR: int, A: SpDCCols, B: SpDCCols, phases: int, hardThreshold, selectNum: int, recoverNum: int,
+                       recoverPct, kselectVersion: int = 1, computationKernel: int = 1, perProcessMemory: int = 0) -> SpTuples:
+    """ParFriends.h:452-777 at P = 1 (the HipMCL expansion step): B is cut into `phases` column slabs (ColSplit rule),
+    every slab of C = A (x) B(:, slab) is pruned on the device by MCLPruneRecoverySelect before the next one is
+    multiplied, and the pruned slabs are concatenated (ColConcatenate). Unpruned C never exists as a whole.
+    computationKernel (hash / heap) and perProcessMemory (automatic phase count) are accepted for signature parity."""
+    _check_types(SR, A, B)
+    phases = max(1, min(int(phases), max(1, B.n)))
+    dA, dB = ctx.upload(A), ctx.upload(B)
+    slabs = ctx.colsplit(dB, phases) if phases > 1 else [dB]
+    pruned = []
+    for Bs in slabs:
+        Cs = ctx.spgemm(SR, dA, Bs)
+        pruned.append(ctx.mcl_prune(Cs, float(hardThreshold), int(selectNum), int(recoverNum), float(recoverPct)))
+        Cs.free()
+    D = ctx.colconcat(pruned) if len(pruned) > 1 else pruned[0]
+    out = _download_tuples(ctx, D)
+    if len(pruned) > 1:
+        D.free()
+    for x in pruned:
+        x.free()
+    if phases > 1:
+        for x in slabs:
+            x.free()
+    dA.free()
+    dB.free()
+    return out
+
+
 def MultiwayMerge(ctx, SR: int, ArrSpTups, mdim=0, ndim=0, delarrs=False) -> SpTuples:
     """MultiwayMerge.h:428-429: k column-sorted lists -> one, SR::add on equal (row, col).
     ArrSpTups: list of SpTuples (or SpDCCols). Zero lists -> empty mdim x ndim result."""

@@ -70,6 +70,14 @@ class DistStats(C.Structure):
         return d
 
 
+class PruneStats(C.Structure):
+    _fields_ = [("nnz_in", C.c_int64), ("nnz_out", C.c_int64), ("nzc_out", C.c_int64), ("cols_recovered", C.c_int64),
+                ("cols_selected", C.c_int64), ("cols_recovered_after_select", C.c_int64), ("ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class SlabResult(C.Structure):
     _fields_ = [("nnz", C.c_int64), ("nzc", C.c_int64), ("pattern_sum", C.c_uint64), ("value_sum", C.c_uint64)]
 
@@ -109,6 +117,9 @@ SIGNATURES = {
     "cbgpu_spgemm_symbolic": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_spgemm_local_host": (C.c_int, [_P, C.c_int, C.POINTER(_DcscView), C.POINTER(_DcscView), C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_merge": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(Stats)]),
+    "cbgpu_mcl_prune": (C.c_int, [_P, _P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.POINTER(_P), C.POINTER(PruneStats)]),
+    "cbgpu_mat_make_col_stochastic": (C.c_int, [_P, _P]),
+    "cbgpu_mat_inflate": (C.c_int, [_P, _P, C.c_double]),
     "cbgpu_grid_make": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(Grid)]),
     "cbgpu_block_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_block_owner": (C.c_int, [C.c_int64, C.c_int, C.c_int64]),
@@ -330,6 +341,22 @@ class Context:
         self._check(self.lib.cbgpu_merge(self.handle, sr, len(mats), arr, C.byref(h), C.byref(st)))
         out = DeviceMatrix(self, h)
         return (out, st) if want_stats else out
+
+    def mcl_prune(self, A: DeviceMatrix, hard_threshold: float, select_num: int, recover_num: int, recover_pct: float,
+                  want_stats=False):
+        """MCLPruneRecoverySelect (ParFriends.h:186-354) of a block holding whole columns -> new DeviceMatrix."""
+        h = _P()
+        st = PruneStats()
+        self._check(self.lib.cbgpu_mcl_prune(self.handle, A.handle, C.c_double(hard_threshold), C.c_int64(select_num),
+                                             C.c_int64(recover_num), C.c_double(recover_pct), C.byref(h), C.byref(st)))
+        out = DeviceMatrix(self, h)
+        return (out, st) if want_stats else out
+
+    def make_col_stochastic(self, A: DeviceMatrix):
+        self._check(self.lib.cbgpu_mat_make_col_stochastic(self.handle, A.handle))
+
+    def inflate(self, A: DeviceMatrix, power: float):
+        self._check(self.lib.cbgpu_mat_inflate(self.handle, A.handle, C.c_double(power)))
 
     def gen_rmat(self, scale, nedges, seed, a=0.57, b=0.19, c=0.19, scramble=True, dtype=F64, value_mode=0):
         h = _P()

@@ -171,6 +171,26 @@ int cbgpu_spgemm_local_host(cbgpu_ctx *ctx, int semiring, const cbgpu_dcsc_view 
 int cbgpu_merge(cbgpu_ctx *ctx, int semiring, int k, const cbgpu_mat *const *lists, cbgpu_mat **out,
                 cbgpu_stats *stats);
 
+/* ---------------------------------------------------------------- MCL pruning epilogue of the phased multiply
+ * replaces: MCLPruneRecoverySelect (ParFriends.h:186-354), which MemEfficientSpGEMM runs on every column slab of C
+ * (:744), for a block that holds WHOLE columns (one rank per process column): A.Prune(val <= hardThreshold), the column
+ * sums / counts (Reduce(Column)), Kselect1 (SpParMat.cpp:1413-1700) and PruneColumn(thresholds, std::less) fused into
+ * one per-column pass. Column thresholds: hardThreshold; the recoverNum-th largest entry for columns left with fewer
+ * than recoverNum entries summing below recoverPct; the selectNum-th largest for columns left with more than selectNum
+ * entries (with the reference's second recovery check after selection). Entries below their column's threshold go.
+ * Floating-point blocks only (the reference instantiates it for float / double). */
+typedef struct {
+  int64_t nnz_in, nnz_out, nzc_out;
+  int64_t cols_recovered, cols_selected, cols_recovered_after_select;
+  float ms;
+} cbgpu_prune_stats;
+int cbgpu_mcl_prune(cbgpu_ctx *ctx, const cbgpu_mat *A, double hardThreshold, int64_t selectNum, int64_t recoverNum,
+                    double recoverPct, cbgpu_mat **out, cbgpu_prune_stats *stats);
+/* in place: every column scaled to sum 1 (MakeColStochastic, Applications/MCL.cpp:389-394) */
+int cbgpu_mat_make_col_stochastic(cbgpu_ctx *ctx, cbgpu_mat *A);
+/* in place: v = pow(v, power), then MakeColStochastic (Inflate, Applications/MCL.cpp:431-437) */
+int cbgpu_mat_inflate(cbgpu_ctx *ctx, cbgpu_mat *A, double power);
+
 /* ---------------------------------------------------------------- process grids and distributed SpGEMM
  * Host-side arithmetic of the reference's distributions (no GPU needed):
  * 2D owner rule SpParMat::Owner (SpParMat.cpp:5081-5107), 3D split SpParMat3D::Owner/LocalDim

@@ -161,12 +161,40 @@ class RefOracle(_Base):
         L.ref_result_copy.argtypes = [C.c_void_p] * 4
         L.ref_result_free.argtypes = [C.c_void_p]
         L.ref_set_num_threads.argtypes = [C.c_int]
+        if hasattr(L, "ref_mcl_prune"):
+            L.ref_mcl_prune.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.c_double, C.c_int,
+                                        C.POINTER(C.c_void_p)]
+            L.ref_memeff_prune.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_int64,
+                                           C.c_double, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 
     def num_threads(self) -> int:
         return int(self.lib.ref_num_threads())
 
     def set_num_threads(self, n: int):
         self.lib.ref_set_num_threads(int(n))
+
+    def mcl_prune(self, A: Csc, hard: float, select: int, recover: int, pct: float, sr: int = 0, kselect_version: int = 1):
+        """The reference's MCLPruneRecoverySelect (ParFriends.h:186-354) on A as a P=1 SpParMat."""
+        dt = SR_DTYPES[sr][2]
+        sa, ka = _as_ref(A, dt)
+        h = C.c_void_p()
+        rc = self.lib.ref_mcl_prune(sr, C.byref(sa), hard, select, recover, pct, kselect_version, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"ref_mcl_prune failed rc={rc}")
+        return self._result(h, A.m, A.n, dt)
+
+    def memeff_prune(self, A: Csc, B: Csc, phases: int, hard: float, select: int, recover: int, pct: float, sr: int = 0,
+                     kselect_version: int = 1, kernel: int = 1):
+        """The reference's MemEfficientSpGEMM (ParFriends.h:453-777) at P=1 with its pruning parameters."""
+        da, db, dc = SR_DTYPES[sr]
+        sa, ka = _as_ref(A, da)
+        sb, kb = _as_ref(B, db)
+        h = C.c_void_p()
+        rc = self.lib.ref_memeff_prune(sr, C.byref(sa), C.byref(sb), phases, hard, select, recover, pct, kselect_version,
+                                       kernel, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"ref_memeff_prune failed rc={rc}")
+        return self._result(h, A.m, B.n, dc)
 
     def spgemm(self, A: Csc, B: Csc, sr: int = 0, routine: int = REF_LOCAL_HYBRID, canonical: bool = True,
                phases: int = 1, want_time: bool = False):
@@ -290,6 +318,50 @@ class PortOracle(_Base):
         nnz = np.zeros(B.n, dtype=np.int64)
         self.lib.port_symbolic(C.byref(sa), C.byref(sb), flop.ctypes.data, nnz.ctypes.data)
         return flop, nnz
+
+
+def kselect1(col_vals: np.ndarray, k: int):
+    """Kselect1 for one column (SpParMat.cpp:1413-1700, result rule :1672-1684): the k-th largest entry; a column with
+    fewer than k entries yields its smallest entry, an empty one numeric_limits<NT>::min()."""
+    n = len(col_vals)
+    if n == 0:
+        return np.finfo(col_vals.dtype).tiny
+    s = np.sort(col_vals)[::-1]
+    return s[k - 1] if n >= k >= 1 else s[-1]
+
+
+def mcl_prune_recovery_select(A: Csc, hard, select: int, recover: int, pct):
+    """numpy restatement of MCLPruneRecoverySelect (ParFriends.h:186-354) for a matrix whose columns are whole
+    (P = 1): per column, statistics of the entries above the hard threshold (:196-201), the recover rule (:208-243),
+    the select rule with the second recovery check (:248-335), then PruneColumn(thresholds, std::less) (:339).
+    Returns (pruned Csc, per-column thresholds)."""
+    dt = A.vals.dtype
+    hard = dt.type(hard)
+    pct = dt.type(pct)
+    thr = np.full(A.n, hard, dtype=dt)
+    keep = np.zeros(A.nnz, dtype=bool)
+    for j in range(A.n):
+        b, e = int(A.colptr[j]), int(A.colptr[j + 1])
+        v = A.vals[b:e]
+        pruned = v[v > hard]  # A.Prune(val <= hardThreshold)
+        n_all, n_pr = len(v), len(pruned)
+        s_pr = pruned.sum(dtype=dt) if n_pr else dt.type(0)
+        t = hard
+        if n_pr < recover and n_all > n_pr and s_pr < pct:
+            t = kselect1(v, recover)
+        elif select > 0 and n_pr > select:
+            t = kselect1(v, select)
+            if recover > 0:
+                sel = v[~(v < t)]
+                if len(sel) < recover and sel.sum(dtype=dt) < pct:
+                    t = kselect1(v, recover)
+        thr[j] = t
+        keep[b:e] = ~(v < t)
+    colptr = np.zeros(A.n + 1, dtype=np.int64)
+    cols = A.cols_expanded()
+    np.add.at(colptr, cols[keep] + 1, 1)
+    np.cumsum(colptr, out=colptr)
+    return Csc(A.m, A.n, colptr, A.rows[keep].copy(), A.vals[keep].copy()), thr
 
 
 def best_oracle():

@@ -200,6 +200,44 @@ extern "C" int CB_FN(ref_symbolic_sr)(const ref_csc *A, const ref_csc *B, int64_
   return 0;
 }
 
+/* MCLPruneRecoverySelect (ParFriends.h:186-354) on a P=1 SpParMat, and MemEfficientSpGEMM (ParFriends.h:453-777) with its
+ * pruning parameters. Instantiated for the floating-point PlusTimes semirings only (what MCL.cpp uses). */
+extern "C" int CB_FN(ref_mcl_prune_sr)(const ref_csc *A, double hard, int64_t select, int64_t recover, double pct,
+                                        int kselect_version, ref_result **out) {
+#if CB_SR == 0 || CB_SR == 1
+  typedef SpDCCols<IT, NTO> DC;
+  std::shared_ptr<CommGrid> grid;
+  grid.reset(new CommGrid(MPI_COMM_WORLD, 0, 0));
+  SpParMat<IT, NTO, DC> PA(make_dcsc<NTO>(A), grid);
+  MCLPruneRecoverySelect(PA, (NTO)hard, (IT)select, (IT)recover, (NTO)pct, kselect_version);
+  SpTuples<IT, NTO> ct(*PA.seqptr());
+  *out = to_result(ct, 1);
+  return 0;
+#else
+  (void)A; (void)hard; (void)select; (void)recover; (void)pct; (void)kselect_version; (void)out;
+  return -2;
+#endif
+}
+
+extern "C" int CB_FN(ref_memeff_prune_sr)(const ref_csc *A, const ref_csc *B, int phases, double hard, int64_t select,
+                                           int64_t recover, double pct, int kselect_version, int kernel, ref_result **out) {
+#if CB_SR == 0 || CB_SR == 1
+  typedef SpDCCols<IT, NT1> DA; typedef SpDCCols<IT, NT2> DB; typedef SpDCCols<IT, NTO> DC;
+  std::shared_ptr<CommGrid> grid;
+  grid.reset(new CommGrid(MPI_COMM_WORLD, 0, 0));
+  SpParMat<IT, NT1, DA> PA(make_dcsc<NT1>(A), grid);
+  SpParMat<IT, NT2, DB> PB(make_dcsc<NT2>(B), grid);
+  SpParMat<IT, NTO, DC> PC = MemEfficientSpGEMM<SR, NTO, DC>(PA, PB, phases, (NTO)hard, (IT)select, (IT)recover, (NTO)pct,
+                                                             kselect_version, kernel, (int64_t)0);
+  SpTuples<IT, NTO> ct(*PC.seqptr());
+  *out = to_result(ct, 1);
+  return 0;
+#else
+  (void)A; (void)B; (void)phases; (void)hard; (void)select; (void)recover; (void)pct; (void)kselect_version; (void)kernel; (void)out;
+  return -2;
+#endif
+}
+
 #else /* ------------------------------- dispatcher ------------------------------- */
 #include <omp.h>
 int cblas_splits = 1; /* every CombBLAS program defines this (CombBLAS.h:76) */
@@ -207,7 +245,10 @@ int cblas_splits = 1; /* every CombBLAS program defines this (CombBLAS.h:76) */
 #define DECL(i)                                                                                                        \
   extern "C" int ref_spgemm_sr##i(int, const ref_csc *, const ref_csc *, int, int, ref_result **, double *);           \
   extern "C" int ref_merge_sr##i(int, int, const ref_csc *, int, int, ref_result **, double *);                        \
-  extern "C" int ref_symbolic_sr##i(const ref_csc *, const ref_csc *, int64_t *, int64_t **, int64_t **);
+  extern "C" int ref_symbolic_sr##i(const ref_csc *, const ref_csc *, int64_t *, int64_t **, int64_t **);                \
+  extern "C" int ref_mcl_prune_sr##i(const ref_csc *, double, int64_t, int64_t, double, int, ref_result **);              \
+  extern "C" int ref_memeff_prune_sr##i(const ref_csc *, const ref_csc *, int, double, int64_t, int64_t, double, int, int, \
+                                        ref_result **);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7) DECL(8)
 #define CASE(i, call) case i: return call;
 #define ALL(fn, ...)                                                                                                   \
@@ -229,6 +270,14 @@ int ref_merge(int hash, int semiring, int k, const ref_csc *lists, int sorted, i
 }
 int ref_symbolic(int semiring, const ref_csc *A, const ref_csc *B, int64_t *nzc, int64_t **flop, int64_t **nnz) {
   ALL(ref_symbolic_sr, A, B, nzc, flop, nnz)
+}
+int ref_mcl_prune(int semiring, const ref_csc *A, double hard, int64_t select, int64_t recover, double pct,
+                  int kselect_version, ref_result **out) {
+  ALL(ref_mcl_prune_sr, A, hard, select, recover, pct, kselect_version, out)
+}
+int ref_memeff_prune(int semiring, const ref_csc *A, const ref_csc *B, int phases, double hard, int64_t select,
+                     int64_t recover, double pct, int kselect_version, int kernel, ref_result **out) {
+  ALL(ref_memeff_prune_sr, A, B, phases, hard, select, recover, pct, kselect_version, kernel, out)
 }
 void ref_free(void *p) { delete[] static_cast<int64_t *>(p); }
 int64_t ref_result_nnz(const ref_result *r) { return (int64_t)r->rows.size(); }

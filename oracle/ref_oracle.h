@@ -49,6 +49,14 @@ int ref_merge(int hash, int semiring, int k, const ref_csc *lists, int sorted, i
 /* reference symbolic pass: per-non-empty-B-column flop (estimateFLOP, mtSpGEMM.h:1058) and nnz
  * (estimateNNZ_Hash, mtSpGEMM.h:807); arrays sized nzc(B), *nzc receives the count. Caller frees with ref_free. */
 int ref_symbolic(int semiring, const ref_csc *A, const ref_csc *B, int64_t *nzc, int64_t **flop, int64_t **nnz);
+
+/* MCLPruneRecoverySelect (ParFriends.h:186-354) applied to A as a P=1 SpParMat; semiring 0 (double) or 1 (float) names
+ * the value type. Result canonical (column-major, rows ascending). */
+int ref_mcl_prune(int semiring, const ref_csc *A, double hard, int64_t select, int64_t recover, double pct,
+                  int kselect_version, ref_result **out);
+/* MemEfficientSpGEMM (ParFriends.h:453-777) at P=1 WITH its pruning parameters; kernel 1 = hash, 2 = heap */
+int ref_memeff_prune(int semiring, const ref_csc *A, const ref_csc *B, int phases, double hard, int64_t select,
+                     int64_t recover, double pct, int kselect_version, int kernel, ref_result **out);
 void ref_free(void *p);
 
 int64_t ref_result_nnz(const ref_result *r);
