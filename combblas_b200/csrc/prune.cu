@@ -52,6 +52,13 @@ struct OrdKey<float> {
 
 __device__ __forceinline__ int prune_lane() { return threadIdx.x & 31; }
 
+constexpr int kLongCol = 4096;      // columns with more entries than this are handled by a whole CTA
+constexpr int kPruneThreads = 512;  // CTA size of the long-column kernels (4 histogram bins per thread)
+constexpr int kDigitBits = 11;      // radix-select digit of the long-column kernel
+constexpr int kBins = 1 << kDigitBits;
+constexpr int kCandCap = 4096;      // candidates kept in shared memory once few enough share the selected prefix
+static_assert(kBins == 4 * kPruneThreads, "find_digit gives every thread four bins");
+
 // k-th largest of v[0..n), 1 <= k <= n, by one warp: radix select from the most significant byte of the ordered key
 template <class T>
 __device__ T warp_kth_largest(const T *v, int n, int k, int *hist /* 256 ints of this warp */) {
@@ -153,6 +160,7 @@ mcl_threshold_kernel(const int64_t *cp, const T *vals, int64_t nzc, T hard, long
   if (col >= nzc) return;
   int *hist = hist_all[warp];
   const int64_t b = cp[col];
+  if (cp[col + 1] - b > kLongCol) return; // a whole CTA takes the long columns (mcl_threshold_long_kernel)
   const int n = (int)(cp[col + 1] - b);
   const T *v = vals + b;
   int npr;
@@ -193,6 +201,7 @@ mcl_compact_kernel(const int64_t *cp, const int32_t *rows, const T *vals, int64_
   const int64_t col = (int64_t)blockIdx.x * 8 + warp;
   if (col >= nzc) return;
   const int64_t b = cp[col];
+  if (cp[col + 1] - b > kLongCol) return;
   const int n = (int)(cp[col + 1] - b);
   const T t = thr[col];
   int64_t o = optr[col];
@@ -216,6 +225,242 @@ mcl_compact_kernel(const int64_t *cp, const int32_t *rows, const T *vals, int64_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ long columns
+// One CTA per column. The passes over the column are what costs (an expansion slab is far larger than L2), so the
+// statistics of the hard threshold come with the first pass, the k-th largest value is found with 11-bit digits
+// (two passes narrow a column of 1e6 values in (0,1] to a few hundred candidates, which then live in shared memory), and
+// the survivor count falls out of the post-selection statistics.
+template <class V>
+__device__ __forceinline__ V block_sum(V v, V *scratch /* 32 */) {
+  const int lane = prune_lane(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  __syncthreads(); // scratch free
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  V s = 0;
+  for (int w = 0; w < nwarp; ++w) s += scratch[w];
+  return s;
+}
+
+// digit (bin index) where the count accumulated from the highest bin reaches `need`; out = {digit, rank inside the bin,
+// size of the bin}. Thread t owns the bins kBins-1-4t .. kBins-4-4t.
+__device__ __forceinline__ void find_digit(const int *hist, int need, int *scratch /* 32 */, int *out /* 3 */) {
+  const int lane = prune_lane(), warp = threadIdx.x >> 5;
+  int c[4], s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    c[j] = hist[kBins - 1 - (4 * (int)threadIdx.x + j)];
+    s += c[j];
+  }
+  int incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += x;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  for (int w = 0; w < warp; ++w) incl += scratch[w];
+  const int excl = incl - s;
+  if (excl < need && need <= incl) {
+    int r = need - excl;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (r > 0 && r <= c[j]) {
+        out[0] = kBins - 1 - (4 * (int)threadIdx.x + j);
+        out[1] = r;
+        out[2] = c[j];
+        r = 0;
+      } else if (r > 0) {
+        r -= c[j];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <class T>
+struct PruneShared {
+  int hist[kBins];
+  typename OrdKey<T>::U cand[kCandCap];
+  int iscratch[32];
+  T tscratch[32];
+  int out[3];
+  int ncand;
+};
+
+// Kselect1's answer for one long column, by the whole CTA
+template <class T>
+__device__ T block_kselect(const T *v, int n, long long k, PruneShared<T> &sh) {
+  typedef typename OrdKey<T>::U U;
+  const int tid = threadIdx.x;
+  if (k < 1 || (long long)n < k) { // fewer than k entries: the smallest one
+    T m = v[0];
+    for (int i = tid; i < n; i += kPruneThreads) m = v[i] < m ? v[i] : m;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      T o = __shfl_xor_sync(0xFFFFFFFFu, m, d);
+      m = o < m ? o : m;
+    }
+    __syncthreads();
+    if (prune_lane() == 0) sh.tscratch[tid >> 5] = m;
+    __syncthreads();
+    for (int w = 0; w < (kPruneThreads >> 5); ++w) m = sh.tscratch[w] < m ? sh.tscratch[w] : m;
+    __syncthreads();
+    return m;
+  }
+  U prefix = 0;
+  int need = (int)k, shift = OrdKey<T>::BITS, ncand = 0;
+  bool in_smem = false;
+  while (shift > 0) {
+    const int w = shift >= kDigitBits ? kDigitBits : shift; // 64 = 5 x 11 + 9, 32 = 2 x 11 + 10
+    const U himask = (shift >= OrdKey<T>::BITS) ? (U)0 : (U)(~(U)0 << shift); // bits fixed so far
+    shift -= w;
+    for (int i = tid; i < kBins; i += kPruneThreads) sh.hist[i] = 0;
+    __syncthreads();
+    const U dmask = (U)((1u << w) - 1u);
+    if (!in_smem) {
+      for (int i = tid; i < n; i += kPruneThreads) {
+        const U key = OrdKey<T>::key(v[i]);
+        if ((key & himask) == prefix) atomicAdd(&sh.hist[(int)((key >> shift) & dmask)], 1);
+      }
+    } else {
+      for (int i = tid; i < ncand; i += kPruneThreads) {
+        const U key = sh.cand[i];
+        if ((key & himask) == prefix) atomicAdd(&sh.hist[(int)((key >> shift) & dmask)], 1);
+      }
+    }
+    __syncthreads();
+    find_digit(sh.hist, need, sh.iscratch, sh.out); // ends with a barrier
+    const int digit = sh.out[0], cnt = sh.out[2];
+    need = sh.out[1];
+    prefix |= (U)digit << shift;
+    if (shift == 0) break;
+    if (!in_smem && cnt <= kCandCap) { // few enough values share the prefix: finish in shared memory
+      if (tid == 0) sh.ncand = 0;
+      __syncthreads();
+      const U fixed = (U)(~(U)0 << shift);
+      for (int i = tid; i < n; i += kPruneThreads) {
+        const U key = OrdKey<T>::key(v[i]);
+        if ((key & fixed) == prefix) sh.cand[atomicAdd(&sh.ncand, 1)] = key;
+      }
+      __syncthreads();
+      ncand = sh.ncand;
+      in_smem = true;
+    }
+    __syncthreads(); // sh.out / sh.hist are rewritten by the next level
+  }
+  __syncthreads();
+  return OrdKey<T>::val(prefix);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kPruneThreads)
+mcl_threshold_long_kernel(const int64_t *cp, const T *vals, const int32_t *list, T hard, long long selectNum,
+                          long long recoverNum, T recoverPct, T *thr, int64_t *keep, unsigned long long *counters) {
+  __shared__ PruneShared<T> sh;
+  const int tid = threadIdx.x;
+  const int64_t col = list[blockIdx.x];
+  const int64_t b = cp[col];
+  const int n = (int)(cp[col + 1] - b);
+  const T *v = vals + b;
+  // pass 1: statistics of A.Prune(val <= hardThreshold), and the survivors of the plain hard threshold
+  int npr = 0, nge = 0;
+  T spr = 0;
+  for (int i = tid; i < n; i += kPruneThreads) {
+    const T x = v[i];
+    if (x > hard) {
+      ++npr;
+      spr += x;
+    }
+    if (!(x < hard)) ++nge;
+  }
+  npr = block_sum<int>(npr, sh.iscratch);
+  nge = block_sum<int>(nge, sh.iscratch);
+  spr = block_sum<T>(spr, sh.tscratch);
+  T t = hard;
+  long long kept = nge;
+  const bool recover = (long long)npr < recoverNum && n > npr && spr < recoverPct;
+  const int rule = recover ? 1 : ((selectNum > 0 && (long long)npr > selectNum) ? 2 : 0);
+  if (rule) {
+    t = block_kselect<T>(v, n, rule == 1 ? recoverNum : selectNum, sh);
+    int again = 0;
+    do {
+      int n1 = 0;
+      T s1 = 0;
+      for (int i = tid; i < n; i += kPruneThreads) {
+        const T x = v[i];
+        if (!(x < t)) {
+          ++n1;
+          s1 += x;
+        }
+      }
+      n1 = block_sum<int>(n1, sh.iscratch);
+      s1 = block_sum<T>(s1, sh.tscratch);
+      kept = n1;
+      // recovery can be attempted after selection (ParFriends.h:288-331)
+      if (rule == 2 && !again && recoverNum > 0 && (long long)n1 < recoverNum && s1 < recoverPct) {
+        t = block_kselect<T>(v, n, recoverNum, sh);
+        again = 1;
+        if (tid == 0) atomicAdd(&counters[2], 1ull);
+      } else {
+        again = 0;
+      }
+    } while (again);
+    if (tid == 0) atomicAdd(&counters[rule - 1], 1ull);
+  }
+  if (tid == 0) {
+    thr[col] = t;
+    keep[col] = kept;
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kPruneThreads)
+mcl_compact_long_kernel(const int64_t *cp, const int32_t *rows, const T *vals, const int32_t *list, const T *thr,
+                        const int64_t *optr, int32_t *orows, T *ovals) {
+  __shared__ int wcnt[kPruneThreads / 32];
+  const int tid = threadIdx.x, lane = prune_lane(), warp = tid >> 5;
+  const int64_t col = list[blockIdx.x];
+  const int64_t b = cp[col];
+  const int n = (int)(cp[col + 1] - b);
+  const T t = thr[col];
+  int64_t o = optr[col];
+  for (int base = 0; base < n; base += kPruneThreads) {
+    const int i = base + tid;
+    T x = T();
+    int r = 0;
+    bool in = false;
+    if (i < n) {
+      x = vals[b + i];
+      r = rows[b + i];
+      in = !(x < t);
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kPruneThreads / 32; ++w) {
+      const int c = wcnt[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (in) {
+      const int64_t p = o + before + __popc(m & ((1u << lane) - 1u));
+      orows[p] = r;
+      ovals[p] = x;
+    }
+    o += total;
+    __syncthreads();
+  }
+}
+
+__global__ void long_cols_kernel(const int64_t *cp, int64_t nzc, int32_t *list, int *count) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nzc && cp[j + 1] - cp[j] > kLongCol) list[atomicAdd(count, 1)] = (int32_t)j;
+}
+
 template <class T>
 static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double hard, int64_t selectNum, int64_t recoverNum,
                            double recoverPct, cbgpu_mat_impl **out, cbgpu_prune_stats *stats) {
@@ -235,11 +480,28 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
   CB_CUDA(ctx, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
   int64_t nnz_out = 0;
   unsigned long long hc[4] = {0, 0, 0, 0};
+  int32_t *list = nullptr;
+  int *nlong_dev = nullptr;
+  int nlong = 0;
+  if (nzc >= (int64_t)1 << 31) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many columns");
   if (nzc > 0) {
+    CB_TRY(dev_alloc_t(ctx, &list, (size_t)nzc));
+    CB_TRY(dev_alloc_t(ctx, &nlong_dev, 1));
+    CB_CUDA(ctx, cudaMemsetAsync(nlong_dev, 0, sizeof(int), st));
+    long_cols_kernel<<<(unsigned)((nzc + 255) / 256), 256, 0, st>>>(A->cp, nzc, list, nlong_dev);
+    CB_LAUNCH_CHECK(ctx);
+    CB_CUDA(ctx, cudaMemcpyAsync(&nlong, nlong_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     mcl_threshold_kernel<T><<<(unsigned)((nzc + 7) / 8), 256, 0, st>>>(A->cp, reinterpret_cast<const T *>(A->numx), nzc, (T)hard,
                                                                       (long long)selectNum, (long long)recoverNum, (T)recoverPct,
                                                                       thr, keep, counters);
     CB_LAUNCH_CHECK(ctx);
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (nlong > 0) {
+      mcl_threshold_long_kernel<T><<<(unsigned)nlong, kPruneThreads, 0, st>>>(A->cp, reinterpret_cast<const T *>(A->numx), list,
+                                                                              (T)hard, (long long)selectNum, (long long)recoverNum,
+                                                                              (T)recoverPct, thr, keep, counters);
+      CB_LAUNCH_CHECK(ctx);
+    }
     CB_TRY(exclusive_scan_i64(ctx, keep, optr, nzc));
     CB_CUDA(ctx, cudaMemcpyAsync(&nnz_out, optr + nzc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -253,8 +515,13 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
   if (nzc > 0 && nnz_out > 0) {
     mcl_compact_kernel<T><<<(unsigned)((nzc + 7) / 8), 256, 0, st>>>(A->cp, A->ir, reinterpret_cast<const T *>(A->numx), nzc, thr,
                                                                     optr, C->ir, reinterpret_cast<T *>(C->numx));
-    cudaError_t e = cudaGetLastError();
     ctx->launches++;
+    if (nlong > 0) {
+      mcl_compact_long_kernel<T><<<(unsigned)nlong, kPruneThreads, 0, st>>>(A->cp, A->ir, reinterpret_cast<const T *>(A->numx), list,
+                                                                            thr, optr, C->ir, reinterpret_cast<T *>(C->numx));
+      ctx->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = set_error(ctx, CBGPU_ERR_CUDA, "mcl_compact_kernel: %s", cudaGetErrorString(e));
   }
   if (rc == CBGPU_OK) rc = compact_columns(ctx, A->jc, optr, nzc, &C->jc, &C->cp, &C->nzc);
@@ -262,6 +529,8 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
   dev_free(ctx, keep);
   dev_free(ctx, optr);
   dev_free(ctx, counters);
+  dev_free(ctx, list);
+  dev_free(ctx, nlong_dev);
   if (rc != CBGPU_OK) {
     mat_release(ctx, C);
     return rc;

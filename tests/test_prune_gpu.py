@@ -79,10 +79,17 @@ def test_prune_long_columns(ctx):
     rng = np.random.default_rng(11)
     m, n = 400000, 300
     lens = np.minimum(m, (rng.pareto(0.9, n) * 40).astype(np.int64))
-    lens[:4] = [300000, 100000, 1100, 1401]
+    lens[:6] = [300000, 100000, 1100, 1401, 20000, 12000]
     rows = np.concatenate([np.sort(rng.choice(m, int(k), replace=False)) for k in lens])
     cols = np.repeat(np.arange(n), lens)
     vals = rng.random(len(rows)) ** 4
+    # ties that do not fit the shared-memory candidate buffer: a column of equal values, and one whose selectNum-th
+    # largest entry lies inside a run of 9000 equal values
+    o4, o5 = int(lens[:4].sum()), int(lens[:5].sum())
+    vals[o4:o4 + 20000] = 0.125
+    vals[o5:o5 + 9000] = 0.25
+    vals[o5 + 9000:o5 + 12000] = 0.25 + rng.random(3000)
+    vals[o5:o5 + 12000] = rng.permutation(vals[o5:o5 + 12000])
     M = sp.csc_matrix((vals, (rows, cols)), shape=(m, n))
     s = np.asarray(M.sum(0)).ravel()
     s[s == 0] = 1
@@ -90,7 +97,13 @@ def test_prune_long_columns(ctx):
     want, _ = mcl_prune_recovery_select(A, 1e-4, 1100, 1400, 0.9)
     got = device_prune(ctx, A, 1e-4, 1100, 1400, 0.9)
     assert_bit_exact(got, want)
-    assert got[3].cols_selected >= 2
+    assert got[3].cols_selected >= 4
+    # a select threshold inside the tie run (column 5: 3000 larger values, then 9000 equal ones)
+    want2, _ = mcl_prune_recovery_select(A, 1e-9, 5000, 0, 0.9)
+    assert_bit_exact(device_prune(ctx, A, 1e-9, 5000, 0, 0.9), want2)
+    # recover rule on long columns: everything is below the hard threshold, the top recoverNum entries come back
+    want3, _ = mcl_prune_recovery_select(A, 0.9, 0, 7000, 10.0)
+    assert_bit_exact(device_prune(ctx, A, 0.9, 0, 7000, 10.0), want3)
 
 
 def test_make_col_stochastic_and_inflate(ctx):
