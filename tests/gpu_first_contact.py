@@ -1,7 +1,7 @@
 """First-contact GPU check: runs a ladder of cases without stopping at the first failure and prints one line each."""
 import sys, time, traceback
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import combblas_b200 as cb
 from oracle.oracle import Csc, SR_DTYPES, best_oracle, PortOracle
 from tests.util import assert_same, random_pair, rmat, to_csc, to_dcsc, typed
