@@ -476,6 +476,167 @@ static int fiber_reduce(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cbgpu_ma
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------------- fiber-fused 3D multiply
+// Option `fiber_fused` (off until it has been validated on several GPUs): the 3D product without partial results.
+// The reference's 3D algorithm lets every layer l compute the full-size partial product A(:,K_l) B(K_l,:) and then
+// reduce-scatters C along the fiber (ParFriends.h:3578-3642): the traffic and the merge are O(nnz(C)) per layer. For
+// SpGEMM nnz(C) >> nnz(A) + nnz(B), so it is far cheaper to replicate the INPUTS along the fiber instead: rank (i,j,l')
+// collects the blocks A_l(i,k) of its process row from every stage k of every layer l (row broadcasts + fiber
+// all-gather) and the column sub-slab l' of B_l(k,j) from every (l,k) (column broadcasts + fiber all-to-all), and
+// computes its final piece C(i,j)[:, sub-slab l'] = [A_0(i,:) A_1(i,:) ...] (x) [B_0(:,j); B_1(:,j); ...][:, sub-slab l'] as ONE
+// local multiply. Same operand distribution (A column-split, B row-split across layers), same products, same output
+// distribution (C column-split across layers) as Mult_AnXBn_SUMMA3D; nothing is merged.
+
+// slab[p] goes to fiber rank p, recv[p] arrives from fiber rank p (p != my layer); shapes by one all-gather
+static int fiber_exchange_slabs(cbgpu_ctx *ctx, cbgpu_comm *comm, std::vector<cbgpu_mat *> &slab, std::vector<cbgpu_mat *> &recv,
+                                int64_t *bytes) {
+  const int L = comm->grid.layers, me = comm->grid.my_layer;
+  const int dt = slab[me]->dtype;
+  const size_t vb = dtype_size(dt);
+  std::vector<int64_t> mine((size_t)3 * L), sizes((size_t)3 * L * L, 0);
+  for (int l = 0; l < L; ++l) {
+    mine[3 * l] = slab[l]->nnz;
+    mine[3 * l + 1] = slab[l]->nzc;
+    mine[3 * l + 2] = slab[l]->m;
+  }
+  int64_t *d = nullptr;
+  CB_TRY(dev_alloc_t(ctx, &d, (size_t)3 * L * (L + 1)));
+  CB_CUDA(ctx, cudaMemcpyAsync(d, mine.data(), sizeof(int64_t) * 3 * L, cudaMemcpyHostToDevice, ctx->stream));
+  CB_NCCL(ctx, nccl().AllGather(d, d + 3 * L, (size_t)3 * L, ncclInt64, comm->fiber, ctx->stream));
+  CB_CUDA(ctx, cudaMemcpyAsync(sizes.data(), d + 3 * L, sizeof(int64_t) * 3 * L * L, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CB_TRY(dev_free(ctx, d));
+  for (int p = 0; p < L; ++p) {
+    if (p == me) continue;
+    const int64_t nnz = sizes[(size_t)3 * L * p + 3 * me], nzc = sizes[(size_t)3 * L * p + 3 * me + 1];
+    const int64_t m = sizes[(size_t)3 * L * p + 3 * me + 2];
+    CB_TRY(mat_alloc(ctx, m, slab[me]->n, nnz, nzc, dt, &recv[p]));
+    if (nnz == 0) CB_CUDA(ctx, cudaMemsetAsync(recv[p]->cp, 0, 8, ctx->stream));
+  }
+  ncclResult_t r = nccl().GroupStart();
+  for (int p = 0; p < L && r == ncclSuccess; ++p) {
+    if (p == me) continue;
+    cbgpu_mat *S = slab[p], *R = recv[p];
+    if (S->nnz > 0) {
+      r = nccl().Send(S->jc, (size_t)S->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Send(S->cp, (size_t)(S->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Send(S->ir, (size_t)S->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Send(S->numx, (size_t)S->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+      *bytes += S->nzc * 16 + 8 + S->nnz * (4 + (int64_t)vb);
+    }
+    if (r == ncclSuccess && R->nnz > 0) {
+      r = nccl().Recv(R->jc, (size_t)R->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Recv(R->cp, (size_t)(R->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Recv(R->ir, (size_t)R->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Recv(R->numx, (size_t)R->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+    }
+  }
+  ncclResult_t r2 = nccl().GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess)
+    return set_error(ctx, CBGPU_ERR_NCCL, "fiber exchange failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
+  return CBGPU_OK;
+}
+
+// all blocks of `own` along communicator `c` (nranks ranks, this rank is `me`), in rank order; blk[me] == own
+static int allgather_blocks(cbgpu_ctx *ctx, ncclComm_t c, int nranks, int me, const cbgpu_mat *own, std::vector<cbgpu_mat *> &blk,
+                            std::vector<cbgpu_mat *> &owned, int64_t *bytes) {
+  std::vector<int64_t> ess;
+  CB_TRY(gather_essentials(ctx, c, nranks, own, ess));
+  blk.assign(nranks, nullptr);
+  owned.assign(nranks, nullptr);
+  for (int r = 0; r < nranks; ++r) {
+    CB_TRY(bcast_block(ctx, c, r, me, own, &ess[4 * r], own->dtype, &owned[r], bytes));
+    blk[r] = owned[r] ? owned[r] : const_cast<cbgpu_mat *>(own);
+  }
+  return CBGPU_OK;
+}
+
+static void release_all(cbgpu_ctx *ctx, std::vector<cbgpu_mat *> &v) {
+  for (cbgpu_mat *&m : v) {
+    mat_release(ctx, m);
+    m = nullptr;
+  }
+}
+
+// [A_0(i,:) A_1(i,:) ...]: the A blocks of this process row from every stage of every layer, (layer, stage) order
+static int gather_A_all_layers(cbgpu_ctx *ctx, cbgpu_comm *comm, const cbgpu_mat *A, cbgpu_mat **Aall, cbgpu_dist_stats *ds) {
+  const cbgpu_grid &g = comm->grid;
+  Timer tm(ctx->stream);
+  tm.start();
+  int rc = CBGPU_OK;
+  cbgpu_mat *Arow = nullptr; // [A_l(i,0) ... A_l(i,stages-1)] of my layer
+  const cbgpu_mat *mine = A;
+  if (g.grid_cols > 1) {
+    std::vector<cbgpu_mat *> blk, owned;
+    rc = allgather_blocks(ctx, comm->row, g.grid_cols, g.my_col, A, blk, owned, &ds->bytes_bcast);
+    if (rc == CBGPU_OK) rc = mat_colconcat(ctx, g.grid_cols, blk.data(), &Arow);
+    release_all(ctx, owned);
+    mine = Arow;
+  }
+  if (rc == CBGPU_OK) {
+    std::vector<cbgpu_mat *> blk, owned;
+    rc = allgather_blocks(ctx, comm->fiber, g.layers, g.my_layer, mine, blk, owned, &ds->bytes_fiber);
+    if (rc == CBGPU_OK) rc = mat_colconcat(ctx, g.layers, blk.data(), Aall);
+    release_all(ctx, owned);
+  }
+  mat_release(ctx, Arow);
+  ds->ms_bcast += tm.stop();
+  return rc;
+}
+
+// one column slab Bslab of this rank's B block -> this rank's final piece of C for that slab
+static int fiber_fused_slab(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *Aall, const cbgpu_mat *Bslab,
+                            cbgpu_mat **C, cbgpu_dist_stats *ds) {
+  const cbgpu_grid &g = comm->grid;
+  const int L = g.layers;
+  Timer tm(ctx->stream);
+  int rc = CBGPU_OK;
+  // [B_l(0,j); B_l(1,j); ...] of my layer (column broadcasts of the SUMMA stages)
+  tm.start();
+  cbgpu_mat *Bcol = nullptr;
+  const cbgpu_mat *mine = Bslab;
+  if (g.grid_rows > 1) {
+    std::vector<cbgpu_mat *> blk, owned;
+    rc = allgather_blocks(ctx, comm->col, g.grid_rows, g.my_row, Bslab, blk, owned, &ds->bytes_bcast);
+    if (rc == CBGPU_OK) rc = mat_rowstack(ctx, g.grid_rows, blk.data(), &Bcol);
+    release_all(ctx, owned);
+    mine = Bcol;
+    ds->stages += g.grid_rows;
+  }
+  ds->ms_bcast += tm.stop();
+  // column sub-slab l' of it goes to fiber rank l' (the split fiber_reduce applies to C: SpParMat3D.cpp:576-609)
+  std::vector<cbgpu_mat *> slab(L, nullptr), recv(L, nullptr), parts(L, nullptr);
+  tm.start();
+  for (int l = 0; l < L && rc == CBGPU_OK; ++l) {
+    int64_t c0, c1;
+    cbgpu_block_range(mine->n, L, l, &c0, &c1);
+    rc = mat_colslice(ctx, mine, c0, c1, &slab[l]);
+  }
+  if (rc == CBGPU_OK) rc = fiber_exchange_slabs(ctx, comm, slab, recv, &ds->bytes_fiber);
+  cbgpu_mat *Ball = nullptr;
+  if (rc == CBGPU_OK) {
+    for (int l = 0; l < L; ++l) parts[l] = (l == g.my_layer) ? slab[l] : recv[l];
+    rc = mat_rowstack(ctx, L, parts.data(), &Ball);
+  }
+  ds->ms_fiber_exchange += tm.stop();
+  release_all(ctx, slab);
+  release_all(ctx, recv);
+  mat_release(ctx, Bcol);
+  if (rc == CBGPU_OK && Aall->n != Ball->m)
+    rc = set_error(ctx, CBGPU_ERR_DIMMISMATCH, "fiber-fused multiply: inner dimensions differ (%lld vs %lld)", (long long)Aall->n,
+                   (long long)Ball->m);
+  if (rc == CBGPU_OK) {
+    cbgpu_stats st;
+    memset(&st, 0, sizeof(st));
+    tm.start();
+    rc = cbgpu_spgemm_local(ctx, semiring, Aall, Ball, C, &st);
+    ds->ms_multiply += tm.stop();
+    if (rc == CBGPU_OK) add_stats(ds->local, st);
+  }
+  mat_release(ctx, Ball);
+  return rc;
+}
+
 } // namespace cbgpu
 
 extern "C" {
@@ -503,11 +664,18 @@ int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
   memset(&ds, 0, sizeof(ds));
   Timer all(ctx->stream);
   all.start();
-  cbgpu_mat *Cl = nullptr; // this layer's partial product: full block shape
-  CB_TRY(summa_layer(ctx, comm, semiring, A, B, &Cl, &ds));
   int rc = CBGPU_OK;
-  if (comm->grid.layers == 1) *C = Cl;
-  else rc = fiber_reduce(ctx, comm, semiring, Cl, C, &ds);
+  if (comm->grid.layers > 1 && ctx->opt.fiber_fused) {
+    cbgpu_mat *Aall = nullptr;
+    rc = gather_A_all_layers(ctx, comm, A, &Aall, &ds);
+    if (rc == CBGPU_OK) rc = fiber_fused_slab(ctx, comm, semiring, Aall, B, C, &ds);
+    mat_release(ctx, Aall);
+  } else {
+    cbgpu_mat *Cl = nullptr; // this layer's partial product: full block shape
+    CB_TRY(summa_layer(ctx, comm, semiring, A, B, &Cl, &ds));
+    if (comm->grid.layers == 1) *C = Cl;
+    else rc = fiber_reduce(ctx, comm, semiring, Cl, C, &ds);
+  }
   ds.ms_total = all.stop();
   if (stats) *stats = ds;
   return rc;
@@ -529,6 +697,30 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
   std::vector<cbgpu_mat *> Bs(phases, nullptr);
   if (phases == 1) Bs[0] = const_cast<cbgpu_mat *>(B);
   else CB_TRY(cbgpu_mat_colsplit(ctx, B, phases, Bs.data()));
+  const bool fiber_fused = L > 1 && ctx->opt.fiber_fused;
+  if (fiber_fused) {
+    // inputs replicated along the fiber instead of partial results reduced along it: A's side is gathered once for all
+    // phases, every phase exchanges its (small) slab of B and multiplies; no second thread, nothing to merge
+    cbgpu_mat *Aall = nullptr;
+    int rcf = gather_A_all_layers(ctx, comm, A, &Aall, &ds);
+    for (int p = 0; p < phases && rcf == CBGPU_OK; ++p) {
+      cbgpu_mat *Cp = nullptr;
+      rcf = fiber_fused_slab(ctx, comm, semiring, Aall, Bs[p], &Cp, &ds);
+      if (rcf != CBGPU_OK) break;
+      results[p].nnz = Cp->nnz;
+      results[p].nzc = Cp->nzc;
+      results[p].pattern_sum = results[p].value_sum = 0;
+      if (want_checksum) rcf = cbgpu_mat_checksum(ctx, Cp, &results[p].pattern_sum, &results[p].value_sum);
+      if (slabs) slabs[p] = Cp;
+      else mat_release(ctx, Cp);
+    }
+    mat_release(ctx, Aall);
+    if (phases > 1)
+      for (int p = 0; p < phases; ++p) mat_release(ctx, Bs[p]);
+    ds.ms_total = all.stop();
+    if (stats) *stats = ds;
+    return rcf;
+  }
   if (L > 1 && !comm->ctx2) {
     int rc2 = cbgpu_create(ctx->device, nullptr, &comm->ctx2);
     if (rc2 != CBGPU_OK) return set_error(ctx, rc2, "could not create the second context of the pipeline");

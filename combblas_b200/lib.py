@@ -365,7 +365,7 @@ class Context:
 
 
 OPTION_NAMES = ["bitmap_window_log2", "bitmap_min_nnz", "bitmap_smem_acc", "bitmap_cta_threads", "bitmap_small_threads",
-                "bitmap_small_minblocks", "bitmap_save_mb", "light_max", "force_path", "merge_engine", "summa_fused",
+                "bitmap_small_minblocks", "bitmap_save_mb", "light_max", "force_path", "merge_engine", "summa_fused", "fiber_fused",
                 "debug_numeric"]
 
 

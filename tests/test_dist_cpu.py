@@ -101,3 +101,53 @@ def test_distributed_plan_over_gloo(world, layers):
     port = 29600 + world * 10 + layers
     mp.spawn(_worker, args=(world, layers, port, ret), nprocs=world, join=True)
     assert len(ret) == world and all(ret.values()), dict(ret)
+
+
+@pytest.mark.parametrize("world,layers", [(2, 2), (8, 2), (4, 4), (16, 4)])
+def test_fiber_fused_plan_equals_global_product(world, layers):
+    """The plan of the fiber-fused 3D multiply (csrc/dist.cu, option fiber_fused), replayed with scipy for every rank:
+    A blocks of the process row from every (layer, stage) side by side, the rank's column sub-slab of the B blocks of its
+    process column from every (layer, stage) stacked in the same order -- one local product, which must be exactly the
+    rank's block of the global product in the reference's 3D output distribution (C column-split across layers)."""
+    import scipy.sparse as sp
+
+    sys.path.insert(0, ROOT)
+    import combblas_b200 as cb
+    from combblas_b200 import lib as cblib
+    from combblas_b200.host import local_range
+    from tests.util import rmat
+
+    G = rmat(9, 8, seed=4)
+    G.data = np.floor(G.data) + 1.0  # small integers: products and sums are exact, comparison can be bit for bit
+    n = G.shape[0]
+    A = cb.SpDCCols.from_scipy(G, np.float64)
+    Cg = (G @ G).tocsc()
+    Cg.sort_indices()
+    grids = [cblib.make_grid(world, r, layers) for r in range(world)]
+    at = {(g.my_row, g.my_col, g.my_layer): r for r, g in enumerate(grids)}
+    assert len(at) == world
+    Ablk = [cb.partition_3d(A, g, True) for g in grids]
+    Bblk = [cb.partition_3d(A, g, False) for g in grids]
+
+    def sci(D):
+        cp, rows, vals = D.to_csc()
+        return sp.csc_matrix((vals, rows, cp), shape=(D.m, D.n))
+
+    for r, g in enumerate(grids):
+        pr, L = g.grid_cols, g.layers
+        Aall = sp.hstack([sci(Ablk[at[(g.my_row, k, l)]]) for l in range(L) for k in range(pr)], format="csc")
+        parts = []
+        for l in range(L):
+            Bcol = sp.vstack([sci(Bblk[at[(k, g.my_col, l)]]) for k in range(pr)], format="csc")
+            c0, c1 = cb.block_range(Bcol.shape[1], L, g.my_layer)
+            parts.append(Bcol[:, c0:c1])
+        Ball = sp.vstack(parts, format="csc")
+        assert Aall.shape[1] == Ball.shape[0] == n
+        mine = (Aall @ Ball).tocsc()
+        mine.sort_indices()
+        r0, r1, c0, c1 = local_range(g, n, n, True)
+        want = Cg[r0:r1, c0:c1].tocsc()
+        want.sort_indices()
+        assert mine.shape == want.shape, (r, mine.shape, want.shape)
+        assert np.array_equal(mine.indptr, want.indptr) and np.array_equal(mine.indices, want.indices), f"rank {r}: pattern"
+        assert np.array_equal(mine.data, want.data), f"rank {r}: values"
