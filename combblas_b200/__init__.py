@@ -17,6 +17,7 @@ from .lib import (  # noqa: F401
     Comm,
     SlabPipeline,
     PruneStats,
+    MemEffStats,
     lib_path,
     load_library,
     F64, F32, I64, I32, BOOL,

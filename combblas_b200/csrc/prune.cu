@@ -13,7 +13,10 @@
 // hard threshold, the choice recover / select / recover-after-select, a radix select for the k-th largest value where
 // one is needed, and the count of survivors. A second kernel compacts the survivors in place order.
 #include <float.h>
+#include <math.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "common.cuh"
 #include "util.cuh"
 
@@ -611,6 +614,82 @@ int cbgpu_mcl_prune(cbgpu_ctx *ctx, const cbgpu_mat *A, double hardThreshold, in
   if (A->dtype == CBGPU_F64) return mcl_prune_typed<double>(ctx, A, hardThreshold, selectNum, recoverNum, recoverPct, out, stats);
   if (A->dtype == CBGPU_F32) return mcl_prune_typed<float>(ctx, A, hardThreshold, selectNum, recoverNum, recoverPct, out, stats);
   return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "MCL pruning needs a floating-point block (dtype %d)", A->dtype);
+}
+
+/* MemEfficientSpGEMM at P = 1 (ParFriends.h:452-777): column slabs of B (ColSplit rule), one multiply per slab, every
+ * finished slab pruned in HBM by MCLPruneRecoverySelect (:744) before the next one is multiplied, ColConcatenate (:772). */
+int cbgpu_memefficient_spgemm(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                              double hardThreshold, int64_t selectNum, int64_t recoverNum, double recoverPct, cbgpu_mat **C,
+                              cbgpu_memeff_stats *stats) {
+  if (!ctx || !A || !B || !C) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cbgpu_memeff_stats ms;
+  memset(&ms, 0, sizeof(ms));
+  cudaEvent_t e0, e1;
+  CB_CUDA(ctx, cudaEventCreate(&e0));
+  CB_CUDA(ctx, cudaEventCreate(&e1));
+  cudaEventRecord(e0, ctx->stream);
+  if (phases <= 0) {
+    // CalculateNumberOfPhases (ParFriends.h:780-843) with the exact symbolic count instead of an estimate: an unpruned
+    // slab (12 B per entry) may take a quarter of the HBM that is free right now
+    int64_t flops = 0, nnz = 0;
+    CB_TRY(cbgpu_spgemm_symbolic(ctx, A, B, &flops, &nnz));
+    size_t freeb = 0, totalb = 0;
+    CB_CUDA(ctx, cudaMemGetInfo(&freeb, &totalb));
+    const double budget = (double)std::max<size_t>(freeb / 4, (size_t)1 << 30);
+    phases = (int)std::min<double>(std::max<double>(1.0, ceil((double)nnz * 12.0 / budget)), (double)std::max<int64_t>(1, B->n));
+  }
+  phases = (int)std::min<int64_t>(std::max<int64_t>(1, phases), std::max<int64_t>(1, B->n));
+  ms.phases = phases;
+  std::vector<cbgpu_mat *> slabs(phases, nullptr), pieces(phases, nullptr);
+  int rc = CBGPU_OK;
+  if (phases > 1) rc = cbgpu_mat_colsplit(ctx, B, phases, slabs.data());
+  for (int p = 0; p < phases && rc == CBGPU_OK; ++p) {
+    const cbgpu_mat *Bs = phases > 1 ? slabs[p] : B;
+    cbgpu_mat *Cs = nullptr;
+    cbgpu_stats st;
+    memset(&st, 0, sizeof(st));
+    rc = cbgpu_spgemm_local(ctx, semiring, A, Bs, &Cs, &st);
+    if (rc != CBGPU_OK) break;
+    ms.flops += st.flops;
+    ms.nnz_unpruned += st.nnz_out;
+    ms.ms_multiply += st.ms_total;
+    if (Cs->dtype == CBGPU_F64 || Cs->dtype == CBGPU_F32) {
+      cbgpu_prune_stats ps;
+      rc = cbgpu_mcl_prune(ctx, Cs, hardThreshold, selectNum, recoverNum, recoverPct, &pieces[p], &ps);
+      mat_release(ctx, Cs);
+      if (rc != CBGPU_OK) break;
+      ms.ms_prune += ps.ms;
+      ms.cols_recovered += ps.cols_recovered;
+      ms.cols_selected += ps.cols_selected;
+      ms.cols_recovered_after_select += ps.cols_recovered_after_select;
+    } else {
+      pieces[p] = Cs; // the reference instantiates the pruning for floating-point results only
+    }
+  }
+  cbgpu_mat *out = nullptr;
+  if (rc == CBGPU_OK) {
+    if (phases > 1) rc = cbgpu_mat_colconcat(ctx, phases, pieces.data(), &out);
+    else {
+      out = pieces[0];
+      pieces[0] = nullptr;
+    }
+  }
+  for (int p = 0; p < phases; ++p) {
+    mat_release(ctx, pieces[p]);
+    if (phases > 1) mat_release(ctx, slabs[p]);
+  }
+  if (rc == CBGPU_OK) {
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms.ms_total, e0, e1);
+    ms.nnz_out = out->nnz;
+    if (stats) *stats = ms;
+    *C = out;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 int cbgpu_mat_make_col_stochastic(cbgpu_ctx *ctx, cbgpu_mat *A) {

@@ -199,26 +199,14 @@ def MemEfficientSpGEMM(ctx, SR: int, A: SpDCCols, B: SpDCCols, phases: int, hard
                        recoverPct, kselectVersion: int = 1, computationKernel: int = 1, perProcessMemory: int = 0) -> SpTuples:
     """ParFriends.h:452-777 at P = 1 (the HipMCL expansion step): B is cut into `phases` column slabs (ColSplit rule),
     every slab of C = A (x) B(:, slab) is pruned on the device by MCLPruneRecoverySelect before the next one is
-    multiplied, and the pruned slabs are concatenated (ColConcatenate). Unpruned C never exists as a whole.
-    computationKernel (hash / heap) and perProcessMemory (automatic phase count) are accepted for signature parity."""
+    multiplied, and the pruned slabs are concatenated (ColConcatenate). Unpruned C never exists as a whole
+    (cbgpu_memefficient_spgemm). phases <= 0 picks the phase count from the symbolic pass and the free HBM.
+    computationKernel (hash / heap) and perProcessMemory are accepted for signature parity."""
     _check_types(SR, A, B)
-    phases = max(1, min(int(phases), max(1, B.n)))
     dA, dB = ctx.upload(A), ctx.upload(B)
-    slabs = ctx.colsplit(dB, phases) if phases > 1 else [dB]
-    pruned = []
-    for Bs in slabs:
-        Cs = ctx.spgemm(SR, dA, Bs)
-        pruned.append(ctx.mcl_prune(Cs, float(hardThreshold), int(selectNum), int(recoverNum), float(recoverPct)))
-        Cs.free()
-    D = ctx.colconcat(pruned) if len(pruned) > 1 else pruned[0]
+    D = ctx.memefficient_spgemm(SR, dA, dB, int(phases), float(hardThreshold), int(selectNum), int(recoverNum), float(recoverPct))
     out = _download_tuples(ctx, D)
-    if len(pruned) > 1:
-        D.free()
-    for x in pruned:
-        x.free()
-    if phases > 1:
-        for x in slabs:
-            x.free()
+    D.free()
     dA.free()
     dB.free()
     return out

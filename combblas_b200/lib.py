@@ -78,6 +78,15 @@ class PruneStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class MemEffStats(C.Structure):
+    _fields_ = [("phases", C.c_int), ("flops", C.c_int64), ("nnz_unpruned", C.c_int64), ("nnz_out", C.c_int64),
+                ("cols_recovered", C.c_int64), ("cols_selected", C.c_int64), ("cols_recovered_after_select", C.c_int64),
+                ("ms_multiply", C.c_float), ("ms_prune", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class SlabResult(C.Structure):
     _fields_ = [("nnz", C.c_int64), ("nzc", C.c_int64), ("pattern_sum", C.c_uint64), ("value_sum", C.c_uint64)]
 
@@ -118,6 +127,8 @@ SIGNATURES = {
     "cbgpu_spgemm_local_host": (C.c_int, [_P, C.c_int, C.POINTER(_DcscView), C.POINTER(_DcscView), C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_merge": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_mcl_prune": (C.c_int, [_P, _P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.POINTER(_P), C.POINTER(PruneStats)]),
+    "cbgpu_memefficient_spgemm": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
+                                            C.POINTER(_P), C.POINTER(MemEffStats)]),
     "cbgpu_mat_make_col_stochastic": (C.c_int, [_P, _P]),
     "cbgpu_mat_inflate": (C.c_int, [_P, _P, C.c_double]),
     "cbgpu_grid_make": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(Grid)]),
@@ -349,6 +360,17 @@ class Context:
         st = PruneStats()
         self._check(self.lib.cbgpu_mcl_prune(self.handle, A.handle, C.c_double(hard_threshold), C.c_int64(select_num),
                                              C.c_int64(recover_num), C.c_double(recover_pct), C.byref(h), C.byref(st)))
+        out = DeviceMatrix(self, h)
+        return (out, st) if want_stats else out
+
+    def memefficient_spgemm(self, sr: int, A: DeviceMatrix, B: DeviceMatrix, phases: int, hard_threshold: float, select_num: int,
+                            recover_num: int, recover_pct: float, want_stats=False):
+        """MemEfficientSpGEMM (ParFriends.h:452-777) at P = 1 on resident operands; phases <= 0 = automatic."""
+        h = _P()
+        st = MemEffStats()
+        self._check(self.lib.cbgpu_memefficient_spgemm(self.handle, sr, A.handle, B.handle, int(phases), C.c_double(hard_threshold),
+                                                       C.c_int64(select_num), C.c_int64(recover_num), C.c_double(recover_pct),
+                                                       C.byref(h), C.byref(st)))
         out = DeviceMatrix(self, h)
         return (out, st) if want_stats else out
 

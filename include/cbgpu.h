@@ -186,6 +186,20 @@ typedef struct {
 } cbgpu_prune_stats;
 int cbgpu_mcl_prune(cbgpu_ctx *ctx, const cbgpu_mat *A, double hardThreshold, int64_t selectNum, int64_t recoverNum,
                     double recoverPct, cbgpu_mat **out, cbgpu_prune_stats *stats);
+/* The phased multiply with its pruning epilogue on one GPU. replaces: MemEfficientSpGEMM (ParFriends.h:452-777) at P = 1:
+ * B is cut into `phases` column slabs (ColSplit rule, dcsc.cpp:1202), every slab of C = A (x) B(:, slab) is pruned in HBM by
+ * cbgpu_mcl_prune before the next one is multiplied, the pruned slabs are concatenated (ColConcatenate, :772).
+ * phases <= 0: chosen from the exact symbolic nnz(C) so that an unpruned slab fits a quarter of the free HBM
+ * (CalculateNumberOfPhases, ParFriends.h:780-843). Results that are not floating point are multiplied but not pruned. */
+typedef struct {
+  int phases;
+  int64_t flops, nnz_unpruned, nnz_out;
+  int64_t cols_recovered, cols_selected, cols_recovered_after_select;
+  float ms_multiply, ms_prune, ms_total;
+} cbgpu_memeff_stats;
+int cbgpu_memefficient_spgemm(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                              double hardThreshold, int64_t selectNum, int64_t recoverNum, double recoverPct, cbgpu_mat **C,
+                              cbgpu_memeff_stats *stats);
 /* in place: every column scaled to sum 1 (MakeColStochastic, Applications/MCL.cpp:389-394) */
 int cbgpu_mat_make_col_stochastic(cbgpu_ctx *ctx, cbgpu_mat *A);
 /* in place: v = pow(v, power), then MakeColStochastic (Inflate, Applications/MCL.cpp:431-437) */

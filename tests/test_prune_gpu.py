@@ -158,6 +158,29 @@ def test_memefficient_spgemm_with_pruning_equals_reference(ctx, ref_oracle, phas
         assert 0 < want.nnz
 
 
+def test_memefficient_spgemm_device_entry(ctx, ref_oracle):
+    """cbgpu_memefficient_spgemm on resident operands: automatic phase count, statistics, integer results unpruned"""
+    M = dyadic_rmat(10, 3)
+    A = Csc.from_scipy(M, np.float64)
+    dA = ctx.upload(cb.SpDCCols.from_scipy(M, np.float64))
+    want = ref_oracle.memeff_prune(A, A, 1, 0.4, 20, 25, 40.0)
+    for phases in (0, 5):
+        D, st = ctx.memefficient_spgemm(cb.PlusTimesSRing_f64, dA, dA, phases, 0.4, 20, 25, 40.0, want_stats=True)
+        rows, cols, vals = ctx.download_coo(D)
+        assert np.array_equal(cols, want.cols_expanded()) and np.array_equal(rows, want.rows) and np.array_equal(vals, want.vals)
+        assert st.phases == (phases if phases else 1) and st.nnz_out == want.nnz and st.nnz_unpruned > st.nnz_out
+        assert st.cols_selected > 0 and st.flops > 0
+        D.free()
+    dA.free()
+    Mi = M.copy()
+    Mi.data = np.floor(Mi.data * 256)
+    dI = ctx.upload(cb.SpDCCols.from_scipy(Mi, np.int64))
+    D, st = ctx.memefficient_spgemm(cb.PlusTimesSRing_i64, dI, dI, 3, 0.4, 20, 25, 40.0, want_stats=True)
+    assert st.nnz_out == st.nnz_unpruned == (Mi @ Mi).nnz
+    D.free()
+    dI.free()
+
+
 def test_hipmcl_expansion_step(ctx, ref_oracle):
     """column-stochastic weighted R-MAT (MCL.cpp:389-394), one expansion with MCL-style parameters scaled to the size"""
     M = rmat(11, 8, 5)
