@@ -469,6 +469,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "fiber_fused")) return &o.fiber_fused;
+  if (!strcmp(name, "hash_rank_sort")) return &o.hash_rank_sort;
   if (!strcmp(name, "debug_numeric")) return &o.debug_numeric;
   return nullptr;
 }

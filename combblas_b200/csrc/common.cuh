@@ -35,6 +35,7 @@ struct Options {
   int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only
   int64_t debug_numeric = 0;       // profiling experiments only; non-zero values produce wrong results
   int64_t summa_fused = 1;         // 1 = all SUMMA stages as one stacked local multiply, 0 = stage loop + merge
+  int64_t hash_rank_sort = 0;      // per-warp hash classes: rank the hits by counting instead of sorting them (to be validated)
   int64_t fiber_fused = 0;         // 3D: replicate the inputs along the fiber instead of reducing partial results (see dist.cu)
   int64_t merge_engine = 0;        // 1 = k-way merges through the accumulation engine instead of streaming 2-way rounds
 };

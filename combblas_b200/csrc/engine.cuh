@@ -55,6 +55,7 @@ struct Source {
   const int32_t *task_col;
   const uint32_t *task_win;
   int debug; // profiling experiments only (results are wrong when non-zero): 1 = no accumulate, 2 = no rank, 3 = no value load
+  int rank_sort; // per-warp hash classes: order the hits by counting smaller keys instead of a bitonic sort (option hash_rank_sort)
 };
 
 struct Task {
@@ -546,12 +547,27 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   }
   group_sync<GROUP_WARPS>();
   const int n = *cnt;
+  const int64_t obase = taskptr[t];
+  if (GROUP_WARPS == 1 && s.rank_sort) {
+    // The keys of a task are distinct, so the sorted position of a hit is the number of smaller keys: every lane counts
+    // them for its hits against broadcast reads of the whole list (n <= 256) -- no barriers, no dependent shared-memory
+    // round trips, where the bitonic network needs log^2(n)/2 of them.
+    const unsigned *keyhi = reinterpret_cast<const unsigned *>(sortbuf) + 1; // high word of entry j at keyhi[2 * j]
+    for (int i = gtid; i < n; i += GT) {
+      const unsigned long long e = sortbuf[i];
+      const unsigned key = (unsigned)(e >> 32);
+      int r = 0;
+      for (int j = 0; j < n; ++j) r += keyhi[2 * j] < key ? 1 : 0;
+      Cir[obase + r] = (int32_t)key;
+      Cval[obase + r] = SR::to_out(acc[(unsigned)e]);
+    }
+    return;
+  }
   int P = 2;
   while (P < n) P <<= 1;
   for (int i = n + gtid; i < P; i += GT) sortbuf[i] = ~0ull;
   group_sync<GROUP_WARPS>();
   group_bitonic<GROUP_WARPS>(sortbuf, P, gtid, GT);
-  const int64_t obase = taskptr[t];
   for (int i = gtid; i < n; i += GT) {
     unsigned long long e = sortbuf[i];
     Cir[obase + i] = (int32_t)(e >> 32);

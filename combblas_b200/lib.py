@@ -387,7 +387,7 @@ class Context:
 
 
 OPTION_NAMES = ["bitmap_window_log2", "bitmap_min_nnz", "bitmap_smem_acc", "bitmap_cta_threads", "bitmap_small_threads",
-                "bitmap_small_minblocks", "bitmap_save_mb", "light_max", "force_path", "merge_engine", "summa_fused", "fiber_fused",
+                "bitmap_small_minblocks", "bitmap_save_mb", "light_max", "force_path", "merge_engine", "summa_fused", "fiber_fused", "hash_rank_sort",
                 "debug_numeric"]
 
 
