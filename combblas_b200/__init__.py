@@ -31,7 +31,7 @@ from .host import (  # noqa: F401
     OrAndSRing_bool, PlusTimesSRing_bool_f64, PlusTimesSRing_i32, SelectMaxSRing_i64,
     semiring_types,
     LocalHybridSpGEMM, LocalSpGEMMHash, LocalSpGEMM, MultiwayMerge, MultiwayMergeHash, EstimateFLOP,
-    MCLPruneRecoverySelect, MemEfficientSpGEMM,
+    MCLPruneRecoverySelect, MemEfficientSpGEMM, CalculateNumberOfPhases,
     block_range, block_owner, partition_2d, partition_3d,
 )
 

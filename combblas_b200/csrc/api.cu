@@ -473,6 +473,19 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "debug_numeric")) return &o.debug_numeric;
   return nullptr;
 }
+int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_process, int idx_bytes, int in_val_bytes,
+                           int out_val_bytes, int64_t per_process_memory_gb) {
+  if (max_local_nnz_a < 0 || nnz_product_per_process < 0 || idx_bytes <= 0 || in_val_bytes <= 0 || out_val_bytes <= 0)
+    return CBGPU_ERR_INVALID;
+  const int64_t per_in = 2 * (int64_t)idx_bytes + in_val_bytes, per_out = 2 * (int64_t)idx_bytes + out_val_bytes;
+  const int64_t input_mem = max_local_nnz_a * per_in * 4;           // four copies, two of them SUMMA's (ParFriends.h:802)
+  const int64_t asquare_mem = nnz_product_per_process * per_out * 2; // an extra copy in the merge / selection (:806)
+  const int64_t remaining = per_process_memory_gb * 1000000000ll - input_mem; // every phase result is discarded (:825)
+  if (remaining <= 0) return CBGPU_ERR_INVALID;
+  const int64_t phases = 1 + asquare_mem / remaining;
+  return phases > 0x7FFFFFFF ? 0x7FFFFFFF : (int)phases;
+}
+
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {
   int64_t *s = option_slot(ctx, name);
   if (!s) return set_error(ctx, CBGPU_ERR_INVALID, "unknown option %s", name);

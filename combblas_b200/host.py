@@ -182,6 +182,19 @@ def LocalSpGEMM(ctx, SR: int, A: SpDCCols, B: SpDCCols, clearA=False, clearB=Fal
     return LocalHybridSpGEMM(ctx, SR, A, B, clearA, clearB)
 
 
+def CalculateNumberOfPhases(max_local_nnz_A: int, nnz_product_per_process: int, perProcessMemory: int, idx_bytes: int = 8,
+                            in_val_bytes: int = 8, out_val_bytes: int = 8) -> int:
+    """ParFriends.h:779-832 (host arithmetic only, no GPU): phases = 1 + asquareMem / remainingMem. The reference feeds
+    it an estimate of the per-process nnz of the product; ctx.symbolic(A, B) gives the exact number."""
+    from .lib import load_library
+
+    r = load_library().cbgpu_calculate_phases(int(max_local_nnz_A), int(nnz_product_per_process), idx_bytes, in_val_bytes,
+                                              out_val_bytes, int(perProcessMemory))
+    if r < 1:
+        raise ValueError("the operands alone do not fit perProcessMemory")
+    return r
+
+
 def MCLPruneRecoverySelect(ctx, A: SpDCCols, hardThreshold, selectNum: int, recoverNum: int, recoverPct,
                            kselectVersion: int = 1) -> SpTuples:
     """ParFriends.h:186-354 for a block holding whole columns (P = 1 / one rank per process column). Host block in,

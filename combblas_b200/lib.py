@@ -129,6 +129,7 @@ SIGNATURES = {
     "cbgpu_mcl_prune": (C.c_int, [_P, _P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.POINTER(_P), C.POINTER(PruneStats)]),
     "cbgpu_memefficient_spgemm": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
                                             C.POINTER(_P), C.POINTER(MemEffStats)]),
+    "cbgpu_calculate_phases": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "cbgpu_mat_make_col_stochastic": (C.c_int, [_P, _P]),
     "cbgpu_mat_inflate": (C.c_int, [_P, _P, C.c_double]),
     "cbgpu_grid_make": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(Grid)]),

@@ -200,6 +200,13 @@ typedef struct {
 int cbgpu_memefficient_spgemm(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                               double hardThreshold, int64_t selectNum, int64_t recoverNum, double recoverPct, cbgpu_mat **C,
                               cbgpu_memeff_stats *stats);
+/* Host arithmetic of CalculateNumberOfPhases (ParFriends.h:779-832), no GPU needed: phases = 1 + asquareMem / remainingMem
+ * with asquareMem = nnz_product_per_process * (2 idx_bytes + out_val_bytes) * 2 and remainingMem = per_process_memory_gb
+ * * 1e9 - max_local_nnz_a * (2 idx_bytes + in_val_bytes) * 4. The reference estimates nnz_product_per_process
+ * (EstPerProcessNnzSUMMA, :1698); here cbgpu_spgemm_symbolic supplies the exact count. Returns the phase count (>= 1),
+ * or CBGPU_ERR_INVALID when the inputs alone exceed the memory. */
+int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_process, int idx_bytes, int in_val_bytes,
+                           int out_val_bytes, int64_t per_process_memory_gb);
 /* in place: every column scaled to sum 1 (MakeColStochastic, Applications/MCL.cpp:389-394) */
 int cbgpu_mat_make_col_stochastic(cbgpu_ctx *ctx, cbgpu_mat *A);
 /* in place: v = pow(v, power), then MakeColStochastic (Inflate, Applications/MCL.cpp:431-437) */

@@ -130,3 +130,22 @@ def test_host_spdccols_roundtrip():
     assert D.nzc == int((np.diff(M.indptr) > 0).sum())
     S = D.colslice(10, 30)
     assert S.nnz == M[:, 10:30].nnz and S.n == 20
+
+
+def test_calculate_phases_arithmetic():
+    """CalculateNumberOfPhases (ParFriends.h:779-832) restated: phases = 1 + asquareMem / remainingMem"""
+    import combblas_b200 as cb
+
+    def ref(gannz, asq, mem_gb, si=8, sv_in=8, sv_out=8):
+        input_mem = gannz * (2 * si + sv_in) * 4
+        asquare_mem = asq * (2 * si + sv_out) * 2
+        return 1 + asquare_mem // (mem_gb * 1000000000 - input_mem)
+
+    for gannz, asq, mem in [(16_000_000, 9_700_000_000, 64), (65_000_000, 72_000_000_000, 180), (1000, 5000, 1), (4_000_000, 0, 2)]:
+        assert cb.CalculateNumberOfPhases(gannz, asq, mem) == ref(gannz, asq, mem)
+    assert cb.CalculateNumberOfPhases(16_000_000, 9_700_000_000, 64, idx_bytes=4, in_val_bytes=4, out_val_bytes=4) == \
+        ref(16_000_000, 9_700_000_000, 64, 4, 4, 4)
+    import pytest
+
+    with pytest.raises(ValueError):
+        cb.CalculateNumberOfPhases(10_000_000_000, 1, 1)  # the inputs alone exceed 1 GB
