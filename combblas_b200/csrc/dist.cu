@@ -107,6 +107,17 @@ int cbgpu_grid_make(int world, int rank, int layers, cbgpu_grid *g) {
   return CBGPU_OK;
 }
 
+// the rank map of the older 3D code (3DSpGEMM/CCGrid.h:14-17): the layer index runs fastest
+int cbgpu_grid_make_ccgrid(int world, int rank, int layers, cbgpu_grid *g) {
+  int rc = cbgpu_grid_make(world, rank, layers, g);
+  if (rc != CBGPU_OK) return rc;
+  g->my_layer = rank % layers;          // layer_grid  = myrank % c_factor
+  int in_layer = rank / layers;         // RankInLayer = myrank / c_factor
+  g->my_row = in_layer / g->grid_cols;  // RankInCol   = RankInLayer / GridCols
+  g->my_col = in_layer % g->grid_cols;  // RankInRow   = RankInLayer % GridCols
+  return CBGPU_OK;
+}
+
 int cbgpu_block_range(int64_t dim, int parts, int index, int64_t *begin, int64_t *end) {
   if (parts < 1 || index < 0 || index >= parts || dim < 0) return CBGPU_ERR_INVALID;
   int64_t per = dim / parts;

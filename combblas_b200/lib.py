@@ -133,6 +133,7 @@ SIGNATURES = {
     "cbgpu_mat_make_col_stochastic": (C.c_int, [_P, _P]),
     "cbgpu_mat_inflate": (C.c_int, [_P, _P, C.c_double]),
     "cbgpu_grid_make": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(Grid)]),
+    "cbgpu_grid_make_ccgrid": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(Grid)]),
     "cbgpu_block_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_block_owner": (C.c_int, [C.c_int64, C.c_int, C.c_int64]),
     "cbgpu_grid_local_range": (C.c_int, [C.POINTER(Grid), C.c_int64, C.c_int64, C.c_int] + [C.POINTER(C.c_int64)] * 4),
@@ -439,9 +440,11 @@ class SlabPipeline:
             raise errors[0]
 
 
-def make_grid(world: int, rank: int, layers: int = 1) -> Grid:
+def make_grid(world: int, rank: int, layers: int = 1, ccgrid: bool = False) -> Grid:
+    """CommGrid / CommGrid3D rank map, or (ccgrid=True) the one of the older 3D code (3DSpGEMM/CCGrid.h:14-17)."""
     g = Grid()
-    rc = load_library().cbgpu_grid_make(world, rank, layers, C.byref(g))
+    fn = load_library().cbgpu_grid_make_ccgrid if ccgrid else load_library().cbgpu_grid_make
+    rc = fn(world, rank, layers, C.byref(g))
     if rc != 0:
         raise CbgpuError(rc, f"no {layers}-layer square grid over {world} ranks (reference: NOTSQUARE / GRIDMISMATCH)")
     return g

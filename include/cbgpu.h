@@ -225,6 +225,9 @@ typedef struct {
   int my_layer, my_row, my_col; /* position of `rank` */
 } cbgpu_grid;
 int cbgpu_grid_make(int world, int rank, int layers, cbgpu_grid *grid);
+/* same grid shape with the rank map of the older 3D code path (3DSpGEMM/CCGrid.h:14-17: layer = rank % c,
+ * rank in layer = rank / c); the communicators of cbgpu_comm_create follow whichever map built the grid */
+int cbgpu_grid_make_ccgrid(int world, int rank, int layers, cbgpu_grid *grid);
 /* half-open range [begin,end) of the global dimension `dim` owned by block `index` of `parts` (last takes remainder) */
 int cbgpu_block_range(int64_t dim, int parts, int index, int64_t *begin, int64_t *end);
 int cbgpu_block_owner(int64_t dim, int parts, int64_t global_index);

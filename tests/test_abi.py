@@ -149,3 +149,23 @@ def test_calculate_phases_arithmetic():
 
     with pytest.raises(ValueError):
         cb.CalculateNumberOfPhases(10_000_000_000, 1, 1)  # the inputs alone exceed 1 GB
+
+
+def test_ccgrid_rank_map():
+    """3DSpGEMM/CCGrid.h:14-17: layer = rank % c, RankInLayer = rank / c, row = RankInLayer / cols, col = RankInLayer % cols;
+    CommGrid3D.h:75-76 (the default map): layer = rank / procPerLayer, rankInLayer = rank % procPerLayer"""
+    from combblas_b200 import lib as cblib
+
+    for world, c in [(2, 2), (8, 2), (16, 4), (18, 2), (4, 1)]:
+        per = world // c
+        pr = int(round(per ** 0.5))
+        seen = set()
+        for rank in range(world):
+            g = cblib.make_grid(world, rank, c, ccgrid=True)
+            ril = rank // c
+            assert (g.my_layer, g.my_row, g.my_col) == (rank % c, ril // pr, ril % pr)
+            assert (g.grid_rows, g.grid_cols, g.layers) == (pr, pr, c)
+            seen.add((g.my_layer, g.my_row, g.my_col))
+            d = cblib.make_grid(world, rank, c)
+            assert (d.my_layer, d.my_row, d.my_col) == (rank // per, (rank % per) // pr, (rank % per) % pr)
+        assert len(seen) == world
