@@ -1,6 +1,8 @@
 """GPU: the device MCL pruning epilogue (cbgpu_mcl_prune, cbgpu_mat_make_col_stochastic, cbgpu_mat_inflate) and the
 phased multiply with pruning (MemEfficientSpGEMM mirror) against the oracle: the numpy restatement of
 MCLPruneRecoverySelect (pinned against the reference in tests/test_prune_oracle.py) and the reference itself."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -197,3 +199,21 @@ def test_hipmcl_expansion_step(ctx, ref_oracle):
     assert got.getnnz() == want.nnz
     assert np.array_equal(got.cols, want.cols_expanded()) and np.array_equal(got.rows, want.rows)
     assert np.allclose(got.vals, want.vals, rtol=1e-12, atol=0)
+
+
+@pytest.mark.skipif(os.environ.get("CBGPU_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="written without GPU time left to run it once; enable with CBGPU_TEST_EXPERIMENTAL=1")
+def test_prune_fuzz_against_oracle(ctx):
+    """the seeded draws of tests/test_prune_oracle.py::test_restatement_fuzz_against_reference on the device"""
+    rng = np.random.default_rng(2026)
+    for it in range(80):
+        m, n = int(rng.integers(1, 400)), int(rng.integers(3, 120))
+        A = skewed_stochastic(max(m, 8), n, 1000 + it, np.float64)
+        if it % 4 == 0:
+            A = Csc(A.m, A.n, A.colptr, A.rows, np.round(A.vals * 8) / 8 + (rng.integers(0, 2, A.nnz) * 0.125))
+        hard = float(rng.choice([0.0, -1.0, 1e-4, 1e-2, 0.05, 0.3]))
+        select = int(rng.choice([0, 1, 2, 5, 17, 1100]))
+        recover = int(rng.choice([0, 1, 3, 9, 25, 1400]))
+        pct = float(rng.choice([0.0, 0.3, 0.9, 1.5, 1e9]))
+        want, _ = mcl_prune_recovery_select(A, hard, select, recover, pct)
+        assert_bit_exact(device_prune(ctx, A, hard, select, recover, pct), want)

@@ -91,3 +91,20 @@ def test_every_rule_fires():
                     if len(sel) < recover and sel.sum(dtype=dt) < pct_t:
                         fired.add("recover_after_select")
     assert fired == {"recover", "select", "recover_after_select"}, fired
+
+
+def test_restatement_fuzz_against_reference(ref_oracle):
+    """80 seeded random (shape, parameter) draws, including k larger than any column, zero / negative thresholds and ties"""
+    rng = np.random.default_rng(2026)
+    for it in range(80):
+        m, n = int(rng.integers(1, 400)), int(rng.integers(3, 120))
+        A = skewed_stochastic(max(m, 8), n, 1000 + it, np.float64)
+        if it % 4 == 0:  # ties: few distinct values
+            A = Csc(A.m, A.n, A.colptr, A.rows, np.round(A.vals * 8) / 8 + (rng.integers(0, 2, A.nnz) * 0.125))
+        hard = float(rng.choice([0.0, -1.0, 1e-4, 1e-2, 0.05, 0.3]))
+        select = int(rng.choice([0, 1, 2, 5, 17, 1100]))
+        recover = int(rng.choice([0, 1, 3, 9, 25, 1400]))
+        pct = float(rng.choice([0.0, 0.3, 0.9, 1.5, 1e9]))
+        want = ref_oracle.mcl_prune(A, hard, select, recover, pct)
+        got, _ = mcl_prune_recovery_select(A, hard, select, recover, pct)
+        assert same(got, want), (it, m, n, hard, select, recover, pct, got.nnz, want.nnz)
