@@ -55,7 +55,9 @@ struct Source {
   const int32_t *task_col;
   const uint32_t *task_win;
   int debug; // profiling experiments only (results are wrong when non-zero): 1 = no accumulate, 2 = no rank, 3 = no value load
+#ifdef CBGPU_EXPERIMENTAL_RANK_SORT
   int rank_sort; // per-warp hash classes: order the hits by counting smaller keys instead of a bitonic sort (option hash_rank_sort)
+#endif
 };
 
 struct Task {
@@ -548,6 +550,7 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   group_sync<GROUP_WARPS>();
   const int n = *cnt;
   const int64_t obase = taskptr[t];
+#ifdef CBGPU_EXPERIMENTAL_RANK_SORT // build with `make EXTRA=-DCBGPU_EXPERIMENTAL_RANK_SORT`: written when no GPU time was left to run it
   if (GROUP_WARPS == 1 && s.rank_sort) {
     // The keys of a task are distinct, so the sorted position of a hit is the number of smaller keys: every lane counts
     // them for its hits against broadcast reads of the whole list (n <= 256) -- no barriers, no dependent shared-memory
@@ -563,6 +566,7 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
     }
     return;
   }
+#endif
   int P = 2;
   while (P < n) P <<= 1;
   for (int i = n + gtid; i < P; i += GT) sortbuf[i] = ~0ull;

@@ -290,7 +290,8 @@ def test_large_scale_properties(ctx):
                     reason="options written without GPU time to validate them; run with CBGPU_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("sr", [0, 3, 5])
 def test_experimental_hash_rank_sort(ctx, oracle, sr):
-    """option hash_rank_sort: the per-warp hash classes order their hits by counting smaller keys (no bitonic sort)"""
+    """option hash_rank_sort (library built with EXTRA=-DCBGPU_EXPERIMENTAL_RANK_SORT): the per-warp hash classes order
+    their hits by counting smaller keys (no bitonic sort)"""
     ctx.set_option("hash_rank_sort", 1)
     ctx.set_option("force_path", 1)  # hash wherever it fits
     try:
