@@ -459,7 +459,9 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   Options &o = ctx->opt;
   if (!strcmp(name, "bitmap_window_log2")) return &o.bitmap_window_log2;
   if (!strcmp(name, "bitmap_min_nnz")) return &o.bitmap_min_nnz;
-  if (!strcmp(name, "bitmap_smem_acc")) return &o.bitmap_smem_acc;
+  if (!strcmp(name, "shared_acc")) return &o.shared_acc;
+  if (!strcmp(name, "shared_acc_max")) return &o.shared_acc_max;
+  if (!strcmp(name, "shared_acc_small_max")) return &o.shared_acc_small_max;
   if (!strcmp(name, "bitmap_cta_threads")) return &o.bitmap_cta_threads;
   if (!strcmp(name, "bitmap_small_threads")) return &o.bitmap_small_threads;
   if (!strcmp(name, "bitmap_save_mb")) return &o.bitmap_save_mb;
@@ -469,8 +471,8 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "fiber_fused")) return &o.fiber_fused;
+  if (!strcmp(name, "fiber_pipeline")) return &o.fiber_pipeline;
   if (!strcmp(name, "hash_rank_sort")) return &o.hash_rank_sort;
-  if (!strcmp(name, "debug_numeric")) return &o.debug_numeric;
   return nullptr;
 }
 int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_process, int idx_bytes, int in_val_bytes,
@@ -489,8 +491,6 @@ int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_proc
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {
   int64_t *s = option_slot(ctx, name);
   if (!s) return set_error(ctx, CBGPU_ERR_INVALID, "unknown option %s", name);
-  if (!strcmp(name, "bitmap_smem_acc") && (value < 256 || value > 16384))
-    return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_smem_acc must be in [256, 16384]");
   if (!strcmp(name, "bitmap_cta_threads") && value != 256 && value != 512)
     return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_cta_threads must be 256 or 512");
   if (!strcmp(name, "bitmap_small_threads") && value != 128 && value != 256)

@@ -26,17 +26,19 @@ struct Options {
   // bitmap path
   int64_t bitmap_window_log2 = 17; // rows per window (2^17 rows = 23 KiB of ranked 45-row cells)
   int64_t bitmap_min_nnz = 0;      // 0 = automatic: clamp(window_rows/2048, 32, num_cta_max)
-  int64_t bitmap_smem_acc = 2048;  // accumulators kept in shared memory up to this many outputs per task
+  int64_t shared_acc = 1;          // 1 = bitmap tasks whose outputs fit accumulate in shared memory (exchange protocol), 0 = all in C (L2 reductions)
+  int64_t shared_acc_max = 0;      // > 0: upper limit on the outputs of a shared-accumulator task (default: what the CTA shapes hold)
+  int64_t shared_acc_small_max = -1; // >= 0: upper limit on the outputs of the small (256-thread) shape
   int64_t bitmap_cta_threads = 512; // CTA size of the large-task bitmap kernels (512 or 256)
   int64_t bitmap_small_threads = 128; // CTA size of the small-task bitmap kernels (128 or 256)
   int64_t bitmap_save_mb = 6144;   // HBM budget (MiB) for the ranked cells the symbolic pass hands to the numeric pass; 0 = off
   int64_t light_max = 256;         // with several row windows, columns up to this many products stay one task (<= 2048)
   int64_t bitmap_small_minblocks = 8; // resident CTAs per SM the 128-thread numeric bitmap kernel is compiled for (8 or 12)
   int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only
-  int64_t debug_numeric = 0;       // profiling experiments only; non-zero values produce wrong results
   int64_t summa_fused = 1;         // 1 = all SUMMA stages as one stacked local multiply, 0 = stage loop + merge
   int64_t hash_rank_sort = 0;      // per-warp hash classes: rank the hits by counting instead of sorting them (to be validated)
-  int64_t fiber_fused = 0;         // 3D: replicate the inputs along the fiber instead of reducing partial results (see dist.cu)
+  int64_t fiber_fused = 1;         // 3D: replicate the inputs along the fiber instead of reducing partial results (see dist.cu); 0 = the reference's fiber reduction
+  int64_t fiber_pipeline = 0;      // fiber_fused == 0 only: second host thread + stream overlaps the fiber reduction of slab p with the multiply of slab p+1
   int64_t merge_engine = 0;        // 1 = k-way merges through the accumulation engine instead of streaming 2-way rounds
 };
 

@@ -54,7 +54,6 @@ struct Source {
   // tasks (null task_col: task t is column t over all windows)
   const int32_t *task_col;
   const uint32_t *task_win;
-  int debug; // profiling experiments only (results are wrong when non-zero): 1 = no accumulate, 2 = no rank, 3 = no value load
 #ifdef CBGPU_EXPERIMENTAL_RANK_SORT
   int rank_sort; // per-warp hash classes: order the hits by counting smaller keys instead of a bitonic sort (option hash_rank_sort)
 #endif
@@ -363,6 +362,127 @@ __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task 
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------ flat walk
+// Whole-CTA walk over the PRODUCTS of a task, one product per lane and step, whatever the segment lengths are.
+// A chunk of up to CH segments is staged in shared memory: the empty ones are dropped, every other one leaves the
+// exclusive prefix of the lengths (pre), its multiplier, and base = beg - pre, so that product q of the chunk lives at
+// position base[seg] + q of the row/value arrays. Warp w owns the products [w*T/nw, (w+1)*T/nw) of the chunk and keeps a
+// cursor: the segment of its next product. Per step of 32 products the lanes read the next 32 boundaries pre[cursor+1+lane];
+// a boundary that falls L < 32 products ahead sets bit L, one REDUX.OR merges the bits (the segments are non-empty, so the
+// boundaries are distinct) and a popcount below the lane gives every lane its segment: no search, no per-segment loop,
+// loads coalesced inside every segment. The load of step i+1 is issued before step i is consumed.
+// The average segment of the large R-MAT tasks is 46..80 products; the per-segment cost of the segment-by-segment walk
+// above (cta_walk) was about 50 instructions, i.e. as much as the products themselves.
+template <int CH>
+struct FlatQueueT {
+  long long base[CH];
+  unsigned long long mult[CH];
+  unsigned pre[CH + 34];
+  unsigned long long warp_tot[32];
+};
+
+template <class SR, bool MERGE, bool NEED_VAL, int CH, class USE>
+__device__ __forceinline__ void flat_walk(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<CH> *q, USE &&use) {
+  typedef typename SR::b_t mult_t;
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  constexpr int nwarp = CH >> 5; // blockDim.x == CH
+  constexpr unsigned long long kLenMask = (1ull << 40) - 1ull;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int32_t *__restrict__ rows = k.rows;
+  const aval_t *__restrict__ vals = reinterpret_cast<const aval_t *>(k.vals);
+  for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
+    __syncthreads(); // previous chunk fully consumed
+    int64_t beg = 0;
+    int len = 0;
+    mult_t mult = mult_t();
+    if (cbase + threadIdx.x < k.seg_end) load_segment<SR, MERGE, NEED_VAL>(s, k, cbase + threadIdx.x, beg, len, mult);
+    // one block-wide exclusive scan of (non-empty ? 1 : 0, len) packed as count << 40 | products
+    const unsigned long long x = (len > 0 ? (1ull << 40) : 0ull) | (unsigned long long)(unsigned)len;
+    unsigned long long incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) q->warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long wv = lane < nwarp ? q->warp_tot[lane] : 0ull, winc = wv;
+#pragma unroll
+    for (int d = 1; d < nwarp; d <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+      if (lane >= d) winc += v;
+    }
+    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, nwarp - 1);
+    const unsigned long long excl = __shfl_sync(0xFFFFFFFFu, winc - wv, warp) + incl - x;
+    const int nseg = (int)(total >> 40);
+    const unsigned T = (unsigned)(total & kLenMask); // products of the chunk: CH segments of at most 2^19 rows
+    if (len > 0) {
+      const int idx = (int)(excl >> 40);
+      const unsigned pre = (unsigned)(excl & kLenMask);
+      q->pre[idx] = pre;
+      q->base[idx] = beg - (long long)pre;
+      if (NEED_VAL) q->mult[idx] = mult_bits<mult_t>(mult);
+    }
+    if (threadIdx.x < 34) q->pre[nseg + threadIdx.x] = threadIdx.x == 0 ? T : 0xFFFFFFFFu;
+    __syncthreads();
+    if (T == 0) continue;
+    const unsigned lo = (unsigned)((unsigned long long)T * (unsigned)warp / (unsigned)nwarp);
+    const unsigned hi = (unsigned)((unsigned long long)T * (unsigned)(warp + 1) / (unsigned)nwarp);
+    if (hi <= lo) continue;
+    int cur; // segment of product lo: the largest s with pre[s] <= lo
+    {
+      int a = 0, b = nseg - 1;
+      while (a < b) {
+        const int mid = (a + b + 1) >> 1;
+        if (q->pre[mid] <= lo) a = mid;
+        else b = mid - 1;
+      }
+      cur = a;
+    }
+    struct Fetched {
+      int row;
+      aval_t val;
+      mult_t mu;
+      bool valid;
+    };
+    auto fetch = [&](unsigned q0) -> Fetched {
+      Fetched f;
+      const unsigned L = q->pre[cur + 1 + lane] - q0; // >= 1: the segments are non-empty and `cur` holds product q0
+      const unsigned M = __reduce_or_sync(0xFFFFFFFFu, L < 32u ? (1u << L) : 0u);
+      const bool at32 = __any_sync(0xFFFFFFFFu, L == 32u);
+      const int seg = cur + __popc(M & (0xFFFFFFFFu >> (31 - lane)));
+      cur += __popc(M) + (at32 ? 1 : 0);
+      const unsigned qq = q0 + (unsigned)lane;
+      f.valid = qq < hi;
+      f.row = 0;
+      f.val = aval_t();
+      f.mu = mult_t();
+      if (f.valid) {
+        const long long pos = q->base[seg] + (long long)qq;
+        f.row = rows[pos];
+        if (NEED_VAL) {
+          f.val = vals[pos];
+          f.mu = bits_mult<mult_t>(q->mult[seg]);
+        }
+      }
+      return f;
+    };
+    unsigned q0 = lo;
+    Fetched now = fetch(q0);
+    while (true) {
+      const unsigned q1 = q0 + 32u;
+      const bool more = q1 < hi; // warp-uniform
+      Fetched next;
+      if (more) next = fetch(q1);
+      if (now.valid) use(now.row, now.val, now.mu);
+      if (!more) break;
+      now = next;
+      q0 = q1;
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------ K1: products per task
 template <class SR, bool MERGE>
 __global__ void __launch_bounds__(256) task_flop_kernel(Source<SR, MERGE> s, int64_t ntask, int64_t *flop) {
@@ -634,19 +754,19 @@ __device__ __forceinline__ Window task_window(const Src &s, const Task &k, int64
 
 // clear the cells, then set the bit of every row that occurs in the task
 template <class SR, bool MERGE, int THREADS>
-__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, CtaQueueT<THREADS> *q,
+__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<THREADS> *q,
                                             unsigned long long *cells, int ncell, int rbase) {
   uint4 *c4 = reinterpret_cast<uint4 *>(cells);
   const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) c4[i] = make_uint4(0, 0, 0, 0);
   unsigned *words = reinterpret_cast<unsigned *>(cells);
-  auto ld = [&](int64_t pos) { return k.rows[pos]; };
-  auto use = [&](int row, typename SR::b_t) {
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  auto use = [&](int row, aval_t, typename SR::b_t) {
     const unsigned r = (unsigned)(row - rbase);
     const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
     atomicOr(&words[2 * cell + (bit >> 5)], 1u << (bit & 31));
   };
-  cta_walk<SR, MERGE, false>(s, k, q, ld, use); // starts and ends with __syncthreads
+  flat_walk<SR, MERGE, false>(s, k, q, use); // starts and ends with __syncthreads
 }
 
 // number of present rows; with RANKS the exclusive prefix of every cell is written into its high bits.
@@ -678,7 +798,7 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
                   unsigned long long *saved, int64_t save_stride, int save_count, int32_t *slot_of_task) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
-  __shared__ CtaQueueT<THREADS> queue;
+  __shared__ FlatQueueT<THREADS> queue;
   __shared__ int warp_sums[33];
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
@@ -715,7 +835,7 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   // layout: cells[max_cells] u64 | acc[...] acc_t
   unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
   acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
-  __shared__ CtaQueueT<THREADS> queue;
+  __shared__ FlatQueueT<THREADS> queue;
   __shared__ int warp_sums[33];
   int t = order[blockIdx.x];
   Task k = load_task(s, t);
@@ -739,7 +859,7 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
   // Row emission: every lane walks its own cells (c, c + blockDim, ...) and emits one row per iteration, fetching its
   // next cell when the current one is exhausted, so lanes whose cells hold few rows do not idle while a neighbour
   // drains a full cell. Neighbouring lanes start on neighbouring cells, whose ranks are adjacent in Cir.
-  if (s.debug != 2) {
+  {
     int c = threadIdx.x;
     unsigned lo = 0, hi = 0;
     int rowbase = 0;
@@ -766,33 +886,101 @@ num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int6
       *o++ = rowbase + b;
     }
   }
-  if (s.debug == 4) return; // mark + scan + row emission only
   if (GMEM_ACC) {
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(SR::identity());
   } else {
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) acc[i] = SR::identity();
   }
   __syncthreads();
-  if (s.debug == 3) return; // everything but the accumulate walk
   typedef typename Source<SR, MERGE>::aval_t aval_t;
-  auto ld = [&](int64_t pos) { return RowVal<aval_t>{k.rows[pos], ((const aval_t *)k.vals)[pos]}; };
-  auto use = [&](const RowVal<aval_t> &x, typename SR::b_t mu) {
-    const unsigned r = (unsigned)(x.row - rbase);
+  auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
+    const unsigned r = (unsigned)(row - rbase);
     const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
     const unsigned long long cw = cells[cell];
     const unsigned rank = (unsigned)(cw >> kCellRows) + (unsigned)__popcll(cw & ((1ull << bit) - 1ull));
     acc_t v;
-    if (MERGE) v = SR::from_out((out_t)x.val);
-    else v = SR::mul((typename SR::a_t)x.val, mu);
-    if (s.debug == 1) {
-      if (v == SR::identity() && rank == 0x7FFFFFFFu) Cval[obase] = SR::to_out(v); // keep the work alive, never taken
-    } else if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
+    if (MERGE) v = SR::from_out((out_t)aval);
+    else v = SR::mul((typename SR::a_t)aval, mu);
+    if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
     else SR::accumulate(&acc[rank], v);
   };
-  cta_walk<SR, MERGE, true>(s, k, &queue, ld, use);
+  flat_walk<SR, MERGE, true>(s, k, &queue, use);
   if (!GMEM_ACC) {
     for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(acc[i]);
   }
+}
+
+// K4 (bitmap, accumulators in shared memory): the numeric kernel of every task whose outputs fit the CTA's shared memory.
+// Ranked cells as above (handed over by the symbolic pass, or marked and scanned again); the sorted rows are scattered by
+// rank into a staging area and leave with coalesced stores; every product then finds its slot with one cell load and a
+// popcount and is added to a shared-memory accumulator with the exchange protocol of semiring.cuh (no CAS loop, no L2
+// reduction); the values leave once, coalesced. Nothing of C is touched twice and nothing is pre-filled.
+// FIRST: most outputs of the class receive a single product (compression close to 1).
+template <class SR, bool MERGE, int THREADS, int MINB, bool FIRST>
+__global__ void __launch_bounds__(THREADS, MINB)
+num_sacc_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t m, int max_cells, const int64_t *taskptr, int32_t *Cir,
+                typename SR::out_t *Cval, const unsigned long long *saved, int64_t save_stride, const int32_t *slot_of_task) {
+  typedef typename SR::acc_t acc_t;
+  typedef typename SR::out_t out_t;
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: cells[max_cells] u64 | acc[outputs of the largest task of the class] acc_t
+  unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
+  acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
+  __shared__ FlatQueueT<THREADS> queue;
+  __shared__ int warp_sums[33];
+  const int t = order[blockIdx.x];
+  Task k = load_task(s, t);
+  task_segments(s, k);
+  const Window w = task_window(s, k, m);
+  const int rbase = w.rbase, ncell = w.ncell;
+  const int64_t obase = taskptr[t];
+  const int nnz = (int)(taskptr[t + 1] - obase);
+  const int slot = slot_of_task ? slot_of_task[t] : -1;
+  if (slot >= 0) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(saved + (int64_t)slot * save_stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(cells);
+    const int nvec = (ncell + 1) >> 1;
+    for (int i = threadIdx.x; i < nvec; i += THREADS) dst[i] = src[i];
+    __syncthreads();
+  } else {
+    bitmap_mark(s, k, &queue, cells, ncell, rbase);
+    bitmap_scan<true>(cells, ncell, warp_sums);
+  }
+  // rows: every thread unpacks its cells into the staging area (the accumulator array, not yet in use) at the ranks the
+  // cells carry, then the CTA copies the sorted list out with coalesced stores
+  int32_t *stage = reinterpret_cast<int32_t *>(acc);
+  for (int c = threadIdx.x; c < ncell; c += THREADS) {
+    const unsigned long long cw = cells[c];
+    unsigned lo = (unsigned)cw;
+    unsigned hi = (unsigned)(cw >> 32) & ((1u << (kCellRows - 32)) - 1u);
+    int o = (int)(cw >> kCellRows);
+    const int rowbase = rbase + c * kCellRows;
+    while (lo) {
+      stage[o++] = rowbase + __ffs(lo) - 1;
+      lo &= lo - 1;
+    }
+    while (hi) {
+      stage[o++] = rowbase + 31 + __ffs(hi);
+      hi &= hi - 1;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nnz; i += THREADS) Cir[obase + i] = stage[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity();
+  auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
+    const unsigned r = (unsigned)(row - rbase);
+    const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
+    const unsigned long long cw = cells[cell];
+    const unsigned rank = (unsigned)(cw >> kCellRows) + (unsigned)__popcll(cw & ((1ull << bit) - 1ull));
+    acc_t v;
+    if (MERGE) v = SR::from_out((out_t)aval);
+    else v = SR::mul((typename SR::a_t)aval, mu);
+    SR::template accumulate_shared<FIRST>(&acc[rank], v);
+  };
+  flat_walk<SR, MERGE, true>(s, k, &queue, use); // starts and ends with __syncthreads
+  for (int i = threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(acc[i]);
 }
 
 } // namespace cbgpu

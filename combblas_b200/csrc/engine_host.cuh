@@ -34,11 +34,11 @@ static __global__ void sym_bucket_kernel(const int64_t *flop, const uint32_t *ta
   bucket[i] = (uint8_t)((sb == 0 || !use_bitmap) ? sb : sb + 40);
 }
 
-// numeric path choice per task: bucket = size bucket of the outputs (+0 hash, +40 bitmap/shared accumulators,
-// +80 bitmap/accumulators in C itself)
+// numeric path choice per task: bucket = size bucket of the outputs (+0 hash, +80 bitmap with accumulators in C itself,
+// +120 / +160 / +200 bitmap with shared-memory accumulators in the small / medium / large CTA shape)
 static __global__ void num_bucket_kernel(const int64_t *nnz, const uint32_t *task_win, int nwin, int64_t ntask,
-                                         int64_t bitmap_min_nnz, int64_t hash_max_nnz, int64_t smem_acc_max, int force_path,
-                                         uint8_t *bucket) {
+                                         int64_t bitmap_min_nnz, int64_t hash_max_nnz, int64_t cap_s, int64_t cap_m,
+                                         int64_t cap_l, int force_path, uint8_t *bucket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntask) return;
   int64_t v = nnz[i];
@@ -52,7 +52,10 @@ static __global__ void num_bucket_kernel(const int64_t *nnz, const uint32_t *tas
   if (force_path == 1 && v <= hash_max_nnz) use_bitmap = false;
   if (force_path == 2 && can_bitmap) use_bitmap = true;
   if (!use_bitmap) bucket[i] = (uint8_t)sb;
-  else bucket[i] = (uint8_t)(sb + (v <= smem_acc_max ? 40 : 80));
+  else if (v <= cap_s) bucket[i] = (uint8_t)(sb + 120);
+  else if (v <= cap_m) bucket[i] = (uint8_t)(sb + 160);
+  else if (v <= cap_l) bucket[i] = (uint8_t)(sb + 200);
+  else bucket[i] = (uint8_t)(sb + 80);
 }
 
 static __global__ void col_task_count_kernel(const int64_t *colflop, int64_t ncol, int nwin, int64_t lightmax, int64_t *cnt) {
@@ -118,7 +121,17 @@ struct EngineIO {
 
 // symbolic kernel classes (launch order) and numeric kernel classes
 enum { SYM_BM_L = 0, SYM_BM_S = 1, SYM_H_CTA = 2, SYM_H_WARP = 3, SYM_H_WARP_S = 4 };
-enum { NUM_BM_G = 0, NUM_BM_L = 1, NUM_BM_S = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_M2 = 5, NUM_H_WARP_M = 6, NUM_H_WARP_S = 7 };
+enum { NUM_BM_G = 0, NUM_SA_L = 1, NUM_SA_M = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_M2 = 5, NUM_H_WARP_M = 6, NUM_H_WARP_S = 7, NUM_SA_S = 8 };
+
+// shape of the shared-accumulator numeric classes: CTA size and resident CTAs per SM (32 warps per SM in every shape)
+constexpr int kSaccThreadsS = 256, kSaccBlocksS = 4, kSaccThreadsM = 512, kSaccBlocksM = 2, kSaccThreadsL = 1024, kSaccBlocksL = 1;
+// dynamic shared memory one CTA of a shape can have: the SM's 228 KiB minus 1 KiB reserved per resident CTA, split evenly,
+// minus the static workspace of the kernel (flat-walk queue + scan scratch)
+inline int64_t sacc_dynamic_smem(const cbgpu_ctx_impl *ctx, int threads, int blocks, size_t queue_bytes) {
+  const int64_t per_sm = 228 * 1024, per_cta = std::min<int64_t>((per_sm - 1024 * blocks) / blocks, ctx->max_smem_optin > 0 ? ctx->max_smem_optin : 227 * 1024);
+  (void)threads;
+  return ((per_cta - (int64_t)queue_bytes - 256) / 16) * 16;
+}
 
 // src must arrive with Air/Aval (whole columns) and, when the block has several row windows, T2/Wir/Wval set.
 template <class SR, bool MERGE>
@@ -147,7 +160,6 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   src.N = io.ncolA;
   src.task_col = nullptr;
   src.task_win = nullptr;
-  src.debug = (int)opt.debug_numeric;
 #ifdef CBGPU_EXPERIMENTAL_RANK_SORT
   src.rank_sort = (int)opt.hash_rank_sort;
 #endif
@@ -342,17 +354,30 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       else if (b == 8) c = NUM_H_WARP_M2;
       else if (b == 9) c = NUM_H_WARP;
       else if (b >= 10 && b <= 39) c = NUM_H_CTA;
-      else if (b >= 41 && b <= 52) c = NUM_BM_S;
-      else if (b >= 53 && b <= 79) c = NUM_BM_L;
       else if (b >= 81 && b <= 119) c = NUM_BM_G;
+      else if (b >= 121 && b <= 159) c = NUM_SA_S;
+      else if (b >= 161 && b <= 199) c = NUM_SA_M;
+      else if (b >= 201 && b <= 239) c = NUM_SA_L;
       num_class[b] = c;
     }
+    // capacity (outputs per task) of the three shared-accumulator shapes
+    const int64_t dyn_s = sacc_dynamic_smem(ctx, kSaccThreadsS, kSaccBlocksS, sizeof(FlatQueueT<kSaccThreadsS>));
+    const int64_t dyn_m = sacc_dynamic_smem(ctx, kSaccThreadsM, kSaccBlocksM, sizeof(FlatQueueT<kSaccThreadsM>));
+    const int64_t dyn_l = sacc_dynamic_smem(ctx, kSaccThreadsL, kSaccBlocksL, sizeof(FlatQueueT<kSaccThreadsL>));
+    auto cap_of = [&](int64_t dyn) -> int64_t {
+      const int64_t c = (dyn - (int64_t)bm_bytes) / (int64_t)sizeof(acc_t);
+      return (opt.shared_acc && c >= 64) ? c : 0;
+    };
+    int64_t cap_s = cap_of(dyn_s), cap_m = cap_of(dyn_m), cap_l = cap_of(dyn_l);
+    if (opt.shared_acc_max > 0) // tests and tuning: shrink the three capacities together so that small inputs reach every shape
+      cap_l = std::min(cap_l, opt.shared_acc_max), cap_m = std::min(cap_m, opt.shared_acc_max / 2), cap_s = std::min(cap_s, opt.shared_acc_max / 4);
+    if (opt.shared_acc_small_max >= 0) cap_s = std::min(cap_s, opt.shared_acc_small_max);
     if (ntask > 0) {
       // below this many outputs a task is cheaper in the per-warp hash classes than with a window-sized bitmap
       int64_t auto_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 512, 32), 256);
       int64_t bmin = opt.bitmap_min_nnz > 0 ? opt.bitmap_min_nnz : auto_min;
-      num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048,
-                                                                        opt.bitmap_smem_acc, (int)opt.force_path, bucket);
+      num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048, cap_s, cap_m,
+                                                                        cap_l, (int)opt.force_path, bucket);
       CB_LAUNCH_CHECK(ctx);
       CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, task_win, num_class, order, &nb, &nc));
     }
@@ -360,60 +385,56 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     // bitmap, accumulators in C itself: RED.ADD straight into the (L2-resident) output slice of the task.
     // Largest tasks by 512 threads; the many small ones (<= 2048 outputs) by 128 threads with a small shared-memory
     // footprint so that many of them are in flight per SM (their cost is dependent-load latency, not bandwidth).
-    if (nc.count[NUM_BM_G] + nc.count[NUM_BM_S] > 0) {
+    if (nc.count[NUM_BM_G] > 0) {
       size_t sm = bm_bytes + 16;
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
-      if (nc.count[NUM_BM_G] > 0) {
-        if (opt.bitmap_cta_threads == 256) {
-          auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
-          CB_TRY(optin_smem(ctx, kern, sm));
-          kern<<<(unsigned)nc.count[NUM_BM_G], 256, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
-        } else {
-          auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
-          CB_TRY(optin_smem(ctx, kern, sm));
-          kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
-        }
-        CB_LAUNCH_CHECK(ctx);
+      if (opt.bitmap_cta_threads == 256) {
+        auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
+        CB_TRY(optin_smem(ctx, kern, sm));
+        kern<<<(unsigned)nc.count[NUM_BM_G], 256, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
+                                                           taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
+      } else {
+        auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
+        CB_TRY(optin_smem(ctx, kern, sm));
+        kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
+                                                           taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
       }
-      if (nc.count[NUM_BM_S] > 0) {
-        if (opt.bitmap_small_threads == 256) {
-          auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
-          CB_TRY(optin_smem(ctx, kern, sm));
-          kern<<<(unsigned)nc.count[NUM_BM_S], 256, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
-        } else if (opt.bitmap_small_minblocks == 12) {
-          auto kern = num_bitmap_kernel<SR, MERGE, true, 128, 12>;
-          CB_TRY(optin_smem(ctx, kern, sm));
-          kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
-        } else {
-          auto kern = num_bitmap_kernel<SR, MERGE, true, 128>;
-          CB_TRY(optin_smem(ctx, kern, sm));
-          kern<<<(unsigned)nc.count[NUM_BM_S], 128, sm, st>>>(src, order + nc.begin[NUM_BM_S], nc.count[NUM_BM_S], io.m, max_cells,
-                                                             taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
-        }
-        CB_LAUNCH_CHECK(ctx);
-      }
-      CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
-      stats.tasks_bitmap_gmem = nc.count[NUM_BM_G] + nc.count[NUM_BM_S];
-      stats.flops_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, false) + class_weight(nb, num_class, NUM_BM_S, false);
-      stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true) + class_weight(nb, num_class, NUM_BM_S, true);
-    }
-    // bitmap, accumulators in shared memory (2049 .. bitmap_smem_acc outputs; empty with the default options)
-    if (nc.count[NUM_BM_L] > 0) {
-      auto kern = num_bitmap_kernel<SR, MERGE, false, 512>;
-      size_t smL = bm_bytes + 16 + (size_t)std::max<int64_t>(opt.bitmap_smem_acc, 2048) * sizeof(acc_t);
-      CB_TRY(optin_smem(ctx, kern, smL));
-      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
-      kern<<<(unsigned)nc.count[NUM_BM_L], 512, smL, st>>>(src, order + nc.begin[NUM_BM_L], nc.count[NUM_BM_L], io.m, max_cells,
-                                                          taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
       CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
+      stats.tasks_bitmap_gmem = nc.count[NUM_BM_G];
+      stats.flops_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, false);
+      stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true);
+    }
+    // bitmap, accumulators in shared memory (exchange protocol): three CTA shapes by output count
+    if (nc.count[NUM_SA_L] + nc.count[NUM_SA_M] + nc.count[NUM_SA_S] > 0) {
+      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
+      if (nc.count[NUM_SA_L] > 0) {
+        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false>;
+        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_l));
+        kern<<<(unsigned)nc.count[NUM_SA_L], kSaccThreadsL, (size_t)dyn_l, st>>>(src, order + nc.begin[NUM_SA_L], io.m, max_cells, taskptr,
+                                                                                Cm->ir, Cval, saved, max_cells, slot_of_task);
+        CB_LAUNCH_CHECK(ctx);
+      }
+      if (nc.count[NUM_SA_M] > 0) {
+        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, false>;
+        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_m));
+        kern<<<(unsigned)nc.count[NUM_SA_M], kSaccThreadsM, (size_t)dyn_m, st>>>(src, order + nc.begin[NUM_SA_M], io.m, max_cells, taskptr,
+                                                                                Cm->ir, Cval, saved, max_cells, slot_of_task);
+        CB_LAUNCH_CHECK(ctx);
+      }
+      if (nc.count[NUM_SA_S] > 0) {
+        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsS, kSaccBlocksS, true>;
+        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_s));
+        kern<<<(unsigned)nc.count[NUM_SA_S], kSaccThreadsS, (size_t)dyn_s, st>>>(src, order + nc.begin[NUM_SA_S], io.m, max_cells, taskptr,
+                                                                                Cm->ir, Cval, saved, max_cells, slot_of_task);
+        CB_LAUNCH_CHECK(ctx);
+      }
       CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
-      stats.tasks_bitmap_smem = nc.count[NUM_BM_L];
-      stats.flops_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, false);
-      stats.nnz_bitmap_smem = class_weight(nb, num_class, NUM_BM_L, true);
+      for (int c : {NUM_SA_L, NUM_SA_M, NUM_SA_S}) {
+        stats.tasks_bitmap_smem += nc.count[c];
+        stats.flops_bitmap_smem += class_weight(nb, num_class, c, false);
+        stats.nnz_bitmap_smem += class_weight(nb, num_class, c, true);
+      }
     }
     // hash per CTA: 257..2048 outputs
     if (nc.count[NUM_H_CTA] > 0) {

@@ -11,11 +11,16 @@
 //   accumulate(p, v)   *p = SR::add(v, *p), atomically; p may point to shared or global memory
 //   accumulate_out(p,v) same, but p points into C's value array (out_t) in global memory
 //   add(a, b)          SR::add on two stored values (used by the streaming 2-way merge)
+//   acc_add(a, b)      SR::add on two accumulator values
+//   accumulate_shared<FIRST>(p, v)  *p = SR::add(v, *p) for p in SHARED memory, safe against every other thread of the CTA
+//                      (see exch_accumulate below); FIRST = most slots receive one product only
 //   to_out / from_out  conversion between acc_t and out_t
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
+#include <string.h>
+#include <type_traits>
 
 namespace cbgpu {
 
@@ -31,6 +36,48 @@ __device__ __forceinline__ void atomic_min_f64(double *p, double v) {
   }
 }
 
+
+// Lock-free accumulation into SHARED memory built on ATOMS.EXCH, which is native for 32 and 64 bits on sm_100a, where
+// atomicAdd(double/float/u64) and atomicMax/Min(64 bit) compile to an ATOMS.CAST.SPIN loop. Measured on B200
+// (tools/micro/prims.cu, profiles/r2_micro_prims.txt): EXCH.64 0.21 cycles per lane and SM, the CAS loop 0.79, a
+// RED.ADD.F64 to L2 1.52. The identity of SR::add marks an empty slot -- it carries no information, so a slot that
+// holds it and an empty slot are the same thing. A thread owns whatever it has swapped OUT of a slot; the sum of slot +
+// all owned values never changes, and a thread finishes only when it has swapped its value INTO an empty slot.
+template <class SR, bool FIRST>
+__device__ __forceinline__ void exch_accumulate(typename SR::acc_t *p, typename SR::acc_t v) {
+  typedef typename SR::acc_t T;
+  typedef typename std::conditional<sizeof(T) == 8, unsigned long long, unsigned int>::type U;
+  static_assert(sizeof(T) == sizeof(U), "accumulators are 4 or 8 bytes");
+  U *up = reinterpret_cast<U *>(p);
+  T idv = SR::identity();
+  U ident, x;
+  memcpy(&ident, &idv, sizeof(U));
+  memcpy(&x, &v, sizeof(U));
+  while (true) {
+    U old;
+    if (!FIRST) { // take what is there (usually a partial sum), add, put back
+      old = atomicExch(up, ident);
+      T a, b;
+      memcpy(&a, &old, sizeof(U));
+      memcpy(&b, &x, sizeof(U));
+      a = SR::acc_add(a, b);
+      memcpy(&x, &a, sizeof(U));
+      old = atomicExch(up, x);
+      if (old == ident) return;
+      x = old; // somebody put a value in between: it is mine now
+    } else { // put first (usually into an empty slot); otherwise merge what came out with what is there now
+      old = atomicExch(up, x);
+      if (old == ident) return;
+      const U y = atomicExch(up, ident);
+      T a, b;
+      memcpy(&a, &old, sizeof(U));
+      memcpy(&b, &y, sizeof(U));
+      a = SR::acc_add(a, b);
+      memcpy(&x, &a, sizeof(U));
+    }
+  }
+}
+
 template <int ID>
 struct Semiring;
 
@@ -43,6 +90,8 @@ struct Semiring<0> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a + b; } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a + b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -55,6 +104,8 @@ struct Semiring<1> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a + b; } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a + b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -67,6 +118,8 @@ struct Semiring<2> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return (out_t)((acc_t)a + (acc_t)b); } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a + b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return (out_t)v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return (acc_t)v; }
 };
@@ -79,6 +132,8 @@ struct Semiring<3> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicMax(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a > b ? a : b; } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a > b ? a : b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -91,6 +146,8 @@ struct Semiring<4> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomic_min_f64(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return b < a ? b : a; } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return b < a ? b : a; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -104,6 +161,9 @@ struct Semiring<5> {
   // OR into a byte of C: every writer stores the same value, so a plain store is race-free in effect
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { if (v) *reinterpret_cast<volatile uint8_t *>(p) = 1; }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return (out_t)((a || b) ? 1 : 0); } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a | b; }
+  // OR: every writer stores the same value, a plain store is enough
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { if (v) *reinterpret_cast<volatile acc_t *>(p) = 1u; }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v ? 1 : 0; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v ? 1u : 0u; }
 };
@@ -116,6 +176,8 @@ struct Semiring<6> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a + b; } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a + b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
@@ -128,6 +190,8 @@ struct Semiring<7> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicAdd(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return (out_t)((acc_t)a + (acc_t)b); } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a + b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { atomicAdd(p, v); } // ATOMS.ADD is native for 32 bits
   __device__ static __forceinline__ out_t to_out(acc_t v) { return (out_t)v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return (acc_t)v; }
 };
@@ -140,6 +204,8 @@ struct Semiring<8> {
   __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { atomicMax(p, v); }
   __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { accumulate(reinterpret_cast<acc_t *>(p), v); }
   __device__ static __forceinline__ out_t add(out_t a, out_t b) { return a > b ? a : b; } // SR::add on stored values
+  __device__ static __forceinline__ acc_t acc_add(acc_t a, acc_t b) { return a > b ? a : b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { exch_accumulate<Semiring, FIRST>(p, v); }
   __device__ static __forceinline__ out_t to_out(acc_t v) { return v; }
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };

@@ -28,7 +28,7 @@ def case(sr, A, B, **opts):
         assert_same(got, want, sr)
         return f"flops={st.flops} nnz={st.nnz_out} ms={st.ms_total:.3f} (sym {st.ms_symbolic:.3f} num {st.ms_numeric:.3f}) hw={st.tasks_hash_warp} hc={st.tasks_hash_cta} bs={st.tasks_bitmap_smem} bg={st.tasks_bitmap_gmem}"
     finally:
-        ctx.set_option("force_path", 0); ctx.set_option("bitmap_window_log2", 17); ctx.set_option("bitmap_smem_acc", 2048)
+        ctx.set_option("force_path", 0); ctx.set_option("bitmap_window_log2", 17); ctx.set_option("shared_acc", 1)
 
 for sr in range(9):
     A, B = random_pair(300, 220, 260, 0.05, 0.04, 11 + sr, SR_DTYPES[sr])
@@ -38,5 +38,5 @@ for scale in (8, 11, 13, 14, 16):
     run(f"rmat s{scale} auto", lambda: case(0, A, A))
     run(f"rmat s{scale} hash-only", lambda: case(0, A, A, force_path=1))
     run(f"rmat s{scale} bitmap-only", lambda: case(0, A, A, force_path=2))
-    run(f"rmat s{scale} bitmap gmem", lambda: case(0, A, A, force_path=2, bitmap_smem_acc=256))
+    run(f"rmat s{scale} bitmap gmem", lambda: case(0, A, A, force_path=2, shared_acc=0))
     run(f"rmat s{scale} windows 2^11", lambda: case(0, A, A, bitmap_window_log2=11))

@@ -74,9 +74,13 @@ def test_rmat_scale14_all_paths(ctx, oracle):
     A = rmat(14, 16, seed=2)
     want = oracle.spgemm(to_csc(A, np.float64), to_csc(A, np.float64), 0)
     dA = ctx.upload(to_dcsc(A, np.float64))
-    for force, smem_acc in ((0, 2048), (1, 2048), (2, 8192), (0, 256), (2, 256)):
+    # (force_path, shared_acc, shared_acc_max): every numeric class of the bitmap path -- accumulators in shared memory in the
+    # three CTA shapes (capacity limits lowered so that this small matrix reaches the medium and large shapes) or in C itself
+    for force, shared, cap in ((0, 1, 0), (1, 1, 0), (2, 1, 0), (2, 1, 700), (0, 0, 0), (2, 0, 0)):
         ctx.set_option("force_path", force)
-        ctx.set_option("bitmap_smem_acc", smem_acc)
+        ctx.set_option("shared_acc", shared)
+        ctx.set_option("shared_acc_max", cap)
+        ctx.set_option("shared_acc_small_max", 300 if cap else -1)
         D, st = ctx.spgemm(0, dA, dA, want_stats=True)
         rows, cols, vals = ctx.download_coo(D)
         got = cb.SpTuples(A.shape[0], A.shape[1], rows, cols, vals)
@@ -85,12 +89,40 @@ def test_rmat_scale14_all_paths(ctx, oracle):
         assert st.nnz_out == want.nnz
         if force == 2:
             assert st.tasks_hash_warp + st.tasks_hash_cta == 0
-        if smem_acc == 256:
+        if shared == 0 or cap:
             assert st.tasks_bitmap_gmem > 0
+        if shared == 1 and force != 1:
+            assert st.tasks_bitmap_smem > 0
         D.free()
     ctx.set_option("force_path", 0)
-    ctx.set_option("bitmap_smem_acc", 2048)
+    ctx.set_option("shared_acc", 1)
+    ctx.set_option("shared_acc_max", 0)
+    ctx.set_option("shared_acc_small_max", -1)
     dA.free()
+
+
+@pytest.mark.parametrize("sr", range(9))
+def test_shared_accumulator_classes_every_semiring(ctx, oracle, sr):
+    """the exchange-protocol accumulators (csrc/semiring.cuh exch_accumulate) in all three CTA shapes + the fallback into C,
+    for every semiring: bitmap path forced, capacities lowered so that one R-MAT square spreads over all four classes"""
+    A = rmat(12, 16, seed=20 + sr)
+    ctx.set_option("force_path", 2)
+    ctx.set_option("shared_acc_max", 500)
+    ctx.set_option("shared_acc_small_max", 120)
+    try:
+        ta, tb, _ = SR_DTYPES[sr]
+        want = oracle.spgemm(to_csc(typed(A, ta), ta), to_csc(typed(A, tb), tb), sr)
+        dA, dB = ctx.upload(to_dcsc(typed(A, ta), ta)), ctx.upload(to_dcsc(typed(A, tb), tb))
+        D, st = ctx.spgemm(sr, dA, dB, want_stats=True)
+        rows, cols, vals = ctx.download_coo(D)
+        assert_same(cb.SpTuples(A.shape[0], A.shape[1], rows, cols, vals), want, sr)
+        assert st.tasks_bitmap_smem > 0 and st.tasks_bitmap_gmem > 0
+        for x in (dA, dB, D):
+            x.free()
+    finally:
+        ctx.set_option("force_path", 0)
+        ctx.set_option("shared_acc_max", 0)
+        ctx.set_option("shared_acc_small_max", -1)
 
 
 @pytest.mark.parametrize("wlog2", [10, 12])
