@@ -459,7 +459,8 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "ms_steps": [round(x, 3) for x in ms], "wall_s": round(t_wall, 3),
                 "phases_ms": {"setup": round(st.ms_setup, 3), "symbolic": round(st.ms_symbolic, 3), "numeric": round(st.ms_numeric, 3)},
-                "census": {k: sd[k] for k in sd if k.startswith(("tasks", "flops_", "nnz_"))}}
+                "census": {k: sd[k] for k in sd if k.startswith(("tasks", "flops_", "nnz_"))},
+                "classes": sd.get("classes")}
         if ds is not None:
             dd = ds.as_dict()
             line["dist_ms"] = {k: round(dd[k], 3) for k in ("ms_bcast", "ms_multiply", "ms_merge", "ms_fiber_exchange", "ms_fiber_merge", "ms_total")}

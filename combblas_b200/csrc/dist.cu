@@ -254,7 +254,12 @@ static void add_stats(cbgpu_stats &acc, const cbgpu_stats &s) {
   acc.flops_hash_warp += s.flops_hash_warp; acc.flops_hash_cta += s.flops_hash_cta;
   acc.flops_bitmap_smem += s.flops_bitmap_smem; acc.flops_bitmap_gmem += s.flops_bitmap_gmem;
   acc.nnz_out += s.nnz_out;
-  for (int i = 0; i < CBGPU_K_COUNT; ++i) acc.ms_kernel[i] += s.ms_kernel[i];
+  for (int i = 0; i < CBGPU_K_COUNT; ++i) {
+    acc.ms_kernel[i] += s.ms_kernel[i];
+    acc.class_tasks[i] += s.class_tasks[i];
+    acc.class_flops[i] += s.class_flops[i];
+    acc.class_nnz[i] += s.class_nnz[i];
+  }
 }
 
 struct Timer {

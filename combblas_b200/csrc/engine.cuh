@@ -13,10 +13,10 @@
 // Per task the engine runs a symbolic pass (count distinct rows) and, after an exclusive scan over the
 // counts, a numeric pass that writes the column's rows ASCENDING together with the accumulated values:
 //   hash path   (small tasks) : shared-memory open addressing per warp or per CTA + bitonic sort of the hits
-//   bitmap path (large tasks) : shared-memory presence bitmap of the row window in 64-bit cells (45 row bits + the
-//                               19-bit count of the rows in earlier cells): one load and a popcount give every row
-//                               its sorted output slot, so there is no sort and no probing; values accumulate
-//                               straight into C in HBM (L2 reductions), or in shared memory for tasks that fit.
+//   bitmap path (large tasks) : shared-memory presence bitmap of the row window in 32-row words + per-word rank prefix:
+//                               two loads and a popcount give every row its sorted output slot, so there is no sort
+//                               and no probing; values accumulate in shared memory (exchange protocol) for every task
+//                               whose outputs fit, straight into C in HBM (L2 reductions) for the few that do not.
 // No tensor cores: the work is irregular integer/atomic traffic; the levers are coalesced segment reads,
 // shared-memory atomics, and keeping every SM busy with size-ordered tasks.
 #pragma once
@@ -38,8 +38,9 @@ struct Source {
   int wlog2;
   const int32_t *Air;
   const aval_t *Aval;
-  // window-major copy of A (nwin > 1): piece (window w, column c) is [T2[w*N+c], T2[w*N+c+1]) of Wir/Wval, so that all
-  // tasks of one row window gather from one contiguous, L2-sized slice instead of striding through every column of A
+  // window-major copy of A: piece (window w, column c) starts at T2[w*N+c] & ~3 of Wir/Wval (16-byte aligned, padded to a
+  // multiple of 4 entries with row -1; see util.cu), so that all tasks of one row window gather from one contiguous,
+  // L2-sized slice instead of striding through every column of A, four products per load
   const int64_t *T2;
   int64_t N;
   const int32_t *Wir;
@@ -97,6 +98,64 @@ __device__ __forceinline__ void task_segments(const Source<SR, MERGE> &s, Task &
   k.vals = whole ? (const void *)s.Aval : (const void *)s.Wval;
 }
 
+// Launch-order task record: everything a bitmap kernel needs to start a task, in one 32-byte load (the chain order[] ->
+// task_col/task_win -> Bcp -> taskptr -> slot_of_task was five dependent loads; small tasks are latency bound).
+struct TaskRec {
+  long long seg_begin; // multiply: first entry of the column of B; merge: the column id
+  long long obase;     // numeric: first output position; symbolic: the task id (tasknnz index)
+  int nseg;            // multiply: entries of the column of B
+  int nnz;             // numeric: outputs of the task
+  int slot;            // hand-over slot of the symbolic pass, -1 = none
+  unsigned win;        // wlo | whi << 16
+};
+
+template <class SR, bool MERGE>
+__global__ void task_record_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const int64_t *taskptr,
+                                   const int32_t *slot_of_task, TaskRec *recs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int t = order[i];
+  Task k = load_task(s, t);
+  TaskRec r;
+  r.win = (unsigned)k.wlo | ((unsigned)k.whi << 16);
+  if (MERGE) {
+    r.seg_begin = k.col;
+    r.nseg = s.k;
+  } else {
+    r.seg_begin = s.Bcp[k.col];
+    r.nseg = (int)(s.Bcp[k.col + 1] - r.seg_begin);
+  }
+  if (taskptr) {
+    r.obase = taskptr[t];
+    r.nnz = (int)(taskptr[t + 1] - r.obase);
+  } else {
+    r.obase = t;
+    r.nnz = 0;
+  }
+  r.slot = slot_of_task ? slot_of_task[t] : -1;
+  recs[i] = r;
+}
+
+template <class SR, bool MERGE>
+__device__ __forceinline__ Task task_from_record(const Source<SR, MERGE> &s, const TaskRec &r) {
+  Task k;
+  k.wlo = (int)(r.win & 0xFFFFu);
+  k.whi = (int)(r.win >> 16);
+  if (MERGE) {
+    k.col = (int)r.seg_begin;
+    k.seg_begin = 0;
+    k.seg_end = s.k;
+  } else {
+    k.col = -1;
+    k.seg_begin = r.seg_begin;
+    k.seg_end = r.seg_begin + r.nseg;
+  }
+  const bool whole = (k.whi - k.wlo) == s.nwin || s.T2 == nullptr;
+  k.rows = whole ? s.Air : s.Wir;
+  k.vals = whole ? (const void *)s.Aval : (const void *)s.Wval;
+  return k;
+}
+
 // segment p of task k, first half: the column of A (or of the stacked merge lists) it reads, and its multiplier
 template <class SR, bool MERGE, bool NEED_MULT>
 __device__ __forceinline__ int64_t segment_column(const Source<SR, MERGE> &s, const Task &k, int64_t p, typename SR::b_t &mult) {
@@ -112,9 +171,11 @@ __device__ __forceinline__ void segment_range(const Source<SR, MERGE> &s, const 
     beg = s.T[col];
     len = (int)(s.T[col + 1] - beg);
   } else if (s.T2 != nullptr) {
+    // window-major copy: starts are multiples of 4, the low two bits count the pad entries of the piece (util.cu)
     const int64_t *t = s.T2 + (int64_t)k.wlo * s.N + col;
-    beg = t[0];
-    len = (int)(t[1] - beg);
+    const int64_t a = t[0];
+    beg = a & ~(int64_t)3;
+    len = (int)((t[1] & ~(int64_t)3) - beg - (a & 3));
   } else {
     // no window-major copy (merge: few, long segments): cut the row-sorted column by binary search
     int64_t b0 = s.T[col], e0 = s.T[col + 1];
@@ -363,23 +424,30 @@ __device__ __forceinline__ void cta_walk(const Source<SR, MERGE> &s, const Task 
 }
 
 // ------------------------------------------------------------------------------------------------ flat walk
-// Whole-CTA walk over the PRODUCTS of a task, one product per lane and step, whatever the segment lengths are.
+// Whole-CTA walk over the PRODUCTS of a task, one product per lane and sub-step, whatever the segment lengths are.
 // A chunk of up to CH segments is staged in shared memory: the empty ones are dropped, every other one leaves the
-// exclusive prefix of the lengths (pre), its multiplier, and base = beg - pre, so that product q of the chunk lives at
-// position base[seg] + q of the row/value arrays. Warp w owns the products [w*T/nw, (w+1)*T/nw) of the chunk and keeps a
-// cursor: the segment of its next product. Per step of 32 products the lanes read the next 32 boundaries pre[cursor+1+lane];
-// a boundary that falls L < 32 products ahead sets bit L, one REDUX.OR merges the bits (the segments are non-empty, so the
-// boundaries are distinct) and a popcount below the lane gives every lane its segment: no search, no per-segment loop,
-// loads coalesced inside every segment. The load of step i+1 is issued before step i is consumed.
-// The average segment of the large R-MAT tasks is 46..80 products; the per-segment cost of the segment-by-segment walk
-// above (cta_walk) was about 50 instructions, i.e. as much as the products themselves.
+// exclusive prefix of the lengths (pre), its multiplier, and the addresses rowp / valp of where product 0 of the CHUNK
+// would sit if the segment started there, so that product q of the chunk is read at rowp[seg] + 4 q (one IMAD.WIDE).
+// Warp w owns the products [w*T/nw, (w+1)*T/nw) of the chunk and keeps a cursor: the segment of its next product. Per
+// step of up to 128 products the lanes read the next 32 boundaries pre[cursor+1+lane] once; a boundary that falls L
+// products ahead sets bit L & 31 of mask L >> 5; four REDUX.OR merge the bits (segments are non-empty, so boundaries are
+// distinct) and popcounts below the lane give every lane the segment of each of its four products: no search, no
+// per-segment loop, loads coalesced inside every segment, four independent loads in flight per lane.
+// The average segment of the large R-MAT tasks is 46..80 products (30..40 with 2^16-row windows); the segment-by-segment
+// walk above (cta_walk) spends about 50 instructions per segment, the first version of this walk (one sub-step per
+// boundary load) spent 68 per 32 products (profiles/r2_ncu_flatwalk_v1.txt).
 template <int CH>
 struct FlatQueueT {
-  long long base[CH];
+  long long rowp[CH];
+  long long valp[CH];
   unsigned long long mult[CH];
   unsigned pre[CH + 34];
   unsigned long long warp_tot[32];
+  unsigned total; // products (groups) of the staged chunk
+  int nseg;       // its non-empty segments
 };
+
+constexpr int kFlatSub = 4; // sub-steps of 32 products per boundary-window load
 
 template <class SR, bool MERGE, bool NEED_VAL, int CH, class USE>
 __device__ __forceinline__ void flat_walk(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<CH> *q, USE &&use) {
@@ -388,8 +456,7 @@ __device__ __forceinline__ void flat_walk(const Source<SR, MERGE> &s, const Task
   constexpr int nwarp = CH >> 5; // blockDim.x == CH
   constexpr unsigned long long kLenMask = (1ull << 40) - 1ull;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int32_t *__restrict__ rows = k.rows;
-  const aval_t *__restrict__ vals = reinterpret_cast<const aval_t *>(k.vals);
+  const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane); // bits 0..lane
   for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
     __syncthreads(); // previous chunk fully consumed
     int64_t beg = 0;
@@ -418,10 +485,13 @@ __device__ __forceinline__ void flat_walk(const Source<SR, MERGE> &s, const Task
     const unsigned T = (unsigned)(total & kLenMask); // products of the chunk: CH segments of at most 2^19 rows
     if (len > 0) {
       const int idx = (int)(excl >> 40);
-      const unsigned pre = (unsigned)(excl & kLenMask);
-      q->pre[idx] = pre;
-      q->base[idx] = beg - (long long)pre;
-      if (NEED_VAL) q->mult[idx] = mult_bits<mult_t>(mult);
+      const long long pre = (long long)(excl & kLenMask);
+      q->pre[idx] = (unsigned)pre;
+      q->rowp[idx] = (long long)(k.rows + beg) - 4ll * pre;
+      if (NEED_VAL) {
+        q->valp[idx] = (long long)(reinterpret_cast<const aval_t *>(k.vals) + beg) - (long long)sizeof(aval_t) * pre;
+        q->mult[idx] = mult_bits<mult_t>(mult);
+      }
     }
     if (threadIdx.x < 34) q->pre[nseg + threadIdx.x] = threadIdx.x == 0 ? T : 0xFFFFFFFFu;
     __syncthreads();
@@ -439,48 +509,184 @@ __device__ __forceinline__ void flat_walk(const Source<SR, MERGE> &s, const Task
       }
       cur = a;
     }
-    struct Fetched {
-      int row;
-      aval_t val;
-      mult_t mu;
-      bool valid;
-    };
-    auto fetch = [&](unsigned q0) -> Fetched {
-      Fetched f;
-      const unsigned L = q->pre[cur + 1 + lane] - q0; // >= 1: the segments are non-empty and `cur` holds product q0
-      const unsigned M = __reduce_or_sync(0xFFFFFFFFu, L < 32u ? (1u << L) : 0u);
-      const bool at32 = __any_sync(0xFFFFFFFFu, L == 32u);
-      const int seg = cur + __popc(M & (0xFFFFFFFFu >> (31 - lane)));
-      cur += __popc(M) + (at32 ? 1 : 0);
-      const unsigned qq = q0 + (unsigned)lane;
-      f.valid = qq < hi;
-      f.row = 0;
-      f.val = aval_t();
-      f.mu = mult_t();
-      if (f.valid) {
-        const long long pos = q->base[seg] + (long long)qq;
-        f.row = rows[pos];
-        if (NEED_VAL) {
-          f.val = vals[pos];
-          f.mu = bits_mult<mult_t>(q->mult[seg]);
+    for (unsigned q0 = lo; q0 < hi;) {
+      // distance of the next 32 boundaries; >= 1 because the segments are non-empty and `cur` holds product q0
+      const unsigned L = q->pre[cur + 1 + lane] - q0;
+      // sub-steps of this step: all their boundaries must lie inside the 32 just read
+      const unsigned L31 = __shfl_sync(0xFFFFFFFFu, L, 31);
+      unsigned nsub = min((unsigned)kFlatSub, L31 >> 5);
+      nsub = min(nsub, (hi - q0 + 31u) >> 5);
+      const unsigned Lj = L >> 5, Lb = 1u << (L & 31u);
+      int row[kFlatSub];
+      aval_t val[kFlatSub];
+      mult_t mu[kFlatSub];
+      int seg0 = cur;
+#pragma unroll
+      for (int j = 0; j < kFlatSub; ++j) {
+        row[j] = -1;
+        if ((unsigned)j < nsub) { // warp-uniform
+          const unsigned M = __reduce_or_sync(0xFFFFFFFFu, Lj == (unsigned)j ? Lb : 0u);
+          const int seg = seg0 + __popc(M & le_mask);
+          seg0 += __popc(M);
+          const unsigned qq = q0 + 32u * j + (unsigned)lane;
+          if (qq < hi) {
+            row[j] = *reinterpret_cast<const int32_t *>(q->rowp[seg] + 4ll * qq);
+            if (NEED_VAL) {
+              val[j] = *reinterpret_cast<const aval_t *>(q->valp[seg] + (long long)sizeof(aval_t) * qq);
+              mu[j] = bits_mult<mult_t>(q->mult[seg]);
+            }
+          }
         }
       }
-      return f;
-    };
-    unsigned q0 = lo;
-    Fetched now = fetch(q0);
-    while (true) {
-      const unsigned q1 = q0 + 32u;
-      const bool more = q1 < hi; // warp-uniform
-      Fetched next;
-      if (more) next = fetch(q1);
-      if (now.valid) use(now.row, now.val, now.mu);
-      if (!more) break;
-      now = next;
-      q0 = q1;
+      // a boundary exactly at the first product of the next step moves the cursor once more
+      const unsigned span = nsub << 5;
+      cur = seg0 + (__any_sync(0xFFFFFFFFu, L == span) ? 1 : 0);
+      q0 += span;
+#pragma unroll
+      for (int j = 0; j < kFlatSub; ++j)
+        if (row[j] >= 0) use(row[j], val[j], mu[j]);
     }
   }
   __syncthreads();
+}
+
+// The multiply's walk: the same scheme in units of GROUPS of 4 products. Pieces of the window-major copy start at
+// multiples of 4 entries and are padded with row -1 (util.cu), so a lane takes one group per sub-step with a 16-byte load
+// of row ids and aligned vector loads of values, and one segment lookup serves four products.
+template <class T>
+struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) Quad {
+  T v[4];
+};
+constexpr int kFlatSub4 = 2; // sub-steps of 32 groups (128 products) per boundary-window load
+
+template <class SR, bool NEED_VAL, int CH, class USE>
+__device__ __forceinline__ void flat_walk4(const Source<SR, false> &s, const Task &k, FlatQueueT<CH> *q, USE &&use,
+                                           bool stage_vals = false, bool reuse = false) {
+  // stage_vals: also stage value pointers and multipliers although this walk reads rows only, so that the next walk of
+  // the same single-chunk task can skip the staging (reuse): small tasks are bound by their chain of dependent loads
+  typedef typename SR::b_t mult_t;
+  typedef typename SR::a_t aval_t;
+  constexpr int nwarp = CH >> 5; // blockDim.x == CH
+  constexpr unsigned long long kLenMask = (1ull << 40) - 1ull;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane); // bits 0..lane
+  const int64_t *__restrict__ Tw = s.T2 + (int64_t)k.wlo * s.N;
+  for (int64_t cbase = k.seg_begin; cbase < k.seg_end; cbase += CH) {
+    int nseg;
+    unsigned T;
+    if (!reuse) {
+    __syncthreads(); // previous chunk fully consumed
+    int64_t beg = 0;
+    unsigned ng = 0; // groups of this thread's segment
+    mult_t mult = mult_t();
+    if (cbase + threadIdx.x < k.seg_end) {
+      const int64_t p = cbase + threadIdx.x;
+      const int64_t *t = Tw + s.Bir[p];
+      beg = t[0] & ~(int64_t)3;
+      ng = (unsigned)(((t[1] & ~(int64_t)3) - beg) >> 2);
+      if (NEED_VAL || stage_vals) mult = s.Bval[p];
+    }
+    const unsigned long long x = (ng > 0 ? (1ull << 40) : 0ull) | (unsigned long long)ng;
+    unsigned long long incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) q->warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long wv = lane < nwarp ? q->warp_tot[lane] : 0ull, winc = wv;
+#pragma unroll
+    for (int d = 1; d < nwarp; d <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+      if (lane >= d) winc += v;
+    }
+    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, nwarp - 1);
+    const unsigned long long excl = __shfl_sync(0xFFFFFFFFu, winc - wv, warp) + incl - x;
+    nseg = (int)(total >> 40);
+    T = (unsigned)(total & kLenMask); // groups of the chunk
+    if (ng > 0) {
+      const int idx = (int)(excl >> 40);
+      const long long pre = (long long)(excl & kLenMask);
+      q->pre[idx] = (unsigned)pre;
+      q->rowp[idx] = (long long)(s.Wir + beg) - 16ll * pre;
+      if (NEED_VAL || stage_vals) {
+        q->valp[idx] = (long long)(s.Wval + beg) - 4ll * (long long)sizeof(aval_t) * pre;
+        q->mult[idx] = mult_bits<mult_t>(mult);
+      }
+    }
+    if (threadIdx.x < 34) q->pre[nseg + threadIdx.x] = threadIdx.x == 0 ? T : 0xFFFFFFFFu;
+    if (threadIdx.x == 0) {
+      q->total = T;
+      q->nseg = nseg;
+    }
+    __syncthreads();
+    } else {
+      nseg = q->nseg;
+      T = q->total;
+    }
+    if (T == 0) continue;
+    const unsigned lo = (unsigned)((unsigned long long)T * (unsigned)warp / (unsigned)nwarp);
+    const unsigned hi = (unsigned)((unsigned long long)T * (unsigned)(warp + 1) / (unsigned)nwarp);
+    if (hi <= lo) continue;
+    int cur; // segment of group lo: the largest s with pre[s] <= lo
+    {
+      int a = 0, b = nseg - 1;
+      while (a < b) {
+        const int mid = (a + b + 1) >> 1;
+        if (q->pre[mid] <= lo) a = mid;
+        else b = mid - 1;
+      }
+      cur = a;
+    }
+    for (unsigned q0 = lo; q0 < hi;) {
+      const unsigned L = q->pre[cur + 1 + lane] - q0; // >= 1
+      const unsigned L31 = __shfl_sync(0xFFFFFFFFu, L, 31);
+      unsigned nsub = min((unsigned)kFlatSub4, L31 >> 5);
+      nsub = min(nsub, (hi - q0 + 31u) >> 5);
+      const unsigned Lj = L >> 5, Lb = 1u << (L & 31u);
+      int4 row[kFlatSub4];
+      Quad<aval_t> val[kFlatSub4];
+      mult_t mu[kFlatSub4];
+      int seg0 = cur;
+#pragma unroll
+      for (int j = 0; j < kFlatSub4; ++j) {
+        row[j] = make_int4(-1, -1, -1, -1);
+        if ((unsigned)j < nsub) { // warp-uniform
+          const unsigned M = __reduce_or_sync(0xFFFFFFFFu, Lj == (unsigned)j ? Lb : 0u);
+          const int seg = seg0 + __popc(M & le_mask);
+          seg0 += __popc(M);
+          const unsigned g = q0 + 32u * j + (unsigned)lane;
+          if (g < hi) {
+            row[j] = *reinterpret_cast<const int4 *>(q->rowp[seg] + 16ll * g);
+            if (NEED_VAL) {
+              val[j] = *reinterpret_cast<const Quad<aval_t> *>(q->valp[seg] + 4ll * (long long)sizeof(aval_t) * g);
+              mu[j] = bits_mult<mult_t>(q->mult[seg]);
+            }
+          }
+        }
+      }
+      const unsigned span = nsub << 5;
+      cur = seg0 + (__any_sync(0xFFFFFFFFu, L == span) ? 1 : 0);
+      q0 += span;
+#pragma unroll
+      for (int j = 0; j < kFlatSub4; ++j) {
+        if (row[j].x >= 0) use(row[j].x, val[j].v[0], mu[j]);
+        if (row[j].y >= 0) use(row[j].y, val[j].v[1], mu[j]);
+        if (row[j].z >= 0) use(row[j].z, val[j].v[2], mu[j]);
+        if (row[j].w >= 0) use(row[j].w, val[j].v[3], mu[j]);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// the walk of the bitmap kernels: groups of 4 from the padded window-major copy (multiply), single products (merge)
+template <class SR, bool MERGE, bool NEED_VAL, int CH, class USE>
+__device__ __forceinline__ void bitmap_walk(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<CH> *q, USE &&use,
+                                            bool stage_vals = false, bool reuse = false) {
+  if constexpr (MERGE) flat_walk<SR, MERGE, NEED_VAL>(s, k, q, use);
+  else flat_walk4<SR, NEED_VAL>(s, k, q, use, stage_vals, reuse);
 }
 
 // ------------------------------------------------------------------------------------------------ K1: products per task
@@ -700,16 +906,12 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
 }
 
 // ------------------------------------------------------------------------------------------------ bitmap path
-// The presence bitmap of a row window is an array of 64-bit CELLS in shared memory: the low kCellRows bits mark the
-// rows of the cell that occur in the task, the high kRankBits bits hold (after the scan) the number of present rows in
-// all earlier cells. One 8-byte shared-memory load therefore gives a product both halves of its output rank,
-//     rank(row) = cell >> kCellRows  +  popc(cell & ((1 << bit) - 1)),
-// and a cell array that the symbolic pass stores to HBM lets the numeric pass skip its own mark walk and scan.
-constexpr int kCellRows = 45;
-constexpr int kRankBits = 64 - kCellRows; // 19: row windows of up to 2^19 rows
-constexpr unsigned long long kCellMask = (1ull << kCellRows) - 1ull;
-
-__host__ __device__ __forceinline__ int cells_of_rows(int64_t rows) { return (int)((rows + kCellRows - 1) / kCellRows); }
+// The presence bitmap of a row window is an array of 32-row WORDS in shared memory; after the scan a second array holds
+// for every word the number of present rows in all earlier words, so the output slot of a product is
+//     rank(row) = rank[w] + popc(bits[w] & ((1 << b) - 1)),  w = (row - rbase) >> 5, b = (row - rbase) & 31:
+// no sort, no probing. The symbolic pass can hand the words of a task to the numeric pass through HBM (4 bytes per 32
+// rows), which then only repeats the scan.
+__host__ __device__ __forceinline__ int words_of_rows(int64_t rows) { return (int)((rows + 31) >> 5); }
 
 // block-wide exclusive scan of one int per thread (blockDim <= 1024); returns exclusive prefix, total in *total
 __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /*[32]*/, int *total) {
@@ -739,7 +941,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /*[32]
 
 // the row window of a task
 struct Window {
-  int rbase, wrows, ncell;
+  int rbase, wrows, nword;
 };
 template <class Src>
 __device__ __forceinline__ Window task_window(const Src &s, const Task &k, int64_t m) {
@@ -748,221 +950,171 @@ __device__ __forceinline__ Window task_window(const Src &s, const Task &k, int64
   Window w;
   w.rbase = (int)rbase64;
   w.wrows = (int)(rend - rbase64);
-  w.ncell = cells_of_rows(w.wrows);
+  w.nword = words_of_rows(w.wrows);
   return w;
 }
 
-// clear the cells, then set the bit of every row that occurs in the task
+// clear the words, then set the bit of every row that occurs in the task
 template <class SR, bool MERGE, int THREADS>
-__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<THREADS> *q,
-                                            unsigned long long *cells, int ncell, int rbase) {
-  uint4 *c4 = reinterpret_cast<uint4 *>(cells);
-  const int nvec = (ncell + 1) >> 1; // 2 cells (16 bytes) per uint4
+__device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<THREADS> *q, unsigned *bits,
+                                            int nword, int rbase, bool stage_vals = false) {
+  uint4 *c4 = reinterpret_cast<uint4 *>(bits);
+  const int nvec = (nword + 3) >> 2; // the array is padded to a multiple of 4 words
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) c4[i] = make_uint4(0, 0, 0, 0);
-  unsigned *words = reinterpret_cast<unsigned *>(cells);
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   auto use = [&](int row, aval_t, typename SR::b_t) {
     const unsigned r = (unsigned)(row - rbase);
-    const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
-    atomicOr(&words[2 * cell + (bit >> 5)], 1u << (bit & 31));
+    atomicOr(&bits[r >> 5], 1u << (r & 31u));
   };
-  flat_walk<SR, MERGE, false>(s, k, q, use); // starts and ends with __syncthreads
+  bitmap_walk<SR, MERGE, false>(s, k, q, use, stage_vals); // starts and ends with __syncthreads
 }
 
-// number of present rows; with RANKS the exclusive prefix of every cell is written into its high bits.
-// Ends with __syncthreads (the cells are final afterwards). warp_sums has 33 entries.
+// number of present rows; with RANKS the exclusive prefix of every word goes to rank[]. Ends with __syncthreads.
+// warp_sums has 33 entries.
 template <bool RANKS>
-__device__ __forceinline__ int bitmap_scan(unsigned long long *cells, int ncell, int *warp_sums) {
-  const int cpt = (ncell + blockDim.x - 1) / blockDim.x;
-  const int c0 = min(ncell, (int)threadIdx.x * cpt), c1 = min(ncell, c0 + cpt);
+__device__ __forceinline__ int bitmap_scan(const unsigned *bits, unsigned *rank, int nword, int *warp_sums) {
+  // every thread owns a contiguous run of words; an ODD run length keeps the lanes of a warp on different banks
+  const int wpt = ((nword + blockDim.x - 1) / blockDim.x) | 1;
+  const int c0 = min(nword, (int)threadIdx.x * wpt), c1 = min(nword, c0 + wpt);
   int mine = 0;
-  for (int c = c0; c < c1; ++c) mine += __popcll(cells[c]);
+  for (int c = c0; c < c1; ++c) mine += __popc(bits[c]);
   int run = block_exclusive_scan(mine, warp_sums, warp_sums + 32);
   const int total = warp_sums[32];
   if (RANKS) {
     for (int c = c0; c < c1; ++c) {
-      const unsigned long long w = cells[c];
-      cells[c] = w | ((unsigned long long)run << kCellRows);
-      run += __popcll(w);
+      rank[c] = (unsigned)run;
+      run += __popc(bits[c]);
     }
   }
-  __syncthreads(); // cells final; warp_sums free for the next use
+  __syncthreads(); // ranks final; warp_sums free for the next use
   return total;
 }
 
-// K2 (bitmap): rows of the window present in the task. The first `save_count` CTAs of the launch also rank their
-// cells and store them at saved + blockIdx.x * save_stride for the numeric pass (slot_of_task[t] = blockIdx.x).
+// K2 (bitmap): rows of the window present in the task. The first `save_count` CTAs of the launch also store their
+// words at saved + blockIdx.x * save_stride for the numeric pass (slot_of_task[t] = blockIdx.x).
 template <class SR, bool MERGE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-sym_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int64_t *tasknnz,
-                  unsigned long long *saved, int64_t save_stride, int save_count, int32_t *slot_of_task) {
+sym_bitmap_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t m, int64_t *tasknnz, unsigned *saved,
+                  int64_t save_stride, int save_count, int32_t *slot_of_task) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
+  unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
   __shared__ FlatQueueT<THREADS> queue;
   __shared__ int warp_sums[33];
-  int t = order[blockIdx.x];
-  Task k = load_task(s, t);
-  task_segments(s, k);
+  const TaskRec r = recs[blockIdx.x];
+  const int t = (int)r.obase;
+  const Task k = task_from_record(s, r);
   const Window w = task_window(s, k, m);
-  bitmap_mark(s, k, &queue, cells, w.ncell, w.rbase);
+  bitmap_mark(s, k, &queue, bits, w.nword, w.rbase);
+  const int nnz = bitmap_scan<false>(bits, nullptr, w.nword, warp_sums);
   if ((int)blockIdx.x < save_count) { // uniform per CTA
-    const int nnz = bitmap_scan<true>(cells, w.ncell, warp_sums);
-    const uint4 *src = reinterpret_cast<const uint4 *>(cells);
+    const uint4 *src = reinterpret_cast<const uint4 *>(bits);
     uint4 *dst = reinterpret_cast<uint4 *>(saved + (int64_t)blockIdx.x * save_stride);
-    const int nvec = (w.ncell + 1) >> 1;
+    const int nvec = (w.nword + 3) >> 2;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x == 0) {
-      tasknnz[t] = nnz;
-      slot_of_task[t] = (int)blockIdx.x;
-    }
-  } else {
-    const int nnz = bitmap_scan<false>(cells, w.ncell, warp_sums);
-    if (threadIdx.x == 0) tasknnz[t] = nnz;
+    if (threadIdx.x == 0) slot_of_task[t] = (int)blockIdx.x;
   }
+  if (threadIdx.x == 0) tasknnz[t] = nnz;
 }
 
-// K4 (bitmap): rank every present row by popcount, accumulate values at their final sorted position.
-// GMEM_ACC == false: accumulators in shared memory, copied out at the end;
-// GMEM_ACC == true : accumulators are C's value array itself (atomics resolve in L2).
-template <class SR, bool MERGE, bool GMEM_ACC, int THREADS, int MINB = (THREADS == 512 ? 3 : (THREADS == 256 ? 5 : 8))>
-__global__ void __launch_bounds__(THREADS, MINB)
-num_bitmap_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, int64_t m, int max_cells,
-                  const int64_t *taskptr, int32_t *Cir, typename SR::out_t *Cval, const unsigned long long *saved,
-                  int64_t save_stride, const int32_t *slot_of_task) {
-  typedef typename SR::acc_t acc_t;
-  typedef typename SR::out_t out_t;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: cells[max_cells] u64 | acc[...] acc_t
-  unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
-  acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
-  __shared__ FlatQueueT<THREADS> queue;
-  __shared__ int warp_sums[33];
-  int t = order[blockIdx.x];
-  Task k = load_task(s, t);
-  task_segments(s, k);
-  const Window w = task_window(s, k, m);
-  const int rbase = w.rbase, ncell = w.ncell;
-  const int64_t obase = taskptr[t];
-  const int nnz = (int)(taskptr[t + 1] - obase);
-  const int slot = slot_of_task ? slot_of_task[t] : -1;
+// ranked words of a task in shared memory: taken from the symbolic pass if it stored them, marked again otherwise
+template <class SR, bool MERGE, int THREADS>
+__device__ __forceinline__ void bitmap_obtain(const Source<SR, MERGE> &s, const Task &k, FlatQueueT<THREADS> *q, unsigned *bits,
+                                              unsigned *rank, const Window &w, int *warp_sums, const unsigned *saved,
+                                              int64_t save_stride, int slot, bool stage_vals = false) {
   if (slot >= 0) {
-    // the symbolic pass left the ranked cells of this task in HBM
     const uint4 *src = reinterpret_cast<const uint4 *>(saved + (int64_t)slot * save_stride);
-    uint4 *dst = reinterpret_cast<uint4 *>(cells);
-    const int nvec = (ncell + 1) >> 1;
+    uint4 *dst = reinterpret_cast<uint4 *>(bits);
+    const int nvec = (w.nword + 3) >> 2;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
   } else {
-    bitmap_mark(s, k, &queue, cells, ncell, rbase);
-    bitmap_scan<true>(cells, ncell, warp_sums);
+    bitmap_mark(s, k, q, bits, w.nword, w.rbase, stage_vals);
   }
-  // Row emission: every lane walks its own cells (c, c + blockDim, ...) and emits one row per iteration, fetching its
-  // next cell when the current one is exhausted, so lanes whose cells hold few rows do not idle while a neighbour
-  // drains a full cell. Neighbouring lanes start on neighbouring cells, whose ranks are adjacent in Cir.
-  {
-    int c = threadIdx.x;
-    unsigned lo = 0, hi = 0;
-    int rowbase = 0;
-    int32_t *o = Cir;
-    while (true) {
-      if ((lo | hi) == 0) {
-        if (c >= ncell) break;
-        const unsigned long long cw = cells[c];
-        lo = (unsigned)cw;
-        hi = (unsigned)(cw >> 32) & ((1u << (kCellRows - 32)) - 1u);
-        o = Cir + obase + (int64_t)(cw >> kCellRows);
-        rowbase = rbase + c * kCellRows;
-        c += blockDim.x;
-        continue;
-      }
-      int b;
-      if (lo) {
-        b = __ffs(lo) - 1;
-        lo &= lo - 1;
-      } else {
-        b = 31 + __ffs(hi);
-        hi &= hi - 1;
-      }
-      *o++ = rowbase + b;
+  bitmap_scan<true>(bits, rank, w.nword, warp_sums);
+}
+
+// K4 (bitmap, accumulators in C itself): the fallback for tasks whose outputs do not fit shared memory. Every product is
+// one RED into the task's (L2-resident) slice of C's value array.
+template <class SR, bool MERGE, int THREADS, int MINB = (THREADS == 512 ? 2 : 4)>
+__global__ void __launch_bounds__(THREADS, MINB)
+num_bitmap_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t m, int max_words, int32_t *Cir,
+                  typename SR::out_t *Cval, const unsigned *saved, int64_t save_stride) {
+  typedef typename SR::acc_t acc_t;
+  typedef typename SR::out_t out_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
+  unsigned *rank = bits + max_words;
+  __shared__ FlatQueueT<THREADS> queue;
+  __shared__ int warp_sums[33];
+  const TaskRec r = recs[blockIdx.x];
+  const Task k = task_from_record(s, r);
+  const Window w = task_window(s, k, m);
+  const int rbase = w.rbase;
+  const int64_t obase = r.obase;
+  const int nnz = r.nnz;
+  bitmap_obtain(s, k, &queue, bits, rank, w, warp_sums, saved, save_stride, r.slot);
+  // rows: every thread unpacks words c, c + THREADS, ... (neighbouring lanes write neighbouring pieces of Cir)
+  for (int c = threadIdx.x; c < w.nword; c += THREADS) {
+    unsigned b = bits[c];
+    int32_t *o = Cir + obase + rank[c];
+    const int rowbase = rbase + (c << 5);
+    while (b) {
+      *o++ = rowbase + __ffs(b) - 1;
+      b &= b - 1;
     }
   }
-  if (GMEM_ACC) {
-    for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(SR::identity());
-  } else {
-    for (int i = threadIdx.x; i < nnz; i += blockDim.x) acc[i] = SR::identity();
-  }
-  __syncthreads();
+  for (int i = threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(SR::identity());
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
     const unsigned r = (unsigned)(row - rbase);
-    const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
-    const unsigned long long cw = cells[cell];
-    const unsigned rank = (unsigned)(cw >> kCellRows) + (unsigned)__popcll(cw & ((1ull << bit) - 1ull));
+    const unsigned wd = r >> 5;
+    const unsigned slot = rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (r & 31u)) - 1u));
     acc_t v;
     if (MERGE) v = SR::from_out((out_t)aval);
     else v = SR::mul((typename SR::a_t)aval, mu);
-    if (GMEM_ACC) SR::accumulate_out(&Cval[obase + rank], v);
-    else SR::accumulate(&acc[rank], v);
+    SR::accumulate_out(&Cval[obase + slot], v);
   };
-  flat_walk<SR, MERGE, true>(s, k, &queue, use);
-  if (!GMEM_ACC) {
-    for (int i = threadIdx.x; i < nnz; i += blockDim.x) Cval[obase + i] = SR::to_out(acc[i]);
-  }
+  bitmap_walk<SR, MERGE, true>(s, k, &queue, use); // starts with __syncthreads: the identities are in place
 }
 
 // K4 (bitmap, accumulators in shared memory): the numeric kernel of every task whose outputs fit the CTA's shared memory.
-// Ranked cells as above (handed over by the symbolic pass, or marked and scanned again); the sorted rows are scattered by
-// rank into a staging area and leave with coalesced stores; every product then finds its slot with one cell load and a
-// popcount and is added to a shared-memory accumulator with the exchange protocol of semiring.cuh (no CAS loop, no L2
-// reduction); the values leave once, coalesced. Nothing of C is touched twice and nothing is pre-filled.
+// Ranked words as above; the sorted rows are unpacked by rank into a staging area and leave with coalesced stores; every
+// product then finds its slot with two shared loads and a popcount and is added to a shared-memory accumulator with the
+// exchange protocol of semiring.cuh (no CAS loop, no L2 reduction); the values leave once, coalesced. Nothing of C is
+// touched twice and nothing is pre-filled.
 // FIRST: most outputs of the class receive a single product (compression close to 1).
 template <class SR, bool MERGE, int THREADS, int MINB, bool FIRST>
 __global__ void __launch_bounds__(THREADS, MINB)
-num_sacc_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t m, int max_cells, const int64_t *taskptr, int32_t *Cir,
-                typename SR::out_t *Cval, const unsigned long long *saved, int64_t save_stride, const int32_t *slot_of_task) {
+num_sacc_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_words, int32_t *Cir, typename SR::out_t *Cval,
+                const unsigned *saved, int64_t save_stride) {
   typedef typename SR::acc_t acc_t;
   typedef typename SR::out_t out_t;
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: cells[max_cells] u64 | acc[outputs of the largest task of the class] acc_t
-  unsigned long long *cells = reinterpret_cast<unsigned long long *>(smem_raw);
-  acc_t *acc = reinterpret_cast<acc_t *>(cells + max_cells);
+  // layout: bits[max_words] u32 | rank[max_words] u32 | acc[outputs of the largest task of the class] acc_t
+  unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
+  unsigned *rank = bits + max_words;
+  acc_t *acc = reinterpret_cast<acc_t *>(rank + max_words);
   __shared__ FlatQueueT<THREADS> queue;
   __shared__ int warp_sums[33];
-  const int t = order[blockIdx.x];
-  Task k = load_task(s, t);
-  task_segments(s, k);
+  const TaskRec r = recs[blockIdx.x];
+  const Task k = task_from_record(s, r);
   const Window w = task_window(s, k, m);
-  const int rbase = w.rbase, ncell = w.ncell;
-  const int64_t obase = taskptr[t];
-  const int nnz = (int)(taskptr[t + 1] - obase);
-  const int slot = slot_of_task ? slot_of_task[t] : -1;
-  if (slot >= 0) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(saved + (int64_t)slot * save_stride);
-    uint4 *dst = reinterpret_cast<uint4 *>(cells);
-    const int nvec = (ncell + 1) >> 1;
-    for (int i = threadIdx.x; i < nvec; i += THREADS) dst[i] = src[i];
-    __syncthreads();
-  } else {
-    bitmap_mark(s, k, &queue, cells, ncell, rbase);
-    bitmap_scan<true>(cells, ncell, warp_sums);
-  }
-  // rows: every thread unpacks its cells into the staging area (the accumulator array, not yet in use) at the ranks the
-  // cells carry, then the CTA copies the sorted list out with coalesced stores
+  const int rbase = w.rbase;
+  const int64_t obase = r.obase;
+  const int nnz = r.nnz;
+  // a task whose segments fit one chunk stages them once for both of its walks (mark, accumulate)
+  const bool restage = !MERGE && r.slot < 0 && r.nseg <= THREADS;
+  bitmap_obtain(s, k, &queue, bits, rank, w, warp_sums, saved, save_stride, r.slot, restage);
+  // rows: unpacked into the staging area (the accumulator array, not yet in use) at their ranks, then copied out
   int32_t *stage = reinterpret_cast<int32_t *>(acc);
-  for (int c = threadIdx.x; c < ncell; c += THREADS) {
-    const unsigned long long cw = cells[c];
-    unsigned lo = (unsigned)cw;
-    unsigned hi = (unsigned)(cw >> 32) & ((1u << (kCellRows - 32)) - 1u);
-    int o = (int)(cw >> kCellRows);
-    const int rowbase = rbase + c * kCellRows;
-    while (lo) {
-      stage[o++] = rowbase + __ffs(lo) - 1;
-      lo &= lo - 1;
-    }
-    while (hi) {
-      stage[o++] = rowbase + 31 + __ffs(hi);
-      hi &= hi - 1;
+  for (int c = threadIdx.x; c < w.nword; c += THREADS) {
+    unsigned b = bits[c];
+    int o = (int)rank[c];
+    const int rowbase = rbase + (c << 5);
+    while (b) {
+      stage[o++] = rowbase + __ffs(b) - 1;
+      b &= b - 1;
     }
   }
   __syncthreads();
@@ -971,15 +1123,15 @@ num_sacc_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t m, int max_ce
   for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity();
   auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
     const unsigned r = (unsigned)(row - rbase);
-    const unsigned cell = r / kCellRows, bit = r - cell * kCellRows;
-    const unsigned long long cw = cells[cell];
-    const unsigned rank = (unsigned)(cw >> kCellRows) + (unsigned)__popcll(cw & ((1ull << bit) - 1ull));
+    const unsigned wd = r >> 5;
+    const unsigned slot = rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (r & 31u)) - 1u));
     acc_t v;
     if (MERGE) v = SR::from_out((out_t)aval);
     else v = SR::mul((typename SR::a_t)aval, mu);
-    SR::template accumulate_shared<FIRST>(&acc[rank], v);
+    SR::template accumulate_shared<FIRST>(&acc[slot], v);
   };
-  flat_walk<SR, MERGE, true>(s, k, &queue, use); // starts and ends with __syncthreads
+  __syncthreads(); // accumulators initialised (the walk itself only synchronises when it stages)
+  bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
   for (int i = threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(acc[i]);
 }
 

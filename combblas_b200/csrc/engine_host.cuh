@@ -209,6 +209,8 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   CB_TRY(dev_alloc_t(ctx, &order, (size_t)ntask + 1));
   CB_TRY(dev_alloc_t(ctx, &tasknnz, (size_t)ntask + 1));
   CB_TRY(dev_alloc_t(ctx, &taskptr, (size_t)ntask + 2));
+  TaskRec *recs = nullptr; // launch-order records of the bitmap classes
+  CB_TRY(dev_alloc_t(ctx, &recs, (size_t)ntask + 1));
   BinResult bins;
   ClassRanges sc;
   memset(&bins, 0, sizeof(bins));
@@ -230,24 +232,29 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
                                                                       (int)opt.force_path, bucket);
     CB_LAUNCH_CHECK(ctx);
     CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, task_win, sym_class, order, &bins, &sc));
+    if (bins.listed > 0) {
+      task_record_kernel<SR, MERGE><<<(unsigned)((bins.listed + 255) / 256), 256, 0, st>>>(src, order, bins.listed, nullptr, nullptr, recs);
+      CB_LAUNCH_CHECK(ctx);
+    }
   }
   for (int b = 1; b < 256; ++b) stats.flops += bins.weight[b];
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
 
   // ---- K2: symbolic kernels
-  const int max_cells = (cells_of_rows(std::min<int64_t>(io.m, W)) + 1) & ~1; // even, covers the uint4 clear
-  const size_t bm_bytes = (size_t)max_cells * 8;
-  // Ranked cells of the large symbolic tasks are kept in HBM for the numeric pass (which then needs no mark walk and no
-  // scan of its own): one slot of max_cells words per task, as many tasks as fit the budget.
-  unsigned long long *saved = nullptr;
+  const int max_words = (words_of_rows(std::min<int64_t>(io.m, W)) + 3) & ~3; // multiple of 4: uint4 clears and copies
+  const size_t sym_bytes = (size_t)max_words * 4; // symbolic pass: presence words
+  const size_t bm_bytes = (size_t)max_words * 8;  // numeric pass: presence words + rank prefixes
+  // Presence words of the large symbolic tasks are kept in HBM for the numeric pass (which then needs no mark walk of
+  // its own): one slot of max_words words per task, as many tasks as fit the budget.
+  unsigned *saved = nullptr;
   int32_t *slot_of_task = nullptr;
   int save_count = 0;
   if (io.C && opt.bitmap_save_mb > 0 && sc.count[SYM_BM_L] > 0) {
-    const int64_t fit = (opt.bitmap_save_mb << 20) / (int64_t)bm_bytes;
+    const int64_t fit = (opt.bitmap_save_mb << 20) / (int64_t)sym_bytes;
     save_count = (int)std::min<int64_t>(sc.count[SYM_BM_L], fit);
     if (save_count > 0) {
       // an optimisation only: when HBM is too full for the hand-over buffer the numeric pass marks and ranks again
-      if (dev_alloc_t(ctx, &saved, (size_t)save_count * max_cells) != CBGPU_OK ||
+      if (dev_alloc_t(ctx, &saved, (size_t)save_count * max_words) != CBGPU_OK ||
           dev_alloc_t(ctx, &slot_of_task, (size_t)ntask) != CBGPU_OK) {
         dev_free(ctx, saved);
         dev_free(ctx, slot_of_task);
@@ -266,39 +273,46 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       if (tab[b] == c) s += second ? r.weight2[b] : r.weight[b];
     return s;
   };
-  if (sc.count[SYM_BM_L] + sc.count[SYM_BM_S] > 0) {
+  auto note_class = [&](int kid, int64_t tasks, int64_t flops, int64_t nnz) {
+    stats.class_tasks[kid] += tasks;
+    stats.class_flops[kid] += flops;
+    stats.class_nnz[kid] += nnz;
+  };
+  if (sc.count[SYM_BM_L] > 0) {
     CB_KBEGIN(CBGPU_K_SYM_BITMAP);
-    if (sc.count[SYM_BM_L] > 0) {
-      if (opt.bitmap_cta_threads == 256) {
-        auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
-        CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_L], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz,
-                                                                saved, max_cells, save_count, slot_of_task);
-      } else {
-        auto kern = sym_bitmap_kernel<SR, MERGE, 512>;
-        CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_L], 512, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz,
-                                                                saved, max_cells, save_count, slot_of_task);
-      }
-      CB_LAUNCH_CHECK(ctx);
+    if (opt.bitmap_cta_threads == 256) {
+      auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
+      CB_TRY(optin_smem(ctx, kern, sym_bytes));
+      kern<<<(unsigned)sc.count[SYM_BM_L], 256, sym_bytes, st>>>(src, recs + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz,
+                                                               saved, max_words, save_count, slot_of_task);
+    } else {
+      auto kern = sym_bitmap_kernel<SR, MERGE, 512>;
+      CB_TRY(optin_smem(ctx, kern, sym_bytes));
+      kern<<<(unsigned)sc.count[SYM_BM_L], 512, sym_bytes, st>>>(src, recs + sc.begin[SYM_BM_L], sc.count[SYM_BM_L], io.m, tasknnz,
+                                                               saved, max_words, save_count, slot_of_task);
     }
-    if (sc.count[SYM_BM_S] > 0) {
-      if (opt.bitmap_small_threads == 256) {
-        auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
-        CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_S], 256, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
-                                                                nullptr, 0, 0, nullptr);
-      } else {
-        auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
-        CB_TRY(optin_smem(ctx, kern, bm_bytes));
-        kern<<<(unsigned)sc.count[SYM_BM_S], 128, bm_bytes, st>>>(src, order + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
-                                                                nullptr, 0, 0, nullptr);
-      }
-      CB_LAUNCH_CHECK(ctx);
-    }
+    CB_LAUNCH_CHECK(ctx);
     CB_KEND(CBGPU_K_SYM_BITMAP);
-    stats.flops_sym[0] = class_weight(bins, sym_class, SYM_BM_L, false) + class_weight(bins, sym_class, SYM_BM_S, false);
+    note_class(CBGPU_K_SYM_BITMAP, sc.count[SYM_BM_L], class_weight(bins, sym_class, SYM_BM_L, false), 0);
   }
+  if (sc.count[SYM_BM_S] > 0) {
+    CB_KBEGIN(CBGPU_K_SYM_BITMAP_S);
+    if (opt.bitmap_small_threads == 256) {
+      auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
+      CB_TRY(optin_smem(ctx, kern, sym_bytes));
+      kern<<<(unsigned)sc.count[SYM_BM_S], 256, sym_bytes, st>>>(src, recs + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
+                                                               nullptr, 0, 0, nullptr);
+    } else {
+      auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
+      CB_TRY(optin_smem(ctx, kern, sym_bytes));
+      kern<<<(unsigned)sc.count[SYM_BM_S], 128, sym_bytes, st>>>(src, recs + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
+                                                               nullptr, 0, 0, nullptr);
+    }
+    CB_LAUNCH_CHECK(ctx);
+    CB_KEND(CBGPU_K_SYM_BITMAP_S);
+    note_class(CBGPU_K_SYM_BITMAP_S, sc.count[SYM_BM_S], class_weight(bins, sym_class, SYM_BM_S, false), 0);
+  }
+  stats.flops_sym[0] = class_weight(bins, sym_class, SYM_BM_L, false) + class_weight(bins, sym_class, SYM_BM_S, false);
   if (sc.count[SYM_H_CTA] > 0) {
     auto kern = sym_hash_kernel<SR, MERGE, 8, 12>;
     size_t sm = sizeof(unsigned) << 12;
@@ -380,6 +394,10 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
                                                                         cap_l, (int)opt.force_path, bucket);
       CB_LAUNCH_CHECK(ctx);
       CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, task_win, num_class, order, &nb, &nc));
+      if (nb.listed > 0) {
+        task_record_kernel<SR, MERGE><<<(unsigned)((nb.listed + 255) / 256), 256, 0, st>>>(src, order, nb.listed, taskptr, slot_of_task, recs);
+        CB_LAUNCH_CHECK(ctx);
+      }
     }
     out_t *Cval = reinterpret_cast<out_t *>(Cm->numx);
     // bitmap, accumulators in C itself: RED.ADD straight into the (L2-resident) output slice of the task.
@@ -389,15 +407,15 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       size_t sm = bm_bytes + 16;
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_GMEM);
       if (opt.bitmap_cta_threads == 256) {
-        auto kern = num_bitmap_kernel<SR, MERGE, true, 256>;
+        auto kern = num_bitmap_kernel<SR, MERGE, 256>;
         CB_TRY(optin_smem(ctx, kern, sm));
-        kern<<<(unsigned)nc.count[NUM_BM_G], 256, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                           taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
+        kern<<<(unsigned)nc.count[NUM_BM_G], 256, sm, st>>>(src, recs + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_words,
+                                                           Cm->ir, Cval, saved, max_words);
       } else {
-        auto kern = num_bitmap_kernel<SR, MERGE, true, 512>;
+        auto kern = num_bitmap_kernel<SR, MERGE, 512>;
         CB_TRY(optin_smem(ctx, kern, sm));
-        kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, order + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_cells,
-                                                           taskptr, Cm->ir, Cval, saved, max_cells, slot_of_task);
+        kern<<<(unsigned)nc.count[NUM_BM_G], 512, sm, st>>>(src, recs + nc.begin[NUM_BM_G], nc.count[NUM_BM_G], io.m, max_words,
+                                                           Cm->ir, Cval, saved, max_words);
       }
       CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_BITMAP_GMEM);
@@ -406,35 +424,54 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true);
     }
     // bitmap, accumulators in shared memory (exchange protocol): three CTA shapes by output count
-    if (nc.count[NUM_SA_L] + nc.count[NUM_SA_M] + nc.count[NUM_SA_S] > 0) {
+    if (nc.count[NUM_SA_L] > 0) {
+      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false>;
+      CB_TRY(optin_smem(ctx, kern, (size_t)dyn_l));
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
-      if (nc.count[NUM_SA_L] > 0) {
-        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false>;
-        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_l));
-        kern<<<(unsigned)nc.count[NUM_SA_L], kSaccThreadsL, (size_t)dyn_l, st>>>(src, order + nc.begin[NUM_SA_L], io.m, max_cells, taskptr,
-                                                                                Cm->ir, Cval, saved, max_cells, slot_of_task);
-        CB_LAUNCH_CHECK(ctx);
-      }
-      if (nc.count[NUM_SA_M] > 0) {
-        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, false>;
-        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_m));
-        kern<<<(unsigned)nc.count[NUM_SA_M], kSaccThreadsM, (size_t)dyn_m, st>>>(src, order + nc.begin[NUM_SA_M], io.m, max_cells, taskptr,
-                                                                                Cm->ir, Cval, saved, max_cells, slot_of_task);
-        CB_LAUNCH_CHECK(ctx);
-      }
-      if (nc.count[NUM_SA_S] > 0) {
-        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsS, kSaccBlocksS, true>;
-        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_s));
-        kern<<<(unsigned)nc.count[NUM_SA_S], kSaccThreadsS, (size_t)dyn_s, st>>>(src, order + nc.begin[NUM_SA_S], io.m, max_cells, taskptr,
-                                                                                Cm->ir, Cval, saved, max_cells, slot_of_task);
-        CB_LAUNCH_CHECK(ctx);
-      }
+      kern<<<(unsigned)nc.count[NUM_SA_L], kSaccThreadsL, (size_t)dyn_l, st>>>(src, recs + nc.begin[NUM_SA_L], io.m, max_words, Cm->ir, Cval,
+                                                                              saved, max_words);
+      CB_LAUNCH_CHECK(ctx);
       CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
-      for (int c : {NUM_SA_L, NUM_SA_M, NUM_SA_S}) {
+    }
+    if (nc.count[NUM_SA_M] > 0) {
+      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, false>;
+      CB_TRY(optin_smem(ctx, kern, (size_t)dyn_m));
+      CB_KBEGIN(CBGPU_K_NUM_SACC_M);
+      kern<<<(unsigned)nc.count[NUM_SA_M], kSaccThreadsM, (size_t)dyn_m, st>>>(src, recs + nc.begin[NUM_SA_M], io.m, max_words, Cm->ir, Cval,
+                                                                              saved, max_words);
+      CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_SACC_M);
+    }
+    if (nc.count[NUM_SA_S] > 0) {
+      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsS, kSaccBlocksS, true>;
+      CB_TRY(optin_smem(ctx, kern, (size_t)dyn_s));
+      CB_KBEGIN(CBGPU_K_NUM_SACC_S);
+      kern<<<(unsigned)nc.count[NUM_SA_S], kSaccThreadsS, (size_t)dyn_s, st>>>(src, recs + nc.begin[NUM_SA_S], io.m, max_words, Cm->ir, Cval,
+                                                                              saved, max_words);
+      CB_LAUNCH_CHECK(ctx);
+      CB_KEND(CBGPU_K_NUM_SACC_S);
+    }
+    {
+      const int kid[3] = {CBGPU_K_NUM_BITMAP_SMEM, CBGPU_K_NUM_SACC_M, CBGPU_K_NUM_SACC_S};
+      const int cls[3] = {NUM_SA_L, NUM_SA_M, NUM_SA_S};
+      for (int i = 0; i < 3; ++i) {
+        const int c = cls[i];
         stats.tasks_bitmap_smem += nc.count[c];
         stats.flops_bitmap_smem += class_weight(nb, num_class, c, false);
         stats.nnz_bitmap_smem += class_weight(nb, num_class, c, true);
+        note_class(kid[i], nc.count[c], class_weight(nb, num_class, c, false), class_weight(nb, num_class, c, true));
       }
+      note_class(CBGPU_K_NUM_BITMAP_GMEM, nc.count[NUM_BM_G], class_weight(nb, num_class, NUM_BM_G, false),
+                 class_weight(nb, num_class, NUM_BM_G, true));
+      note_class(CBGPU_K_NUM_HASH_CTA, nc.count[NUM_H_CTA], class_weight(nb, num_class, NUM_H_CTA, false),
+                 class_weight(nb, num_class, NUM_H_CTA, true));
+      note_class(CBGPU_K_NUM_HASH_WARP, nc.count[NUM_H_WARP], class_weight(nb, num_class, NUM_H_WARP, false),
+                 class_weight(nb, num_class, NUM_H_WARP, true));
+      note_class(CBGPU_K_NUM_HASH_WARP_M, nc.count[NUM_H_WARP_M] + nc.count[NUM_H_WARP_M2],
+                 class_weight(nb, num_class, NUM_H_WARP_M, false) + class_weight(nb, num_class, NUM_H_WARP_M2, false),
+                 class_weight(nb, num_class, NUM_H_WARP_M, true) + class_weight(nb, num_class, NUM_H_WARP_M2, true));
+      note_class(CBGPU_K_NUM_HASH_WARP_S, nc.count[NUM_H_WARP_S], class_weight(nb, num_class, NUM_H_WARP_S, false),
+                 class_weight(nb, num_class, NUM_H_WARP_S, true));
     }
     // hash per CTA: 257..2048 outputs
     if (nc.count[NUM_H_CTA] > 0) {
@@ -528,6 +565,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   dev_free(ctx, order);
   dev_free(ctx, tasknnz);
   dev_free(ctx, taskptr);
+  dev_free(ctx, recs);
   dev_free(ctx, saved);
   dev_free(ctx, slot_of_task);
   if (rc != CBGPU_OK) {

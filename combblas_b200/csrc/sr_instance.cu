@@ -18,7 +18,8 @@ static int spgemm_impl(const SpgemmArgs &a) {
   CB_TRY(ensure_dense_colptr(ctx, A));
   int nwin, wlog2;
   engine_windows(ctx, A->m, &nwin, &wlog2);
-  if (nwin > 1 && A->nnz > 0 && B->nnz > 0) CB_TRY(ensure_window_major(ctx, A, nwin, wlog2)); // cached on A
+  // the window-major copy (16-byte aligned pieces) is what the bitmap kernels read, whatever the number of windows; cached on A
+  if (A->nnz > 0 && B->nnz > 0) CB_TRY(ensure_window_major(ctx, A, nwin, wlog2));
   Source<SR, false> src;
   memset(&src, 0, sizeof(src));
   src.T2 = A->win_T2;

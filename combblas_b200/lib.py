@@ -46,14 +46,19 @@ class Stats(C.Structure):
                 ("tasks_bitmap_gmem", C.c_int64), ("flops_hash_warp", C.c_int64), ("flops_hash_cta", C.c_int64),
                 ("flops_bitmap_smem", C.c_int64), ("flops_bitmap_gmem", C.c_int64),
                 ("nnz_hash_warp", C.c_int64), ("nnz_hash_cta", C.c_int64), ("nnz_bitmap_smem", C.c_int64),
-                ("nnz_bitmap_gmem", C.c_int64), ("ms_kernel", C.c_float * 12), ("flops_sym", C.c_int64 * 5)]
+                ("nnz_bitmap_gmem", C.c_int64), ("ms_kernel", C.c_float * 16), ("flops_sym", C.c_int64 * 5),
+                ("class_tasks", C.c_int64 * 16), ("class_flops", C.c_int64 * 16), ("class_nnz", C.c_int64 * 16)]
 
     KERNELS = ["sym_bitmap", "sym_hash_cta_large", "sym_hash_cta", "sym_hash_warp", "sym_hash_warp_small",
                "num_bitmap_gmem", "num_bitmap_smem", "num_hash_cta", "num_hash_warp", "num_hash_warp_small", "flop",
-               "num_hash_warp_mid"]
+               "num_hash_warp_mid", "num_sacc_medium", "num_sacc_small", "sym_bitmap_small", "-"]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_kernel", "flops_sym")}
+        skip = ("ms_kernel", "flops_sym", "class_tasks", "class_flops", "class_nnz")
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in skip}
+        d["classes"] = {n: {"tasks": int(self.class_tasks[i]), "flops": int(self.class_flops[i]), "nnz": int(self.class_nnz[i]),
+                            "ms": round(float(self.ms_kernel[i]), 4)}
+                        for i, n in enumerate(self.KERNELS) if self.class_tasks[i] > 0}
         d["ms_kernel"] = {n: round(float(self.ms_kernel[i]), 4) for i, n in enumerate(self.KERNELS) if self.ms_kernel[i] > 0}
         d["flops_sym"] = [int(x) for x in self.flops_sym]
         return d

@@ -98,15 +98,19 @@ typedef struct {
   int64_t flops_hash_warp, flops_hash_cta, flops_bitmap_smem, flops_bitmap_gmem;
   int64_t nnz_hash_warp, nnz_hash_cta, nnz_bitmap_smem, nnz_bitmap_gmem; /* outputs written per numeric path */
   /* device time of each kernel class of this call (CUDA events on the context's stream), see CBGPU_K_* */
-  float ms_kernel[12];
+  float ms_kernel[16];
   int64_t flops_sym[5]; /* products walked by the symbolic classes CBGPU_K_SYM_* */
+  /* per kernel class (CBGPU_K_*): tasks, products and outputs it handled in this call */
+  int64_t class_tasks[16], class_flops[16], class_nnz[16];
 } cbgpu_stats;
 
 enum {
   CBGPU_K_SYM_BITMAP = 0, CBGPU_K_SYM_HASH_CTA_L = 1, CBGPU_K_SYM_HASH_CTA = 2, CBGPU_K_SYM_HASH_WARP = 3,
   CBGPU_K_SYM_HASH_WARP_S = 4, CBGPU_K_NUM_BITMAP_GMEM = 5, CBGPU_K_NUM_BITMAP_SMEM = 6, CBGPU_K_NUM_HASH_CTA = 7,
   CBGPU_K_NUM_HASH_WARP = 8, CBGPU_K_NUM_HASH_WARP_S = 9, CBGPU_K_FLOP = 10, CBGPU_K_NUM_HASH_WARP_M = 11,
-  CBGPU_K_COUNT = 12
+  /* CBGPU_K_NUM_BITMAP_SMEM is the large (1024-thread) shape of the shared-accumulator kernel; medium and small: */
+  CBGPU_K_NUM_SACC_M = 12, CBGPU_K_NUM_SACC_S = 13, CBGPU_K_SYM_BITMAP_S = 14,
+  CBGPU_K_COUNT = 16
 };
 
 /* ---------------------------------------------------------------- lifecycle */
