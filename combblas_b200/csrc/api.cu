@@ -465,6 +465,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "bitmap_cta_threads")) return &o.bitmap_cta_threads;
   if (!strcmp(name, "bitmap_small_threads")) return &o.bitmap_small_threads;
   if (!strcmp(name, "bitmap_save_mb")) return &o.bitmap_save_mb;
+  if (!strcmp(name, "bitmap_save_min_flop")) return &o.bitmap_save_min_flop;
   if (!strcmp(name, "light_max")) return &o.light_max;
   if (!strcmp(name, "bitmap_small_minblocks")) return &o.bitmap_small_minblocks;
   if (!strcmp(name, "force_path")) return &o.force_path;

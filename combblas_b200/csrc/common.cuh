@@ -31,7 +31,8 @@ struct Options {
   int64_t shared_acc_small_max = -1; // >= 0: upper limit on the outputs of the small (256-thread) shape
   int64_t bitmap_cta_threads = 512; // CTA size of the large-task bitmap kernels (512 or 256)
   int64_t bitmap_small_threads = 128; // CTA size of the small-task bitmap kernels (128 or 256)
-  int64_t bitmap_save_mb = 6144;   // HBM budget (MiB) for the ranked cells the symbolic pass hands to the numeric pass; 0 = off
+  int64_t bitmap_save_mb = 8192;   // HBM budget (MiB) for the presence words the symbolic pass hands to the numeric pass; 0 = off
+  int64_t bitmap_save_min_flop = 8192; // tasks with at least this many products are handed over (4 bytes per 32 rows of the window)
   int64_t light_max = 256;         // with several row windows, columns up to this many products stay one task (<= 2048)
   int64_t bitmap_small_minblocks = 8; // resident CTAs per SM the 128-thread numeric bitmap kernel is compiled for (8 or 12)
   int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only

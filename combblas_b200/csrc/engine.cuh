@@ -111,7 +111,8 @@ struct TaskRec {
 
 template <class SR, bool MERGE>
 __global__ void task_record_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const int64_t *taskptr,
-                                   const int32_t *slot_of_task, TaskRec *recs) {
+                                   const int32_t *slot_of_task, TaskRec *recs, const int64_t *taskflop = nullptr,
+                                   int64_t save_min_flop = 0, int save_cap = 0, int *save_counter = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const int t = order[i];
@@ -133,6 +134,11 @@ __global__ void task_record_kernel(Source<SR, MERGE> s, const int32_t *order, in
     r.nnz = 0;
   }
   r.slot = slot_of_task ? slot_of_task[t] : -1;
+  // symbolic records: tasks with enough products get a hand-over slot for their presence words, while slots last
+  if (save_counter && taskflop[t] >= save_min_flop && ((r.win >> 16) - (r.win & 0xFFFFu)) == 1u) {
+    const int sl = atomicAdd(save_counter, 1);
+    r.slot = sl < save_cap ? sl : -1;
+  }
   recs[i] = r;
 }
 
@@ -990,8 +996,8 @@ __device__ __forceinline__ int bitmap_scan(const unsigned *bits, unsigned *rank,
   return total;
 }
 
-// K2 (bitmap): rows of the window present in the task. The first `save_count` CTAs of the launch also store their
-// words at saved + blockIdx.x * save_stride for the numeric pass (slot_of_task[t] = blockIdx.x).
+// K2 (bitmap): rows of the window present in the task. Tasks whose record carries a hand-over slot also store their
+// words at saved + slot * save_stride for the numeric pass (slot_of_task[t] = slot).
 template <class SR, bool MERGE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sym_bitmap_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t m, int64_t *tasknnz, unsigned *saved,
@@ -1006,12 +1012,12 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64
   const Window w = task_window(s, k, m);
   bitmap_mark(s, k, &queue, bits, w.nword, w.rbase);
   const int nnz = bitmap_scan<false>(bits, nullptr, w.nword, warp_sums);
-  if ((int)blockIdx.x < save_count) { // uniform per CTA
+  if (r.slot >= 0) { // uniform per CTA
     const uint4 *src = reinterpret_cast<const uint4 *>(bits);
-    uint4 *dst = reinterpret_cast<uint4 *>(saved + (int64_t)blockIdx.x * save_stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(saved + (int64_t)r.slot * save_stride);
     const int nvec = (w.nword + 3) >> 2;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x == 0) slot_of_task[t] = (int)blockIdx.x;
+    if (threadIdx.x == 0) slot_of_task[t] = r.slot;
   }
   if (threadIdx.x == 0) tasknnz[t] = nnz;
 }

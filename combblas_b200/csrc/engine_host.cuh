@@ -232,10 +232,6 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
                                                                       (int)opt.force_path, bucket);
     CB_LAUNCH_CHECK(ctx);
     CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, task_win, sym_class, order, &bins, &sc));
-    if (bins.listed > 0) {
-      task_record_kernel<SR, MERGE><<<(unsigned)((bins.listed + 255) / 256), 256, 0, st>>>(src, order, bins.listed, nullptr, nullptr, recs);
-      CB_LAUNCH_CHECK(ctx);
-    }
   }
   for (int b = 1; b < 256; ++b) stats.flops += bins.weight[b];
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -249,23 +245,34 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   unsigned *saved = nullptr;
   int32_t *slot_of_task = nullptr;
   int save_count = 0;
-  if (io.C && opt.bitmap_save_mb > 0 && sc.count[SYM_BM_L] > 0) {
+  int *save_counter = nullptr;
+  if (io.C && opt.bitmap_save_mb > 0 && sc.count[SYM_BM_L] + sc.count[SYM_BM_S] > 0) {
     const int64_t fit = (opt.bitmap_save_mb << 20) / (int64_t)sym_bytes;
-    save_count = (int)std::min<int64_t>(sc.count[SYM_BM_L], fit);
+    save_count = (int)std::min<int64_t>(sc.count[SYM_BM_L] + sc.count[SYM_BM_S], fit);
     if (save_count > 0) {
       // an optimisation only: when HBM is too full for the hand-over buffer the numeric pass marks and ranks again
       if (dev_alloc_t(ctx, &saved, (size_t)save_count * max_words) != CBGPU_OK ||
-          dev_alloc_t(ctx, &slot_of_task, (size_t)ntask) != CBGPU_OK) {
+          dev_alloc_t(ctx, &slot_of_task, (size_t)ntask) != CBGPU_OK || dev_alloc_t(ctx, &save_counter, 4) != CBGPU_OK) {
         dev_free(ctx, saved);
         dev_free(ctx, slot_of_task);
+        dev_free(ctx, save_counter);
         saved = nullptr;
         slot_of_task = nullptr;
+        save_counter = nullptr;
         save_count = 0;
         ctx->last_error.clear();
       } else {
         CB_CUDA(ctx, cudaMemsetAsync(slot_of_task, 0xFF, sizeof(int32_t) * (size_t)ntask, st));
+        CB_CUDA(ctx, cudaMemsetAsync(save_counter, 0, 4 * sizeof(int), st));
       }
     }
+  }
+  // the records of the symbolic launch, now that the hand-over slots can be dealt out
+  if (ntask > 0 && bins.listed > 0) {
+    task_record_kernel<SR, MERGE><<<(unsigned)((bins.listed + 255) / 256), 256, 0, st>>>(
+        src, order, bins.listed, nullptr, nullptr, recs, taskflop, std::max<int64_t>(opt.bitmap_save_min_flop, 1), save_count,
+        save_counter);
+    CB_LAUNCH_CHECK(ctx);
   }
   auto class_weight = [](const BinResult &r, const uint8_t *tab, int c, bool second) {
     int64_t s = 0;
@@ -301,12 +308,12 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       auto kern = sym_bitmap_kernel<SR, MERGE, 256>;
       CB_TRY(optin_smem(ctx, kern, sym_bytes));
       kern<<<(unsigned)sc.count[SYM_BM_S], 256, sym_bytes, st>>>(src, recs + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
-                                                               nullptr, 0, 0, nullptr);
+                                                               saved, max_words, save_count, slot_of_task);
     } else {
       auto kern = sym_bitmap_kernel<SR, MERGE, 128>;
       CB_TRY(optin_smem(ctx, kern, sym_bytes));
       kern<<<(unsigned)sc.count[SYM_BM_S], 128, sym_bytes, st>>>(src, recs + sc.begin[SYM_BM_S], sc.count[SYM_BM_S], io.m, tasknnz,
-                                                               nullptr, 0, 0, nullptr);
+                                                               saved, max_words, save_count, slot_of_task);
     }
     CB_LAUNCH_CHECK(ctx);
     CB_KEND(CBGPU_K_SYM_BITMAP_S);
@@ -434,7 +441,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
     }
     if (nc.count[NUM_SA_M] > 0) {
-      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, false>;
+      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, true>; // compression 1.6: most slots see one product
       CB_TRY(optin_smem(ctx, kern, (size_t)dyn_m));
       CB_KBEGIN(CBGPU_K_NUM_SACC_M);
       kern<<<(unsigned)nc.count[NUM_SA_M], kSaccThreadsM, (size_t)dyn_m, st>>>(src, recs + nc.begin[NUM_SA_M], io.m, max_words, Cm->ir, Cval,
@@ -568,6 +575,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   dev_free(ctx, recs);
   dev_free(ctx, saved);
   dev_free(ctx, slot_of_task);
+  dev_free(ctx, save_counter);
   if (rc != CBGPU_OK) {
     mat_release(ctx, Cm);
     return rc;
