@@ -62,13 +62,13 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 __global__ void checksum_kernel(const int64_t *jc, const int64_t *cp, const int32_t *ir, const unsigned char *vals,
-                                int vbytes, int64_t nzc, unsigned long long *sums) {
+                                int vbytes, int64_t nzc, int64_t row_offset, int64_t col_offset, unsigned long long *sums) {
   int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint64_t ps = 0, vs = 0;
   if (c < nzc) {
-    uint64_t col = (uint64_t)jc[c];
+    uint64_t col = (uint64_t)(jc[c] + col_offset);
     for (int64_t p = cp[c] + (threadIdx.x & 31); p < cp[c + 1]; p += 32) {
-      uint64_t key = (col << 32) ^ (uint64_t)(uint32_t)ir[p];
+      uint64_t key = (col << 32) ^ (uint64_t)(uint32_t)((int64_t)ir[p] + row_offset);
       uint64_t h = mix64(key + 0x9E3779B97F4A7C15ULL);
       uint64_t vb = 0;
       for (int b = 0; b < vbytes; ++b) vb |= (uint64_t)vals[p * vbytes + b] << (8 * b);
@@ -610,13 +610,18 @@ int cbgpu_mat_free(cbgpu_ctx *ctx, cbgpu_mat *M) {
 }
 
 int cbgpu_mat_checksum(cbgpu_ctx *ctx, const cbgpu_mat *M, uint64_t *pattern_sum, uint64_t *value_sum) {
-  if (!ctx || !M) return CBGPU_ERR_INVALID;
+  return cbgpu_mat_checksum_at(ctx, M, 0, 0, pattern_sum, value_sum);
+}
+
+int cbgpu_mat_checksum_at(cbgpu_ctx *ctx, const cbgpu_mat *M, int64_t row_offset, int64_t col_offset, uint64_t *pattern_sum,
+                          uint64_t *value_sum) {
+  if (!ctx || !M || row_offset < 0 || col_offset < 0 || row_offset + M->m > ((int64_t)1 << 32)) return CBGPU_ERR_INVALID;
   unsigned long long *d = nullptr, h[2] = {0, 0};
   CB_TRY(dev_alloc_t(ctx, &d, 2));
   CB_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
   if (M->nzc > 0) {
     checksum_kernel<<<nblocks(M->nzc * 32), 256, 0, ctx->stream>>>(M->jc, M->cp, M->ir, (const unsigned char *)M->numx,
-                                                                   (int)dtype_size(M->dtype), M->nzc, d);
+                                                                   (int)dtype_size(M->dtype), M->nzc, row_offset, col_offset, d);
     CB_LAUNCH_CHECK(ctx);
   }
   CB_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));

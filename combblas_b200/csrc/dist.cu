@@ -232,12 +232,16 @@ static int bcast_block(cbgpu_ctx *ctx, ncclComm_t comm, int root, int me, const 
   }
   const size_t vb = dtype_size(dtype);
   if (nnz > 0) {
-    CB_NCCL(ctx, nccl().GroupStart());
-    CB_NCCL(ctx, nccl().Broadcast(src->jc, src->jc, (size_t)nzc * 8, nccl_bytes(), root, comm, ctx->stream));
-    CB_NCCL(ctx, nccl().Broadcast(src->cp, src->cp, (size_t)(nzc + 1) * 8, nccl_bytes(), root, comm, ctx->stream));
-    CB_NCCL(ctx, nccl().Broadcast(src->ir, src->ir, (size_t)nnz * 4, nccl_bytes(), root, comm, ctx->stream));
-    CB_NCCL(ctx, nccl().Broadcast(src->numx, src->numx, (size_t)nnz * vb, nccl_bytes(), root, comm, ctx->stream));
-    CB_NCCL(ctx, nccl().GroupEnd());
+    ncclResult_t r = nccl().GroupStart();
+    if (r == ncclSuccess) r = nccl().Broadcast(src->jc, src->jc, (size_t)nzc * 8, nccl_bytes(), root, comm, ctx->stream);
+    if (r == ncclSuccess) r = nccl().Broadcast(src->cp, src->cp, (size_t)(nzc + 1) * 8, nccl_bytes(), root, comm, ctx->stream);
+    if (r == ncclSuccess) r = nccl().Broadcast(src->ir, src->ir, (size_t)nnz * 4, nccl_bytes(), root, comm, ctx->stream);
+    if (r == ncclSuccess) r = nccl().Broadcast(src->numx, src->numx, (size_t)nnz * vb, nccl_bytes(), root, comm, ctx->stream);
+    const ncclResult_t r2 = nccl().GroupEnd(); // always closes the group, also after a failed call inside it
+    if (r != ncclSuccess || r2 != ncclSuccess) {
+      mat_release(ctx, R);
+      return set_error(ctx, CBGPU_ERR_NCCL, "block broadcast failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
+    }
     *bytes += nzc * 16 + 8 + nnz * (4 + (int64_t)vb);
   } else if (R) {
     CB_CUDA(ctx, cudaMemsetAsync(R->cp, 0, 8, ctx->stream));
@@ -602,7 +606,7 @@ static int gather_A_all_layers(cbgpu_ctx *ctx, cbgpu_comm *comm, const cbgpu_mat
 
 // one column slab Bslab of this rank's B block -> this rank's final piece of C for that slab
 static int fiber_fused_slab(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *Aall, const cbgpu_mat *Bslab,
-                            cbgpu_mat **C, cbgpu_dist_stats *ds) {
+                            cbgpu_mat **C, cbgpu_dist_stats *ds, int64_t *sym_flops = nullptr, int64_t *sym_nnz = nullptr) {
   const cbgpu_grid &g = comm->grid;
   const int L = g.layers;
   Timer tm(ctx->stream);
@@ -641,7 +645,11 @@ static int fiber_fused_slab(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cons
   if (rc == CBGPU_OK && Aall->n != Ball->m)
     rc = set_error(ctx, CBGPU_ERR_DIMMISMATCH, "fiber-fused multiply: inner dimensions differ (%lld vs %lld)", (long long)Aall->n,
                    (long long)Ball->m);
-  if (rc == CBGPU_OK) {
+  if (rc == CBGPU_OK && sym_flops) { // symbolic only: the products and the outputs this rank will produce
+    tm.start();
+    rc = cbgpu_spgemm_symbolic(ctx, Aall, Ball, sym_flops, sym_nnz);
+    ds->ms_multiply += tm.stop();
+  } else if (rc == CBGPU_OK) {
     cbgpu_stats st;
     memset(&st, 0, sizeof(st));
     tm.start();
@@ -672,6 +680,23 @@ int cbgpu_summa2d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
   return rc;
 }
 
+/* Distributed symbolic pass: the exact number of products and of outputs THIS rank produces in the distributed product, in
+ * the final distribution of C (column-split across layers). replaces: EstPerProcessNnzSUMMA (ParFriends.h:1698, an estimate
+ * that returns 0 in-tree) and the per-stage estimateFLOP / estimateNNZ loop of CalculateNumberOfPhases (:780-843). The inputs
+ * are gathered exactly as the fiber-fused multiply gathers them; nothing of C is allocated. */
+int cbgpu_summa_symbolic(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops,
+                         int64_t *nnz_out) {
+  if (!ctx || !comm || !A || !B || !flops || !nnz_out) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cbgpu_dist_stats ds;
+  memset(&ds, 0, sizeof(ds));
+  cbgpu_mat *Aall = nullptr;
+  int rc = gather_A_all_layers(ctx, comm, A, &Aall, &ds);
+  if (rc == CBGPU_OK) rc = fiber_fused_slab(ctx, comm, semiring, Aall, B, nullptr, &ds, flops, nnz_out);
+  mat_release(ctx, Aall);
+  return rc;
+}
+
 int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, cbgpu_mat **C,
                   cbgpu_dist_stats *stats) {
   if (!ctx || !comm || !A || !B || !C) return CBGPU_ERR_INVALID;
@@ -699,13 +724,40 @@ int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
 
 // Phased distributed multiply (MemEfficientSpGEMM ParFriends.h:453-777, MemEfficientSpGEMM3D :3674-4170): B's local columns
 // are cut into `phases` slabs (ColSplit rule) and one SUMMA runs per slab, so that C never has to exist as a whole.
-// With several layers the two halves of a phase are PIPELINED: a second host thread with its own context and stream
-// runs the fiber exchange + merge of slab p (NVLink traffic, few SMs) while this thread already multiplies slab p+1.
+// With several layers the default is the fiber-fused formulation (inputs replicated along the fiber, nothing merged). With
+// fiber_fused = 0 the reference's fiber reduction runs after each slab; option fiber_pipeline = 1 overlaps the reduction of
+// slab p with the multiply of slab p+1 on a second host thread, context and stream (two NCCL communicators are then in
+// use concurrently from two threads: opt-in).
+static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                             int want_checksum, bool global, int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs,
+                             cbgpu_slab_result *results, cbgpu_dist_stats *stats);
+
 int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                        int want_checksum, cbgpu_mat **slabs, cbgpu_slab_result *results, cbgpu_dist_stats *stats) {
+  return summa_phased_impl(ctx, comm, semiring, A, B, phases, want_checksum, false, 0, 0, slabs, results, stats);
+}
+
+int cbgpu_summa_phased_global(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                              int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs, cbgpu_slab_result *results,
+                              cbgpu_dist_stats *stats) {
+  return summa_phased_impl(ctx, comm, semiring, A, B, phases, 1, true, row_offset, col_offset, slabs, results, stats);
+}
+
+static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                             int want_checksum, bool global, int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs,
+                             cbgpu_slab_result *results, cbgpu_dist_stats *stats) {
   if (!ctx || !comm || !A || !B || phases < 1 || !results) return CBGPU_ERR_INVALID;
   CB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int L = comm->grid.layers;
+  // global position of the piece of C this rank ends up with for slab p: the slab's columns inside B's block (ColSplit rule,
+  // dcsc.cpp:1202), then with layers the fiber's sub-slab of that slab (CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576)
+  auto slab_checksum = [&](cbgpu_ctx *c, int p, const cbgpu_mat *Cp, cbgpu_slab_result *r) -> int {
+    if (!global) return cbgpu_mat_checksum(c, Cp, &r->pattern_sum, &r->value_sum);
+    const int64_t per = B->n / phases, s0 = per * p, s1 = (p == phases - 1) ? B->n : per * (p + 1);
+    int64_t sub0 = 0, sub1 = 0;
+    if (L > 1) cbgpu_block_range(s1 - s0, L, comm->grid.my_layer, &sub0, &sub1);
+    return cbgpu_mat_checksum_at(c, Cp, row_offset, col_offset + s0 + sub0, &r->pattern_sum, &r->value_sum);
+  };
   cbgpu_dist_stats ds;
   memset(&ds, 0, sizeof(ds));
   Timer all(ctx->stream);
@@ -726,7 +778,7 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
       results[p].nnz = Cp->nnz;
       results[p].nzc = Cp->nzc;
       results[p].pattern_sum = results[p].value_sum = 0;
-      if (want_checksum) rcf = cbgpu_mat_checksum(ctx, Cp, &results[p].pattern_sum, &results[p].value_sum);
+      if (want_checksum) rcf = slab_checksum(ctx, p, Cp, &results[p]);
       if (slabs) slabs[p] = Cp;
       else mat_release(ctx, Cp);
     }
@@ -737,7 +789,8 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
     if (stats) *stats = ds;
     return rcf;
   }
-  if (L > 1 && !comm->ctx2) {
+  const bool pipelined = L > 1 && ctx->opt.fiber_pipeline != 0;
+  if (pipelined && !comm->ctx2) {
     int rc2 = cbgpu_create(ctx->device, nullptr, &comm->ctx2);
     if (rc2 != CBGPU_OK) return set_error(ctx, rc2, "could not create the second context of the pipeline");
     comm->ctx2->opt = ctx->opt;
@@ -756,13 +809,13 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
     results[p].nzc = Cp->nzc;
     results[p].pattern_sum = results[p].value_sum = 0;
     int rc = CBGPU_OK;
-    if (want_checksum) rc = cbgpu_mat_checksum(c, Cp, &results[p].pattern_sum, &results[p].value_sum);
+    if (want_checksum) rc = slab_checksum(c, p, Cp, &results[p]);
     if (slabs) slabs[p] = Cp;
     else mat_release(c, Cp);
     return rc;
   };
   std::thread worker;
-  if (L > 1) {
+  if (pipelined) {
     worker = std::thread([&]() {
       cbgpu_ctx *c2 = comm->ctx2;
       cudaSetDevice(c2->device);
@@ -799,6 +852,12 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
       rc = finish_slab(ctx, p, Cl);
       continue;
     }
+    if (!pipelined) { // one host thread, one stream: the fiber reduction of slab p runs before the multiply of slab p + 1
+      cbgpu_mat *Cp = nullptr;
+      rc = fiber_reduce(ctx, comm, semiring, Cl, &Cp, &ds);
+      if (rc == CBGPU_OK) rc = finish_slab(ctx, p, Cp);
+      continue;
+    }
     Item it{Cl, nullptr};
     cudaEventCreateWithFlags(&it.ready, cudaEventDisableTiming);
     cudaEventRecord(it.ready, ctx->stream);
@@ -812,7 +871,7 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
       if (worker_rc != CBGPU_OK) rc = worker_rc;
     }
   }
-  if (L > 1) {
+  if (pipelined) {
     {
       std::lock_guard<std::mutex> lock(mu);
       if (rc != CBGPU_OK) producer_failed = true;

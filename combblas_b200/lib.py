@@ -123,6 +123,7 @@ SIGNATURES = {
     "cbgpu_mat_device_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "cbgpu_mat_free": (C.c_int, [_P, _P]),
     "cbgpu_mat_checksum": (C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cbgpu_mat_checksum_at": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cbgpu_mat_colsplit": (C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
     "cbgpu_mat_colslice": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "cbgpu_mat_colconcat": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
@@ -148,9 +149,14 @@ SIGNATURES = {
     "cbgpu_summa2d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
     "cbgpu_summa3d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
     "cbgpu_summa_phased": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(SlabResult), C.POINTER(DistStats)]),
+    "cbgpu_summa_symbolic": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cbgpu_summa_phased_global": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(SlabResult),
+                                            C.POINTER(DistStats)]),
     "cbgpu_rmat_edges_host": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, _P, _P]),
     "cbgpu_gen_rmat": (C.c_int, [_P, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.c_int, C.POINTER(_P)]),
+    "cbgpu_gen_rmat_block": (C.c_int, [_P, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                       C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P)]),
 }
 
 
@@ -304,9 +310,10 @@ class Context:
                                                     vals.ctypes.data, idx_dtype.itemsize))
         return rows, cols, vals
 
-    def checksum(self, D: DeviceMatrix):
+    def checksum(self, D: DeviceMatrix, row_offset: int = 0, col_offset: int = 0):
+        """order-independent (pattern, value) sums; with offsets, of the block placed at that position of a larger matrix"""
         a, b = C.c_uint64(), C.c_uint64()
-        self._check(self.lib.cbgpu_mat_checksum(self.handle, D.handle, C.byref(a), C.byref(b)))
+        self._check(self.lib.cbgpu_mat_checksum_at(self.handle, D.handle, row_offset, col_offset, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def colslice(self, D: DeviceMatrix, c0: int, c1: int) -> DeviceMatrix:
@@ -386,6 +393,13 @@ class Context:
 
     def inflate(self, A: DeviceMatrix, power: float):
         self._check(self.lib.cbgpu_mat_inflate(self.handle, A.handle, C.c_double(power)))
+
+    def gen_rmat_block(self, scale, nedges, seed, r0, r1, c0, c1, a=0.57, b=0.19, c=0.19, scramble=True, dtype=F64, value_mode=0):
+        """block [r0,r1) x [c0,c1) of gen_rmat's matrix, local indices, without materialising the whole matrix"""
+        h = _P()
+        self._check(self.lib.cbgpu_gen_rmat_block(self.handle, scale, nedges, seed, a, b, c, int(scramble), dtype, value_mode,
+                                                  r0, r1, c0, c1, C.byref(h)))
+        return DeviceMatrix(self, h)
 
     def gen_rmat(self, scale, nedges, seed, a=0.57, b=0.19, c=0.19, scramble=True, dtype=F64, value_mode=0):
         h = _P()
@@ -485,13 +499,25 @@ class Comm:
         self.ctx._check(self.ctx.lib.cbgpu_summa3d(self.ctx.handle, self.handle, sr, A.handle, B.handle, C.byref(h), C.byref(st)))
         return DeviceMatrix(self.ctx, h), st
 
-    def summa_phased(self, sr, A: DeviceMatrix, B: DeviceMatrix, phases: int, want_checksum=False, keep=False):
-        """MemEfficientSpGEMM[3D]-style phased multiply; returns (slab results, kept slabs or None, stats)."""
+    def summa_symbolic(self, sr, A: DeviceMatrix, B: DeviceMatrix):
+        """(products, outputs) this rank produces in the distributed product (exact; EstPerProcessNnzSUMMA's role)"""
+        f, z = C.c_int64(), C.c_int64()
+        self.ctx._check(self.ctx.lib.cbgpu_summa_symbolic(self.ctx.handle, self.handle, sr, A.handle, B.handle, C.byref(f), C.byref(z)))
+        return f.value, z.value
+
+    def summa_phased(self, sr, A: DeviceMatrix, B: DeviceMatrix, phases: int, want_checksum=False, keep=False, global_offsets=None):
+        """MemEfficientSpGEMM[3D]-style phased multiply; returns (slab results, kept slabs or None, stats).
+        global_offsets = (first global row of this rank's A/C block, first global column of its B block): the slab checksums
+        are then taken at their global positions and add up, over slabs and ranks, to the checksum of the whole product."""
         res = (SlabResult * phases)()
         st = DistStats()
         arr = (_P * phases)() if keep else None
-        self.ctx._check(self.ctx.lib.cbgpu_summa_phased(self.ctx.handle, self.handle, sr, A.handle, B.handle, phases,
-                                                        int(want_checksum), arr, res, C.byref(st)))
+        if global_offsets is not None:
+            self.ctx._check(self.ctx.lib.cbgpu_summa_phased_global(self.ctx.handle, self.handle, sr, A.handle, B.handle, phases,
+                                                                   int(global_offsets[0]), int(global_offsets[1]), arr, res, C.byref(st)))
+        else:
+            self.ctx._check(self.ctx.lib.cbgpu_summa_phased(self.ctx.handle, self.handle, sr, A.handle, B.handle, phases,
+                                                            int(want_checksum), arr, res, C.byref(st)))
         kept = [DeviceMatrix(self.ctx, _P(arr[i])) for i in range(phases)] if keep else None
         return list(res), kept, st
 

@@ -146,6 +146,12 @@ int cbgpu_mat_device_arrays(const cbgpu_mat *mat, const int64_t **jc, const int6
 int cbgpu_mat_free(cbgpu_ctx *ctx, cbgpu_mat *mat);
 /* order-independent 64-bit checksum of (row, col, value bits) over all entries; used for slab-wise parity */
 int cbgpu_mat_checksum(cbgpu_ctx *ctx, const cbgpu_mat *mat, uint64_t *pattern_sum, uint64_t *value_sum);
+/* the same sums with the block placed at (row_offset, col_offset) of a larger matrix: the checksums of the blocks of a
+ * distributed matrix, each taken at its global position, add up (mod 2^64) to the checksum of the whole matrix -- this is how
+ * a distributed product is compared with the single-GPU product and with the reference (SpParMat::operator==,
+ * SpParMat.cpp:2891, compares block by block on equal grids; the sum is grid independent). Global rows below 2^32. */
+int cbgpu_mat_checksum_at(cbgpu_ctx *ctx, const cbgpu_mat *mat, int64_t row_offset, int64_t col_offset, uint64_t *pattern_sum,
+                          uint64_t *value_sum);
 /* ColSplit / ColConcatenate of B and C slabs (dcsc.cpp:1202-1277, :1317-1360; SpDCCols.cpp:1054-1263) */
 int cbgpu_mat_colsplit(cbgpu_ctx *ctx, const cbgpu_mat *mat, int parts, cbgpu_mat **out /* parts */);
 int cbgpu_mat_colslice(cbgpu_ctx *ctx, const cbgpu_mat *mat, int64_t col_begin, int64_t col_end, cbgpu_mat **out);
@@ -260,6 +266,11 @@ int cbgpu_summa2d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
 int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B,
                   cbgpu_mat **C, cbgpu_dist_stats *stats);
 
+/* Distributed symbolic pass: products and outputs THIS rank produces in the distributed product (final distribution of C).
+ * replaces: EstPerProcessNnzSUMMA (ParFriends.h:1698) and the estimate loop of CalculateNumberOfPhases (:780-843); exact. */
+int cbgpu_summa_symbolic(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops,
+                         int64_t *nnz_out);
+
 /* Phased distributed multiply: replaces MemEfficientSpGEMM (ParFriends.h:453-777; without the pruning, which stays with
  * the caller) and MemEfficientSpGEMM3D (:3674-4170). B's local columns are cut into `phases` slabs (ColSplit rule), one
  * SUMMA per slab. With several layers the fiber exchange + merge of slab p overlaps the multiply of slab p+1 (second
@@ -271,6 +282,13 @@ typedef struct {
 } cbgpu_slab_result;
 int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                        int want_checksum, cbgpu_mat **slabs, cbgpu_slab_result *results, cbgpu_dist_stats *stats);
+/* the same with every slab's checksums taken at its GLOBAL position: row_offset = first global row of this rank's block of
+ * A / C, col_offset = first global column of this rank's block of B (before the cut into phases and, with layers, into the
+ * fiber's column sub-slabs, whose offsets the library adds). Summed over slabs and ranks they equal the checksums of the
+ * whole product on any grid. */
+int cbgpu_summa_phased_global(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                              int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs, cbgpu_slab_result *results,
+                              cbgpu_dist_stats *stats);
 
 /* ---------------------------------------------------------------- synthetic inputs (own seeded generators)
  * R-MAT (Graph500 initiator a,b,c,d as in 3DSpGEMM/mpipspgemm.cpp:126-133), duplicates summed into the value
@@ -281,6 +299,13 @@ int cbgpu_rmat_edges_host(int scale, int64_t nedges, uint64_t seed, double a, do
 /* value_mode: 0 = multiplicity of the edge (duplicates summed), 1 = one (duplicates collapsed), 2 = 1 + row id */
 int cbgpu_gen_rmat(cbgpu_ctx *ctx, int scale, int64_t nedges, uint64_t seed, double a, double b, double c,
                    int scramble, int dtype, int value_mode, cbgpu_mat **out);
+/* the block [row_begin,row_end) x [col_begin,col_end) of the same matrix with block-local indices, built without ever holding
+ * the whole matrix: every rank of a grid generates the edge stream and keeps what its block owns (what the reference does with
+ * DistEdgeList::GenGraph500Data + the SpParMat(DistEdgeList) all-to-all, DistEdgeList.cpp:223, SpParMat.cpp:3153; and for
+ * 3D blocks the SpParMat3D constructor, SpParMat3D.cpp:187-283) */
+int cbgpu_gen_rmat_block(cbgpu_ctx *ctx, int scale, int64_t nedges, uint64_t seed, double a, double b, double c, int scramble,
+                         int dtype, int value_mode, int64_t row_begin, int64_t row_end, int64_t col_begin, int64_t col_end,
+                         cbgpu_mat **out);
 
 #ifdef __cplusplus
 }

@@ -367,3 +367,65 @@ def mcl_prune_recovery_select(A: Csc, hard, select: int, recover: int, pct):
 def best_oracle():
     """The reference build when present (build container and, prebuilt, the GPU box), else the port."""
     return RefOracle() if RefOracle.available() else PortOracle()
+
+
+def rmat_edges(scale, nedges, seed, a=0.57, b=0.19, c=0.19, scramble=True):
+    """seeded R-MAT edge stream of the benchmark inputs on the host cores (oracle/spgemm_oracle.c port_rmat_edges: the same
+    arithmetic as the library's device generator, asserted equal in tests/test_oracle.py)"""
+    lib = C.CDLL(os.path.join(HERE, "libspgemm_oracle.so"))
+    lib.port_rmat_edges.argtypes = [C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    rows = np.empty(nedges, np.int64)
+    cols = np.empty(nedges, np.int64)
+    if lib.port_rmat_edges(scale, nedges, seed, a, b, c, int(scramble), rows.ctypes.data, cols.ctypes.data) != 0:
+        raise RuntimeError("port_rmat_edges failed")
+    return rows, cols
+
+
+def rmat_csc(scale, edgefactor, seed, a=0.57, b=0.19, c=0.19, scramble=True):
+    """the benchmark's R-MAT as Csc: duplicates summed into the value (SpTuples.cpp:70-124 semantics), rows ascending"""
+    rows, cols = rmat_edges(scale, edgefactor << scale, seed, a, b, c, scramble)
+    n = 1 << scale
+    key = cols * n + rows  # column-major order
+    del rows, cols
+    key.sort()
+    uniq, counts = np.unique(key, return_counts=True)
+    del key
+    ucols = uniq // n
+    urows = uniq - ucols * n
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(ucols, minlength=n), out=colptr[1:])
+    return Csc(n, n, colptr, np.ascontiguousarray(urows), counts.astype(np.float64))
+
+
+# ------------------------------------------------------------------------------------------------ checksums
+# numpy restatement of cbgpu_mat_checksum_at (combblas_b200/csrc/api.cu): order-independent sums over the entries of a matrix
+# placed at (row_offset, col_offset). Used by the checkers to compare column slabs of products that are too large to keep.
+def _mix64(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64, copy=True)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xff51afd7ed558ccd)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xc4ceb9fe1a85ec53)
+    x ^= x >> np.uint64(33)
+    return x
+
+
+def matrix_checksum(rows, cols, vals, row_offset=0, col_offset=0):
+    """(pattern_sum, value_sum) as the device computes them; vals is a float64 / int64 / ... array (bit pattern hashed)."""
+    with np.errstate(over="ignore"):
+        r = (np.asarray(rows, dtype=np.int64) + row_offset).astype(np.uint64) & np.uint64(0xFFFFFFFF)
+        c = (np.asarray(cols, dtype=np.int64) + col_offset).astype(np.uint64)
+        key = (c << np.uint64(32)) ^ r
+        h = _mix64(key + np.uint64(0x9E3779B97F4A7C15))
+        v = np.ascontiguousarray(vals)
+        nb = v.dtype.itemsize
+        if nb == 8:
+            vb = v.view(np.uint64).copy()
+            vb[vb == np.uint64(0x8000000000000000)] = 0
+        elif nb == 4:
+            vb = v.view(np.uint32).astype(np.uint64)
+            vb[vb == np.uint64(0x80000000)] = 0
+        else:
+            vb = v.view(np.uint8).astype(np.uint64)
+        vs = _mix64(h ^ _mix64(vb + np.uint64(0x632BE59BD9B4E019)))
+        return int(h.sum(dtype=np.uint64)), int(vs.sum(dtype=np.uint64))

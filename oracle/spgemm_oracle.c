@@ -329,3 +329,50 @@ void port_set_num_threads(int n) {
   (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Seeded R-MAT edge stream of the benchmark inputs, on the host cores (threaded). Same integer arithmetic as the
+ * library's device generator (combblas_b200/csrc/gen.cu: splitmix64 per level, thresholds scaled to 2^53, seeded
+ * bijective vertex scramble); tests assert that both produce identical edges. The checkers and the reference arm of
+ * bench.py build their matrices from this copy, so that they never touch the product library.
+ * The reference's counterpart is DistEdgeList::GenGraph500Data (DistEdgeList.cpp:223-279). */
+static inline uint64_t gen_splitmix64(uint64_t *s) {
+  *s += 0x9E3779B97F4A7C15ULL;
+  uint64_t z = *s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+int port_rmat_edges(int scale, int64_t nedges, uint64_t seed, double a, double b, double c, int scramble, int64_t *rows,
+                    int64_t *cols) {
+  if (scale < 1 || scale > 31 || nedges < 0 || !rows || !cols) return -1;
+  const double two53 = 9007199254740992.0;
+  const uint64_t ta = (uint64_t)(a * two53), tab = (uint64_t)((a + b) * two53), tabc = (uint64_t)((a + b + c) * two53);
+  const uint64_t mask = (1ULL << scale) - 1;
+  uint64_t ss = seed ^ 0xD1B54A32D192ED03ULL;
+  const uint64_t m1 = gen_splitmix64(&ss) | 1ULL, c1 = gen_splitmix64(&ss), m2 = gen_splitmix64(&ss) | 1ULL;
+  const int sh = scale / 2 > 0 ? scale / 2 : 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < nedges; ++e) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ULL + (uint64_t)e * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL;
+    uint64_t r = 0, cc = 0;
+    for (int l = 0; l < scale; ++l) {
+      const uint64_t u = gen_splitmix64(&s) >> 11;
+      int rb, cb;
+      if (u < ta) { rb = 0; cb = 0; }
+      else if (u < tab) { rb = 0; cb = 1; }
+      else if (u < tabc) { rb = 1; cb = 0; }
+      else { rb = 1; cb = 1; }
+      r = (r << 1) | (uint64_t)rb;
+      cc = (cc << 1) | (uint64_t)cb;
+    }
+    if (scramble) {
+      r = (r * m1 + c1) & mask; r ^= r >> sh; r = (r * m2) & mask;
+      cc = (cc * m1 + c1) & mask; cc ^= cc >> sh; cc = (cc * m2) & mask;
+    }
+    rows[e] = (int64_t)r;
+    cols[e] = (int64_t)cc;
+  }
+  return 0;
+}

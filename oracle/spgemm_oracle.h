@@ -40,6 +40,9 @@ int64_t port_result_nnz(const port_result *r);
 void port_result_copy(const port_result *r, int64_t *rows, int64_t *cols, void *vals);
 void port_result_free(port_result *r);
 int port_num_threads(void);
+/* seeded R-MAT edge stream of the benchmark inputs (same arithmetic as the library's generator), threaded */
+int port_rmat_edges(int scale, int64_t nedges, uint64_t seed, double a, double b, double c, int scramble, int64_t *rows,
+                    int64_t *cols);
 void port_set_num_threads(int n);
 
 #ifdef __cplusplus

@@ -19,9 +19,8 @@ from oracle.oracle import Csc, SR_DTYPES, PortOracle  # noqa: E402
 from tests.util import assert_same, rmat, typed  # noqa: E402
 
 
-# the fiber-fused 3D variant (dist.cu, option fiber_fused) was written when no multi-GPU time was left to validate it:
-# its checks run only on request until it has passed once on 2 and 8 GPUs
-CHECK_FIBER_FUSED = os.environ.get("CBGPU_TEST_FIBER_FUSED", "0") == "1"
+# 3D products run in two formulations that must agree: inputs replicated along the fiber (option fiber_fused = 1, the
+# default) and the reference's reduction of partial results along the fiber (fiber_fused = 0, ParFriends.h:3578-3642)
 
 
 def main():
@@ -60,10 +59,10 @@ def main():
             ctx.set_option("summa_fused", 1)
             assert ctx.checksum(dC2)[0] == ctx.checksum(dC)[0] and dC2.nnz == dC.nnz, "fused and staged SUMMA differ"
             dC2.free()
-        if layers > 1 and CHECK_FIBER_FUSED:  # inputs replicated along the fiber must give the block the fiber reduction gives
-            ctx.set_option("fiber_fused", 1)
-            dC3, _ = comm.summa3d(sr, dA, dB)
+        if layers > 1:  # the reference's fiber reduction must give the block the fiber-fused default gives
             ctx.set_option("fiber_fused", 0)
+            dC3, _ = comm.summa3d(sr, dA, dB)
+            ctx.set_option("fiber_fused", 1)
             same3 = dC3.nnz == dC.nnz and ctx.checksum(dC3)[0] == ctx.checksum(dC)[0]
             if sr not in (0, 1, 6):  # bit-exact semirings: the values too
                 same3 = same3 and ctx.checksum(dC3) == ctx.checksum(dC)
@@ -160,11 +159,32 @@ def main():
         same = same and r.nnz == pc.nnz and r.pattern_sum == ctx.checksum(pc)[0] and ctx.checksum(kp) == ctx.checksum(pc)
     res2, _, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=False)
     same = same and [(r.nnz, r.pattern_sum) for r in res2] == [(r.nnz, r.pattern_sum) for r in res]
-    if layers > 1 and CHECK_FIBER_FUSED:  # the fiber-fused phased driver produces the same slabs
-        ctx.set_option("fiber_fused", 1)
-        res3, _, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=False)
+    if layers > 1:  # the fiber-reducing phased driver (sequential and pipelined) produces the same slabs
         ctx.set_option("fiber_fused", 0)
+        res3, _, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=False)
+        ctx.set_option("fiber_pipeline", 1)
+        res4, _, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=False)
+        ctx.set_option("fiber_pipeline", 0)
+        ctx.set_option("fiber_fused", 1)
         same = same and [(r.nnz, r.pattern_sum) for r in res3] == [(r.nnz, r.pattern_sum) for r in res]
+        same = same and [(r.nnz, r.pattern_sum) for r in res4] == [(r.nnz, r.pattern_sum) for r in res]
+    # global-position checksums of the phased driver add up to the checksum of the whole product (what bench.py reports)
+    from oracle.oracle import matrix_checksum  # noqa: E402
+    want_all = orc.spgemm(Csc.from_scipy(G, np.float64), Csc.from_scipy(G, np.float64), 0)
+    want_sum = matrix_checksum(want_all.rows, want_all.cols_expanded(), want_all.vals)
+    ra, _, _, _ = local_range(grid, n, n, True)
+    _, _, cb0, _ = local_range(grid, n, n, False)
+    resg, _, _ = comm.summa_phased(0, dA, dB, 3, global_offsets=(ra, cb0))
+    M64 = (1 << 64) - 1
+    ps_, vs_ = sum(r.pattern_sum for r in resg) & M64, sum(r.value_sum for r in resg) & M64
+    # the 64-bit words travel as 32-bit halves (no signed overflow in the tensors) and are added modulo 2^64 on the host
+    mine = torch.tensor([ps_ & 0xFFFFFFFF, ps_ >> 32, vs_ & 0xFFFFFFFF, vs_ >> 32, sum(r.nnz for r in resg)], dtype=torch.int64, device="cuda")
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    tot_p = sum(int(v[0].item()) + (int(v[1].item()) << 32) for v in allv) & M64
+    tot_v = sum(int(v[2].item()) + (int(v[3].item()) << 32) for v in allv) & M64
+    tot_n = sum(int(v[4].item()) for v in allv)
+    same = same and tot_n == want_all.nnz and tot_p == want_sum[0] and tot_v == want_sum[1]
     t = torch.tensor([0 if same else 1], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
