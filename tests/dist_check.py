@@ -98,7 +98,7 @@ def main():
     if layers == 1:
         import scipy.sparse as sp
 
-        k3 = 24
+        k3 = 128 if os.environ.get("CBGPU_GALERKIN_FULL", "0") == "1" else 24  # 128: BASELINE config 3 at full size
         n = k3 ** 3
         I = sp.identity(k3, format="csc")
         D1 = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(k3, k3), format="csc")
