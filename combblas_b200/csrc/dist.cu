@@ -397,7 +397,8 @@ static int summa_layer(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
 
 // The fiber stage of the 3D algorithm (ParFriends.h:3578-3642): cut this layer's partial product Cl (consumed) into L
 // column slabs, ship slab l to fiber rank l, merge what arrives with the own slab. Runs entirely on ctx's stream.
-static int fiber_reduce(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cbgpu_mat *Cl, cbgpu_mat **C, cbgpu_dist_stats *ds) {
+static int fiber_reduce(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cbgpu_mat *Cl, cbgpu_mat **C, cbgpu_dist_stats *ds,
+                        const int64_t *widths = nullptr) {
   const cbgpu_grid &g = comm->grid;
   const int L = g.layers;
   Timer tm(ctx->stream);
@@ -406,9 +407,16 @@ static int fiber_reduce(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cbgpu_ma
   //      send ranges ParFriends->h:3578-3600); slab l belongs to fiber rank l
   tm.start();
   std::vector<cbgpu_mat *> slab(L, nullptr), recv(L, nullptr);
+  int64_t cut = 0;
   for (int l = 0; l < L && rc == CBGPU_OK; ++l) {
     int64_t c0, c1;
-    cbgpu_block_range(Cl->n, L, l, &c0, &c1);
+    if (widths) {
+      c0 = cut;
+      c1 = cut + widths[l];
+      cut = c1;
+    } else {
+      cbgpu_block_range(Cl->n, L, l, &c0, &c1);
+    }
     rc = mat_colslice(ctx, Cl, c0, c1, &slab[l]);
   }
   mat_release(ctx, Cl);
@@ -507,54 +515,60 @@ static int fiber_reduce(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cbgpu_ma
 // local multiply. Same operand distribution (A column-split, B row-split across layers), same products, same output
 // distribution (C column-split across layers) as Mult_AnXBn_SUMMA3D; nothing is merged.
 
-// slab[p] goes to fiber rank p, recv[p] arrives from fiber rank p (p != my layer); shapes by one all-gather
-static int fiber_exchange_slabs(cbgpu_ctx *ctx, cbgpu_comm *comm, std::vector<cbgpu_mat *> &slab, std::vector<cbgpu_mat *> &recv,
-                                int64_t *bytes) {
-  const int L = comm->grid.layers, me = comm->grid.my_layer;
+// All-to-all of DCSC blocks along communicator c (nranks ranks, this rank is `me`): slab[p] goes to rank p, recv[p] arrives
+// from rank p (p != me). Essentials {nnz, nzc, m, n} by one all-gather, then grouped send/recv of the four arrays
+// (the device-to-device counterpart of the tuple Alltoallv of ParFriends.h:3612 and SpParMat3D.cpp:51-97).
+static int exchange_blocks(cbgpu_ctx *ctx, ncclComm_t c, int nranks, int me, std::vector<cbgpu_mat *> &slab,
+                           std::vector<cbgpu_mat *> &recv, int64_t *bytes) {
+  const int L = nranks;
   const int dt = slab[me]->dtype;
   const size_t vb = dtype_size(dt);
-  std::vector<int64_t> mine((size_t)3 * L), sizes((size_t)3 * L * L, 0);
+  std::vector<int64_t> mine((size_t)4 * L), sizes((size_t)4 * L * L, 0);
   for (int l = 0; l < L; ++l) {
-    mine[3 * l] = slab[l]->nnz;
-    mine[3 * l + 1] = slab[l]->nzc;
-    mine[3 * l + 2] = slab[l]->m;
+    mine[4 * l] = slab[l]->nnz;
+    mine[4 * l + 1] = slab[l]->nzc;
+    mine[4 * l + 2] = slab[l]->m;
+    mine[4 * l + 3] = slab[l]->n;
   }
   int64_t *d = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &d, (size_t)3 * L * (L + 1)));
-  CB_CUDA(ctx, cudaMemcpyAsync(d, mine.data(), sizeof(int64_t) * 3 * L, cudaMemcpyHostToDevice, ctx->stream));
-  CB_NCCL(ctx, nccl().AllGather(d, d + 3 * L, (size_t)3 * L, ncclInt64, comm->fiber, ctx->stream));
-  CB_CUDA(ctx, cudaMemcpyAsync(sizes.data(), d + 3 * L, sizeof(int64_t) * 3 * L * L, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_TRY(dev_alloc_t(ctx, &d, (size_t)4 * L * (L + 1)));
+  CB_CUDA(ctx, cudaMemcpyAsync(d, mine.data(), sizeof(int64_t) * 4 * L, cudaMemcpyHostToDevice, ctx->stream));
+  CB_NCCL(ctx, nccl().AllGather(d, d + 4 * L, (size_t)4 * L, ncclInt64, c, ctx->stream));
+  CB_CUDA(ctx, cudaMemcpyAsync(sizes.data(), d + 4 * L, sizeof(int64_t) * 4 * L * L, cudaMemcpyDeviceToHost, ctx->stream));
   CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   CB_TRY(dev_free(ctx, d));
   for (int p = 0; p < L; ++p) {
     if (p == me) continue;
-    const int64_t nnz = sizes[(size_t)3 * L * p + 3 * me], nzc = sizes[(size_t)3 * L * p + 3 * me + 1];
-    const int64_t m = sizes[(size_t)3 * L * p + 3 * me + 2];
-    CB_TRY(mat_alloc(ctx, m, slab[me]->n, nnz, nzc, dt, &recv[p]));
-    if (nnz == 0) CB_CUDA(ctx, cudaMemsetAsync(recv[p]->cp, 0, 8, ctx->stream));
+    const int64_t *e = &sizes[(size_t)4 * L * p + 4 * me];
+    CB_TRY(mat_alloc(ctx, e[2], e[3], e[0], e[1], dt, &recv[p]));
+    if (e[0] == 0) CB_CUDA(ctx, cudaMemsetAsync(recv[p]->cp, 0, 8, ctx->stream));
   }
   ncclResult_t r = nccl().GroupStart();
   for (int p = 0; p < L && r == ncclSuccess; ++p) {
     if (p == me) continue;
     cbgpu_mat *S = slab[p], *R = recv[p];
     if (S->nnz > 0) {
-      r = nccl().Send(S->jc, (size_t)S->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-      if (r == ncclSuccess) r = nccl().Send(S->cp, (size_t)(S->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-      if (r == ncclSuccess) r = nccl().Send(S->ir, (size_t)S->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
-      if (r == ncclSuccess) r = nccl().Send(S->numx, (size_t)S->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+      r = nccl().Send(S->jc, (size_t)S->nzc * 8, nccl_bytes(), p, c, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Send(S->cp, (size_t)(S->nzc + 1) * 8, nccl_bytes(), p, c, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Send(S->ir, (size_t)S->nnz * 4, nccl_bytes(), p, c, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Send(S->numx, (size_t)S->nnz * vb, nccl_bytes(), p, c, ctx->stream);
       *bytes += S->nzc * 16 + 8 + S->nnz * (4 + (int64_t)vb);
     }
     if (r == ncclSuccess && R->nnz > 0) {
-      r = nccl().Recv(R->jc, (size_t)R->nzc * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-      if (r == ncclSuccess) r = nccl().Recv(R->cp, (size_t)(R->nzc + 1) * 8, nccl_bytes(), p, comm->fiber, ctx->stream);
-      if (r == ncclSuccess) r = nccl().Recv(R->ir, (size_t)R->nnz * 4, nccl_bytes(), p, comm->fiber, ctx->stream);
-      if (r == ncclSuccess) r = nccl().Recv(R->numx, (size_t)R->nnz * vb, nccl_bytes(), p, comm->fiber, ctx->stream);
+      r = nccl().Recv(R->jc, (size_t)R->nzc * 8, nccl_bytes(), p, c, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Recv(R->cp, (size_t)(R->nzc + 1) * 8, nccl_bytes(), p, c, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Recv(R->ir, (size_t)R->nnz * 4, nccl_bytes(), p, c, ctx->stream);
+      if (r == ncclSuccess) r = nccl().Recv(R->numx, (size_t)R->nnz * vb, nccl_bytes(), p, c, ctx->stream);
     }
   }
   ncclResult_t r2 = nccl().GroupEnd();
   if (r != ncclSuccess || r2 != ncclSuccess)
-    return set_error(ctx, CBGPU_ERR_NCCL, "fiber exchange failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
+    return set_error(ctx, CBGPU_ERR_NCCL, "block exchange failed: %s", nccl().GetErrorString(r != ncclSuccess ? r : r2));
   return CBGPU_OK;
+}
+static int fiber_exchange_slabs(cbgpu_ctx *ctx, cbgpu_comm *comm, std::vector<cbgpu_mat *> &slab, std::vector<cbgpu_mat *> &recv,
+                                int64_t *bytes) {
+  return exchange_blocks(ctx, comm->fiber, comm->grid.layers, comm->grid.my_layer, slab, recv, bytes);
 }
 
 // all blocks of `own` along communicator `c` (nranks ranks, this rank is `me`), in rank order; blk[me] == own
@@ -606,7 +620,8 @@ static int gather_A_all_layers(cbgpu_ctx *ctx, cbgpu_comm *comm, const cbgpu_mat
 
 // one column slab Bslab of this rank's B block -> this rank's final piece of C for that slab
 static int fiber_fused_slab(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *Aall, const cbgpu_mat *Bslab,
-                            cbgpu_mat **C, cbgpu_dist_stats *ds, int64_t *sym_flops = nullptr, int64_t *sym_nnz = nullptr) {
+                            cbgpu_mat **C, cbgpu_dist_stats *ds, int64_t *sym_flops = nullptr, int64_t *sym_nnz = nullptr,
+                            const int64_t *widths = nullptr /* columns of the slab that belong to fiber rank l; null: even cut */) {
   const cbgpu_grid &g = comm->grid;
   const int L = g.layers;
   Timer tm(ctx->stream);
@@ -627,9 +642,16 @@ static int fiber_fused_slab(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, cons
   // column sub-slab l' of it goes to fiber rank l' (the split fiber_reduce applies to C: SpParMat3D.cpp:576-609)
   std::vector<cbgpu_mat *> slab(L, nullptr), recv(L, nullptr), parts(L, nullptr);
   tm.start();
+  int64_t cut = 0;
   for (int l = 0; l < L && rc == CBGPU_OK; ++l) {
     int64_t c0, c1;
-    cbgpu_block_range(mine->n, L, l, &c0, &c1);
+    if (widths) {
+      c0 = cut;
+      c1 = cut + widths[l];
+      cut = c1;
+    } else {
+      cbgpu_block_range(mine->n, L, l, &c0, &c1);
+    }
     rc = mat_colslice(ctx, mine, c0, c1, &slab[l]);
   }
   if (rc == CBGPU_OK) rc = fiber_exchange_slabs(ctx, comm, slab, recv, &ds->bytes_fiber);
@@ -722,15 +744,78 @@ int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
   return rc;
 }
 
-// Phased distributed multiply (MemEfficientSpGEMM ParFriends.h:453-777, MemEfficientSpGEMM3D :3674-4170): B's local columns
-// are cut into `phases` slabs (ColSplit rule) and one SUMMA runs per slab, so that C never has to exist as a whole.
+// Phased distributed multiply (MemEfficientSpGEMM ParFriends.h:453-777, MemEfficientSpGEMM3D :3674-4170): one SUMMA per
+// column slab of B, so that C never has to exist as a whole.
+//   one layer : slab p = ColSplit part p of B's local columns (dcsc.cpp:1202).
+//   L layers  : the reference's plan (ParFriends.h:3774-3811): B's local columns are first cut into the L chunks the fiber
+//               owns in C (CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576-609), every chunk into `phases` pieces,
+//               and phase p takes piece p of EVERY chunk -- each fiber rank gets work in every phase, and the pieces a rank
+//               produces over the phases concatenate to exactly its chunk: the layout of the unphased Mult_AnXBn_SUMMA3D.
 // With several layers the default is the fiber-fused formulation (inputs replicated along the fiber, nothing merged). With
 // fiber_fused = 0 the reference's fiber reduction runs after each slab; option fiber_pipeline = 1 overlaps the reduction of
 // slab p with the multiply of slab p+1 on a second host thread, context and stream (two NCCL communicators are then in
 // use concurrently from two threads: opt-in).
+struct PhasePlan {
+  int phases = 1, L = 1;
+  std::vector<int64_t> c0, c1; // [p * L + l]: columns of B's block in piece p of the chunk of fiber rank l
+  int64_t begin(int p, int l) const { return c0[(size_t)p * L + l]; }
+  int64_t width(int p, int l) const { return c1[(size_t)p * L + l] - c0[(size_t)p * L + l]; }
+};
+static PhasePlan make_phase_plan(int64_t n, int phases, int L) {
+  PhasePlan pl;
+  pl.phases = phases;
+  pl.L = L;
+  pl.c0.assign((size_t)phases * L, 0);
+  pl.c1.assign((size_t)phases * L, 0);
+  for (int l = 0; l < L; ++l) {
+    int64_t k0, k1;
+    cbgpu_block_range(n, L, l, &k0, &k1);
+    for (int p = 0; p < phases; ++p) {
+      int64_t a, b;
+      cbgpu_block_range(k1 - k0, phases, p, &a, &b);
+      pl.c0[(size_t)p * L + l] = k0 + a;
+      pl.c1[(size_t)p * L + l] = k0 + b;
+    }
+  }
+  return pl;
+}
+// the columns of B that phase p multiplies: piece p of every chunk, side by side. owned: the caller releases it
+static int cut_phase_slab(cbgpu_ctx *ctx, const cbgpu_mat *B, const PhasePlan &pl, int p, cbgpu_mat **out, bool *owned) {
+  if (pl.phases == 1 && pl.L == 1) {
+    *out = const_cast<cbgpu_mat *>(B);
+    *owned = false;
+    return CBGPU_OK;
+  }
+  *owned = true;
+  if (pl.L == 1) return mat_colslice(ctx, B, pl.begin(p, 0), pl.begin(p, 0) + pl.width(p, 0), out);
+  std::vector<cbgpu_mat *> parts(pl.L, nullptr);
+  int rc = CBGPU_OK;
+  for (int l = 0; l < pl.L && rc == CBGPU_OK; ++l) rc = mat_colslice(ctx, B, pl.begin(p, l), pl.begin(p, l) + pl.width(p, l), &parts[l]);
+  if (rc == CBGPU_OK) rc = mat_colconcat(ctx, pl.L, parts.data(), out);
+  for (cbgpu_mat *m : parts) mat_release(ctx, m);
+  return rc;
+}
+
+} // extern "C" (plan helpers above have C++ linkage on purpose)
+extern "C" int cbgpu_phase_columns(int64_t n, int phases, int layers, int phase, int layer, int64_t *begin, int64_t *end) {
+  if (n < 0 || phases < 1 || layers < 1 || phase < 0 || phase >= phases || layer < 0 || layer >= layers || !begin || !end)
+    return CBGPU_ERR_INVALID;
+  const PhasePlan pl = make_phase_plan(n, phases, layers);
+  *begin = pl.begin(phase, layer);
+  *end = *begin + pl.width(phase, layer);
+  return CBGPU_OK;
+}
+extern "C" {
+
+// what happens to a finished piece of C before it is reported / kept (the pruning of MemEfficientSpGEMM, ParFriends.h:744)
+struct SlabEpilogue {
+  virtual int apply(cbgpu_ctx *c, int p, cbgpu_mat **Cp) = 0;
+  virtual ~SlabEpilogue() {}
+};
+
 static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                              int want_checksum, bool global, int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs,
-                             cbgpu_slab_result *results, cbgpu_dist_stats *stats);
+                             cbgpu_slab_result *results, cbgpu_dist_stats *stats, SlabEpilogue *epilogue = nullptr);
 
 int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                        int want_checksum, cbgpu_mat **slabs, cbgpu_slab_result *results, cbgpu_dist_stats *stats) {
@@ -745,51 +830,65 @@ int cbgpu_summa_phased_global(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, co
 
 static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                              int want_checksum, bool global, int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs,
-                             cbgpu_slab_result *results, cbgpu_dist_stats *stats) {
+                             cbgpu_slab_result *results, cbgpu_dist_stats *stats, SlabEpilogue *epilogue) {
   if (!ctx || !comm || !A || !B || phases < 1 || !results) return CBGPU_ERR_INVALID;
   CB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int L = comm->grid.layers;
-  // global position of the piece of C this rank ends up with for slab p: the slab's columns inside B's block (ColSplit rule,
-  // dcsc.cpp:1202), then with layers the fiber's sub-slab of that slab (CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576)
+  const int L = comm->grid.layers, me = comm->grid.my_layer;
+  const PhasePlan plan = make_phase_plan(B->n, phases, L);
+  // the piece of C this rank ends up with in phase p covers the columns [plan.begin(p, me), + plan.width(p, me)) of B's block
   auto slab_checksum = [&](cbgpu_ctx *c, int p, const cbgpu_mat *Cp, cbgpu_slab_result *r) -> int {
     if (!global) return cbgpu_mat_checksum(c, Cp, &r->pattern_sum, &r->value_sum);
-    const int64_t per = B->n / phases, s0 = per * p, s1 = (p == phases - 1) ? B->n : per * (p + 1);
-    int64_t sub0 = 0, sub1 = 0;
-    if (L > 1) cbgpu_block_range(s1 - s0, L, comm->grid.my_layer, &sub0, &sub1);
-    return cbgpu_mat_checksum_at(c, Cp, row_offset, col_offset + s0 + sub0, &r->pattern_sum, &r->value_sum);
+    return cbgpu_mat_checksum_at(c, Cp, row_offset, col_offset + plan.begin(p, me), &r->pattern_sum, &r->value_sum);
+  };
+  auto finish_slab = [&](cbgpu_ctx *c, int p, cbgpu_mat *Cp) -> int {
+    int rc = CBGPU_OK;
+    if (epilogue) rc = epilogue->apply(c, p, &Cp);
+    if (rc != CBGPU_OK) {
+      mat_release(c, Cp);
+      return rc;
+    }
+    results[p].nnz = Cp->nnz;
+    results[p].nzc = Cp->nzc;
+    results[p].pattern_sum = results[p].value_sum = 0;
+    if (want_checksum) rc = slab_checksum(c, p, Cp, &results[p]);
+    if (slabs) slabs[p] = Cp;
+    else mat_release(c, Cp);
+    return rc;
   };
   cbgpu_dist_stats ds;
   memset(&ds, 0, sizeof(ds));
   Timer all(ctx->stream);
   all.start();
-  std::vector<cbgpu_mat *> Bs(phases, nullptr);
-  if (phases == 1) Bs[0] = const_cast<cbgpu_mat *>(B);
-  else CB_TRY(cbgpu_mat_colsplit(ctx, B, phases, Bs.data()));
+  std::vector<int64_t> widths(L, 0);
   const bool fiber_fused = L > 1 && ctx->opt.fiber_fused;
-  if (fiber_fused) {
-    // inputs replicated along the fiber instead of partial results reduced along it: A's side is gathered once for all
-    // phases, every phase exchanges its (small) slab of B and multiplies; no second thread, nothing to merge
+  if (fiber_fused || L == 1) {
+    // L > 1: inputs replicated along the fiber instead of partial results reduced along it: A's side is gathered once for
+    // all phases, every phase exchanges its (small) slab of B and multiplies; one host thread, nothing to merge
     cbgpu_mat *Aall = nullptr;
-    int rcf = gather_A_all_layers(ctx, comm, A, &Aall, &ds);
-    for (int p = 0; p < phases && rcf == CBGPU_OK; ++p) {
-      cbgpu_mat *Cp = nullptr;
-      rcf = fiber_fused_slab(ctx, comm, semiring, Aall, Bs[p], &Cp, &ds);
-      if (rcf != CBGPU_OK) break;
-      results[p].nnz = Cp->nnz;
-      results[p].nzc = Cp->nzc;
-      results[p].pattern_sum = results[p].value_sum = 0;
-      if (want_checksum) rcf = slab_checksum(ctx, p, Cp, &results[p]);
-      if (slabs) slabs[p] = Cp;
-      else mat_release(ctx, Cp);
+    int rc = CBGPU_OK;
+    if (L > 1) rc = gather_A_all_layers(ctx, comm, A, &Aall, &ds);
+    for (int p = 0; p < phases && rc == CBGPU_OK; ++p) {
+      cbgpu_mat *Bs = nullptr, *Cp = nullptr;
+      bool owned = false;
+      rc = cut_phase_slab(ctx, B, plan, p, &Bs, &owned);
+      if (rc == CBGPU_OK) {
+        if (L > 1) {
+          for (int l = 0; l < L; ++l) widths[l] = plan.width(p, l);
+          rc = fiber_fused_slab(ctx, comm, semiring, Aall, Bs, &Cp, &ds, nullptr, nullptr, widths.data());
+        } else {
+          rc = summa_layer(ctx, comm, semiring, A, Bs, &Cp, &ds);
+        }
+      }
+      if (owned) mat_release(ctx, Bs);
+      if (rc == CBGPU_OK) rc = finish_slab(ctx, p, Cp);
     }
     mat_release(ctx, Aall);
-    if (phases > 1)
-      for (int p = 0; p < phases; ++p) mat_release(ctx, Bs[p]);
     ds.ms_total = all.stop();
     if (stats) *stats = ds;
-    return rcf;
+    return rc;
   }
-  const bool pipelined = L > 1 && ctx->opt.fiber_pipeline != 0;
+  // ---- the reference's formulation: per-layer SUMMA of the slab, then the fiber reduction of the partial result
+  const bool pipelined = ctx->opt.fiber_pipeline != 0;
   if (pipelined && !comm->ctx2) {
     int rc2 = cbgpu_create(ctx->device, nullptr, &comm->ctx2);
     if (rc2 != CBGPU_OK) return set_error(ctx, rc2, "could not create the second context of the pipeline");
@@ -804,21 +903,12 @@ static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, con
   int worker_rc = CBGPU_OK;
   cbgpu_dist_stats wds;
   memset(&wds, 0, sizeof(wds));
-  auto finish_slab = [&](cbgpu_ctx *c, int p, cbgpu_mat *Cp) -> int {
-    results[p].nnz = Cp->nnz;
-    results[p].nzc = Cp->nzc;
-    results[p].pattern_sum = results[p].value_sum = 0;
-    int rc = CBGPU_OK;
-    if (want_checksum) rc = slab_checksum(c, p, Cp, &results[p]);
-    if (slabs) slabs[p] = Cp;
-    else mat_release(c, Cp);
-    return rc;
-  };
   std::thread worker;
   if (pipelined) {
     worker = std::thread([&]() {
       cbgpu_ctx *c2 = comm->ctx2;
       cudaSetDevice(c2->device);
+      std::vector<int64_t> w2(L, 0);
       for (int p = 0; p < phases; ++p) {
         Item it;
         {
@@ -829,7 +919,8 @@ static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, con
         }
         cudaStreamWaitEvent(c2->stream, it.ready, 0);
         cbgpu_mat *Cp = nullptr;
-        int rc = fiber_reduce(c2, comm, semiring, it.Cl, &Cp, &wds);
+        for (int l = 0; l < L; ++l) w2[l] = plan.width(p, l);
+        int rc = fiber_reduce(c2, comm, semiring, it.Cl, &Cp, &wds, w2.data());
         if (rc == CBGPU_OK) rc = finish_slab(c2, p, Cp);
         cudaStreamSynchronize(c2->stream);
         cudaEventDestroy(it.ready);
@@ -845,16 +936,16 @@ static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, con
   }
   int rc = CBGPU_OK;
   for (int p = 0; p < phases && rc == CBGPU_OK; ++p) {
-    cbgpu_mat *Cl = nullptr;
-    rc = summa_layer(ctx, comm, semiring, A, Bs[p], &Cl, &ds);
+    cbgpu_mat *Bs = nullptr, *Cl = nullptr;
+    bool owned = false;
+    rc = cut_phase_slab(ctx, B, plan, p, &Bs, &owned);
+    if (rc == CBGPU_OK) rc = summa_layer(ctx, comm, semiring, A, Bs, &Cl, &ds);
+    if (owned) mat_release(ctx, Bs);
     if (rc != CBGPU_OK) break;
-    if (L == 1) {
-      rc = finish_slab(ctx, p, Cl);
-      continue;
-    }
     if (!pipelined) { // one host thread, one stream: the fiber reduction of slab p runs before the multiply of slab p + 1
       cbgpu_mat *Cp = nullptr;
-      rc = fiber_reduce(ctx, comm, semiring, Cl, &Cp, &ds);
+      for (int l = 0; l < L; ++l) widths[l] = plan.width(p, l);
+      rc = fiber_reduce(ctx, comm, semiring, Cl, &Cp, &ds, widths.data());
       if (rc == CBGPU_OK) rc = finish_slab(ctx, p, Cp);
       continue;
     }
@@ -886,10 +977,160 @@ static int summa_phased_impl(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, con
     ds.local.kernel_launches += wds.local.kernel_launches + comm->ctx2->launches;
     comm->ctx2->launches = 0;
   }
-  if (phases > 1)
-    for (int p = 0; p < phases; ++p) mat_release(ctx, Bs[p]);
   ds.ms_total = all.stop();
   if (stats) *stats = ds;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- distributed MCL pruning
+// MCLPruneRecoverySelect (ParFriends.h:186-354) decides column by column; on a grid a column of C is spread over the ranks
+// of a process column (same grid column and layer), which the reference handles with column reductions and a distributed
+// Kselect1 (SpParMat.cpp:1413-1700, reductions :1575-1660). Here the piece is re-cut along the process column instead: the
+// local columns are dealt out evenly, every rank receives the row blocks of ITS columns from its peers (device-to-device
+// all-to-all over NVLink), stacks them into whole columns, runs the single-GPU pruning kernels on them (csrc/prune.cu), and
+// the survivors travel back to the row blocks they came from. Same per-column decisions as the reference (they depend on
+// the whole column only); only the pruned entries make the return trip.
+static int prune_distributed(cbgpu_ctx *ctx, cbgpu_comm *comm, cbgpu_mat *piece, double hardThreshold, int64_t selectNum,
+                             int64_t recoverNum, double recoverPct, cbgpu_mat **out, cbgpu_prune_stats *pst, int64_t *bytes) {
+  const cbgpu_grid &g = comm->grid;
+  const int P = g.grid_rows, me = g.my_row;
+  if (P == 1) return cbgpu_mcl_prune(ctx, piece, hardThreshold, selectNum, recoverNum, recoverPct, out, pst);
+  int rc = CBGPU_OK;
+  std::vector<cbgpu_mat *> send(P, nullptr), recv(P, nullptr), parts(P, nullptr);
+  // forward: column range q of my piece goes to the rank in grid row q
+  for (int q = 0; q < P && rc == CBGPU_OK; ++q) {
+    int64_t c0, c1;
+    cbgpu_block_range(piece->n, P, q, &c0, &c1);
+    rc = mat_colslice(ctx, piece, c0, c1, &send[q]);
+  }
+  if (rc == CBGPU_OK) rc = exchange_blocks(ctx, comm->col, P, me, send, recv, bytes);
+  cbgpu_mat *whole = nullptr, *pruned = nullptr;
+  std::vector<int64_t> rows_of(P, 0);
+  if (rc == CBGPU_OK) {
+    for (int q = 0; q < P; ++q) {
+      parts[q] = (q == me) ? send[q] : recv[q];
+      rows_of[q] = parts[q]->m;
+    }
+    rc = mat_rowstack(ctx, P, parts.data(), &whole);
+  }
+  release_all(ctx, send);
+  release_all(ctx, recv);
+  if (rc == CBGPU_OK) rc = cbgpu_mcl_prune(ctx, whole, hardThreshold, selectNum, recoverNum, recoverPct, &pruned, pst);
+  mat_release(ctx, whole);
+  // backward: row block q of the pruned columns returns to the rank in grid row q
+  int64_t r0 = 0;
+  for (int q = 0; q < P && rc == CBGPU_OK; ++q) {
+    rc = cbgpu_mat_submatrix(ctx, pruned, r0, r0 + rows_of[q], 0, pruned->n, &send[q]);
+    r0 += rows_of[q];
+  }
+  mat_release(ctx, pruned);
+  if (rc == CBGPU_OK) rc = exchange_blocks(ctx, comm->col, P, me, send, recv, bytes);
+  if (rc == CBGPU_OK) {
+    for (int q = 0; q < P; ++q) parts[q] = (q == me) ? send[q] : recv[q];
+    rc = mat_colconcat(ctx, P, parts.data(), out);
+  }
+  release_all(ctx, send);
+  release_all(ctx, recv);
+  return rc;
+}
+
+struct PruneEpilogue : SlabEpilogue {
+  cbgpu_comm *comm;
+  double hard, pct;
+  int64_t sel, rec;
+  cbgpu_memeff_stats *ms;
+  int64_t bytes = 0;
+  int apply(cbgpu_ctx *c, int, cbgpu_mat **Cp) override {
+    ms->nnz_unpruned += (*Cp)->nnz;
+    if ((*Cp)->dtype != CBGPU_F64 && (*Cp)->dtype != CBGPU_F32) return CBGPU_OK; // the reference prunes floating point only
+    cbgpu_mat *out = nullptr;
+    cbgpu_prune_stats ps;
+    memset(&ps, 0, sizeof(ps));
+    Timer tm(c->stream);
+    tm.start();
+    int rc = prune_distributed(c, comm, *Cp, hard, sel, rec, pct, &out, &ps, &bytes);
+    ms->ms_prune += tm.stop();
+    if (rc != CBGPU_OK) return rc;
+    ms->cols_recovered += ps.cols_recovered;
+    ms->cols_selected += ps.cols_selected;
+    ms->cols_recovered_after_select += ps.cols_recovered_after_select;
+    mat_release(c, *Cp);
+    *Cp = out;
+    return CBGPU_OK;
+  }
+};
+
+/* The phased distributed multiply WITH its pruning epilogue: replaces MemEfficientSpGEMM (ParFriends.h:452-777) on a 2D grid
+ * and MemEfficientSpGEMM3D (:3673-4170, pruning :4148) on a layered one. Every finished piece of C is pruned
+ * (MCLPruneRecoverySelect, column decisions over the whole distributed column) before the next slab is multiplied; the pruned
+ * pieces are concatenated into this rank's block of C in the layout of Mult_AnXBn_Synch / Mult_AnXBn_SUMMA3D. phases <= 0: from
+ * the distributed symbolic pass, so that an unpruned piece takes at most a quarter of the free HBM of the fullest rank. */
+int cbgpu_memefficient_spgemm_dist(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                                   double hardThreshold, int64_t selectNum, int64_t recoverNum, double recoverPct, cbgpu_mat **C,
+                                   cbgpu_memeff_stats *stats, cbgpu_dist_stats *dstats) {
+  if (!ctx || !comm || !A || !B || !C) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (comm->grid.layers > 1 && !ctx->opt.fiber_fused)
+    return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "the pruning driver uses the fiber-fused 3D formulation (option fiber_fused = 1)");
+  cbgpu_memeff_stats ms;
+  memset(&ms, 0, sizeof(ms));
+  Timer all(ctx->stream);
+  all.start();
+  if (phases <= 0) {
+    // CalculateNumberOfPhases (ParFriends.h:780-843) with exact counts: the largest piece any rank will hold decides
+    int64_t flops = 0, nnz = 0;
+    CB_TRY(cbgpu_summa_symbolic(ctx, comm, semiring, A, B, &flops, &nnz));
+    size_t freeb = 0, totalb = 0;
+    CB_CUDA(ctx, cudaMemGetInfo(&freeb, &totalb));
+    int64_t want = (int64_t)ceil((double)nnz * 12.0 / (double)std::max<size_t>(freeb / 4, (size_t)1 << 30));
+    if (want < 1) want = 1;
+    int64_t *d = nullptr;
+    CB_TRY(dev_alloc_t(ctx, &d, 2 * (size_t)comm->grid.world + 2));
+    CB_CUDA(ctx, cudaMemcpyAsync(d, &want, 8, cudaMemcpyHostToDevice, ctx->stream));
+    CB_NCCL(ctx, nccl().AllGather(d, d + 1, 1, ncclInt64, comm->world, ctx->stream));
+    std::vector<int64_t> all_want((size_t)comm->grid.world, 1);
+    CB_CUDA(ctx, cudaMemcpyAsync(all_want.data(), d + 1, 8 * (size_t)comm->grid.world, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(dev_free(ctx, d));
+    for (int64_t w : all_want) want = std::max(want, w);
+    phases = (int)std::min<int64_t>(want, std::max<int64_t>(1, B->n / std::max(1, comm->grid.layers)));
+  }
+  phases = std::max(1, phases);
+  ms.phases = phases;
+  PruneEpilogue ep;
+  ep.comm = comm;
+  ep.hard = hardThreshold;
+  ep.pct = recoverPct;
+  ep.sel = selectNum;
+  ep.rec = recoverNum;
+  ep.ms = &ms;
+  std::vector<cbgpu_mat *> kept(phases, nullptr);
+  std::vector<cbgpu_slab_result> res(phases);
+  cbgpu_dist_stats ds;
+  memset(&ds, 0, sizeof(ds));
+  int rc = summa_phased_impl(ctx, comm, semiring, A, B, phases, 0, false, 0, 0, kept.data(), res.data(), &ds, &ep);
+  cbgpu_mat *out = nullptr;
+  if (rc == CBGPU_OK) {
+    if (phases > 1) rc = mat_colconcat(ctx, phases, kept.data(), &out);
+    else {
+      out = kept[0];
+      kept[0] = nullptr;
+    }
+  }
+  for (cbgpu_mat *m : kept) mat_release(ctx, m);
+  ms.flops = ds.local.flops;
+  ms.ms_multiply = ds.ms_multiply;
+  ms.ms_total = all.stop();
+  ds.bytes_fiber += 0;
+  if (rc == CBGPU_OK) {
+    ms.nnz_out = out->nnz;
+    *C = out;
+  }
+  if (stats) *stats = ms;
+  if (dstats) {
+    ds.bytes_bcast += ep.bytes; // the pruning all-to-alls travel along the process column, like the column broadcasts
+    *dstats = ds;
+  }
   return rc;
 }
 

@@ -149,6 +149,9 @@ SIGNATURES = {
     "cbgpu_summa2d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
     "cbgpu_summa3d": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(DistStats)]),
     "cbgpu_summa_phased": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(SlabResult), C.POINTER(DistStats)]),
+    "cbgpu_memefficient_spgemm_dist": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
+                                                 C.POINTER(_P), C.POINTER(MemEffStats), C.POINTER(DistStats)]),
+    "cbgpu_phase_columns": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_summa_symbolic": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_summa_phased_global": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(SlabResult),
                                             C.POINTER(DistStats)]),
@@ -498,6 +501,15 @@ class Comm:
         st = DistStats()
         self.ctx._check(self.ctx.lib.cbgpu_summa3d(self.ctx.handle, self.handle, sr, A.handle, B.handle, C.byref(h), C.byref(st)))
         return DeviceMatrix(self.ctx, h), st
+
+    def memefficient_spgemm(self, sr, A: DeviceMatrix, B: DeviceMatrix, phases, hard_threshold, select_num, recover_num, recover_pct):
+        """MemEfficientSpGEMM / MemEfficientSpGEMM3D with the distributed pruning epilogue; returns (pruned block of C, stats, dist stats)"""
+        h = _P()
+        ms, ds = MemEffStats(), DistStats()
+        self.ctx._check(self.ctx.lib.cbgpu_memefficient_spgemm_dist(self.ctx.handle, self.handle, sr, A.handle, B.handle, int(phases),
+                                                                    C.c_double(hard_threshold), int(select_num), int(recover_num),
+                                                                    C.c_double(recover_pct), C.byref(h), C.byref(ms), C.byref(ds)))
+        return DeviceMatrix(self.ctx, h), ms, ds
 
     def summa_symbolic(self, sr, A: DeviceMatrix, B: DeviceMatrix):
         """(products, outputs) this rank produces in the distributed product (exact; EstPerProcessNnzSUMMA's role)"""

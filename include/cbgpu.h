@@ -245,6 +245,11 @@ int cbgpu_block_owner(int64_t dim, int parts, int64_t global_index);
 int cbgpu_grid_local_range(const cbgpu_grid *grid, int64_t m, int64_t n, int split_cols /*1: A,C  0: B*/,
                            int64_t *row_begin, int64_t *row_end, int64_t *col_begin, int64_t *col_end);
 
+/* columns [begin,end) of a rank's block of B (n local columns) that phase `phase` of a phased multiply takes from the chunk of
+ * fiber rank `layer`: one layer = the ColSplit slab (dcsc.cpp:1202); several = piece `phase` of chunk `layer`
+ * (MemEfficientSpGEMM3D, ParFriends.h:3774-3811; chunks by CalculateColSplitDistributionOfLayer, SpParMat3D.cpp:576-609). Host only. */
+int cbgpu_phase_columns(int64_t n, int phases, int layers, int phase, int layer, int64_t *begin, int64_t *end);
+
 typedef struct cbgpu_comm cbgpu_comm; /* NCCL communicators of one rank: world, row, column, fiber */
 int cbgpu_nccl_unique_id(void *id128 /* 128 bytes out */);
 int cbgpu_comm_create(cbgpu_ctx *ctx, const cbgpu_grid *grid, const void *id128, cbgpu_comm **comm);
@@ -289,6 +294,16 @@ int cbgpu_summa_phased(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbg
 int cbgpu_summa_phased_global(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
                               int64_t row_offset, int64_t col_offset, cbgpu_mat **slabs, cbgpu_slab_result *results,
                               cbgpu_dist_stats *stats);
+
+/* The phased distributed multiply WITH its pruning epilogue: replaces MemEfficientSpGEMM (ParFriends.h:452-777) on a 2D grid and
+ * MemEfficientSpGEMM3D (:3673-4170, pruning :4148) on a layered one. Every finished piece of C is pruned by
+ * MCLPruneRecoverySelect (:186-354) over the WHOLE distributed columns -- the pieces of a process column are re-cut so that every
+ * rank holds whole columns of a share, pruned by the single-GPU kernels, and sent back (this replaces the column reductions and the
+ * distributed Kselect1 of SpParMat.cpp:1413-1700) -- before the next slab is multiplied; the pruned pieces are concatenated into
+ * this rank's block of C in the layout of Mult_AnXBn_Synch / Mult_AnXBn_SUMMA3D. phases <= 0: from the distributed symbolic pass. */
+int cbgpu_memefficient_spgemm_dist(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B, int phases,
+                                   double hardThreshold, int64_t selectNum, int64_t recoverNum, double recoverPct, cbgpu_mat **C,
+                                   cbgpu_memeff_stats *stats, cbgpu_dist_stats *dist_stats);
 
 /* ---------------------------------------------------------------- synthetic inputs (own seeded generators)
  * R-MAT (Graph500 initiator a,b,c,d as in 3DSpGEMM/mpipspgemm.cpp:126-133), duplicates summed into the value

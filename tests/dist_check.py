@@ -190,6 +190,51 @@ def main():
     if rank == 0:
         print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} phased expansion (3 slabs, staged + pipelined driver) nnz={whole.nnz}", flush=True)
     failures += int(t.item())
+    # the pieces of the phased driver concatenate to the block of the unphased product (the reference's 3D phase plan)
+    joined = ctx.colconcat(kept)
+    same_layout = joined.nnz == whole.nnz and ctx.checksum(joined) == ctx.checksum(whole) and joined.shape == whole.shape
+    t = torch.tensor([0 if same_layout else 1], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} phased pieces concatenate to the unphased block", flush=True)
+    failures += int(t.item())
+    # ---- config 4 shape (reduced): HipMCL expansion = phased A^2 with the MCL pruning epilogue over whole DISTRIBUTED columns
+    #      (cbgpu_memefficient_spgemm_dist), against the reference's own MemEfficientSpGEMM at P = 1 on the global matrix.
+    #      Dyadic weights: every product and column sum is exact, so the pruning decisions must be identical.
+    from oracle.oracle import RefOracle  # noqa: E402
+    if RefOracle.available():
+        ref = RefOracle()
+        Gm = rmat(11, 8, 21)
+        rngw = np.random.default_rng(21)
+        Gm.data = rngw.integers(1, 256, len(Gm.data)).astype(np.float64) / 256.0
+        Am = Csc.from_scipy(Gm, np.float64)
+        Hm = cb.SpDCCols.from_scipy(Gm, np.float64)
+        dAm, dBm = ctx.upload(cb.partition_3d(Hm, grid, True)), ctx.upload(cb.partition_3d(Hm, grid, False))
+        okm = True
+        for phases_m, (hard, select, recover, pct) in ((3, (0.4, 20, 25, 40.0)), (0, (0.05, 12, 0, 0.9)), (2, (2.0, 30, 40, 1e6))):
+            want_g = ref.memeff_prune(Am, Am, max(1, phases_m), hard, select, recover, pct)
+            dCm, msm, _ = comm.memefficient_spgemm(0, dAm, dBm, phases_m, hard, select, recover, pct)
+            rows, cols, vals = ctx.download_coo(dCm)
+            nm = Gm.shape[0]
+            r0, r1, c0, c1 = local_range(grid, nm, nm, True)
+            Wg = cb.SpDCCols.from_csc(nm, nm, want_g.colptr, want_g.rows, want_g.vals).submatrix(r0, r1, c0, c1)
+            colptr, wrows, wvals = Wg.to_csc()
+            wantb = Csc(r1 - r0, c1 - c0, colptr, wrows, wvals)
+            try:
+                assert dCm.shape == (r1 - r0, c1 - c0)
+                assert len(rows) == wantb.nnz, f"nnz {len(rows)} vs {wantb.nnz}"
+                assert np.array_equal(cols, wantb.cols_expanded()) and np.array_equal(rows, wantb.rows), "pattern differs"
+                assert np.array_equal(vals, wantb.vals), "values differ"
+                assert msm.nnz_unpruned >= msm.nnz_out
+            except AssertionError as e:
+                okm = False
+                print(f"[rank {rank}] FAIL hipmcl phases={phases_m}: {e}", flush=True)
+            dCm.free()
+        t = torch.tensor([0 if okm else 1], device="cuda")
+        dist.all_reduce(t)
+        if rank == 0:
+            print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} HipMCL expansion with distributed pruning == reference MemEfficientSpGEMM (3 parameter sets)", flush=True)
+        failures += int(t.item())
     comm.destroy()
     dist.barrier()
     dist.destroy_process_group()

@@ -151,3 +151,26 @@ def test_fiber_fused_plan_equals_global_product(world, layers):
         assert mine.shape == want.shape, (r, mine.shape, want.shape)
         assert np.array_equal(mine.indptr, want.indptr) and np.array_equal(mine.indices, want.indices), f"rank {r}: pattern"
         assert np.array_equal(mine.data, want.data), f"rank {r}: values"
+
+
+def test_phase_plan_pieces_tile_the_layer_chunks():
+    """cbgpu_phase_columns: the pieces a fiber rank produces over the phases are its chunk of the block's columns, in order
+    (so the phased 3D product has the layout of the unphased one, ParFriends.h:3774-3811 / SpParMat3D.cpp:576-609)"""
+    import ctypes as C
+
+    import combblas_b200 as cb
+
+    lib = cb.load_library()
+    for n, phases, layers in [(1000, 3, 2), (17, 5, 4), (4096, 1, 2), (7, 3, 1), (5, 8, 2), (0, 2, 2)]:
+        for l in range(layers):
+            k0, k1 = C.c_int64(), C.c_int64()
+            assert lib.cbgpu_block_range(n, layers, l, C.byref(k0), C.byref(k1)) == 0
+            at = k0.value
+            for p in range(phases):
+                b, e = C.c_int64(), C.c_int64()
+                assert lib.cbgpu_phase_columns(n, phases, layers, p, l, C.byref(b), C.byref(e)) == 0
+                assert b.value == at and e.value >= b.value
+                at = e.value
+            assert at == k1.value
+    b, e = C.c_int64(), C.c_int64()
+    assert lib.cbgpu_phase_columns(10, 2, 2, 2, 0, C.byref(b), C.byref(e)) != 0

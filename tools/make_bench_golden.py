@@ -26,13 +26,19 @@ gold = json.load(open(a.out)) if os.path.exists(a.out) else {}
 for scale in a.scales:
     n = 1 << scale
     G = ctx.gen_rmat(scale, bench.EDGEFACTOR << scale, bench.SEED, bench.A_, bench.B_, bench.C_, True, cb.F64, 0)
-    flops, nnz_sym = ctx.symbolic(G, G)
-    phases = max(1, int(np.ceil(nnz_sym * 12 / 48e9)))
+    if scale <= 22:
+        flops, nnz_sym = ctx.symbolic(G, G)
+        phases = max(1, int(np.ceil(nnz_sym * 12 / 48e9)))
+    else:  # too many (column, window) tasks for one symbolic call: slabs sized from the growth of nnz(C) (7.6x per two scales)
+        flops = 0
+        phases = int(np.ceil(7.2e10 * 7.6 ** ((scale - 22) / 2.0) * 12 / 36e9))
     per = n // phases
     slabs = ctx.colsplit(G, phases) if phases > 1 else [G]
     nnz, ps, vs = 0, 0, 0
     for i, Bs in enumerate(slabs):
-        Cs = ctx.spgemm(0, G, Bs)
+        Cs, st = ctx.spgemm(0, G, Bs, want_stats=True)
+        if scale > 22:
+            flops += int(st.flops)
         nnz += Cs.info().nnz
         p_, v_ = ctx.checksum(Cs, 0, per * i)
         ps, vs = (ps + p_) & M64, (vs + v_) & M64
