@@ -1,6 +1,7 @@
 // extern "C" surface of libcbgpu.so (include/cbgpu.h): lifecycle, DCSC staging in HBM, local multiply,
 // merge, column slabs. Distributed entry points live in dist.cu, the synthetic generators in gen.cu.
 #include <string.h>
+#include <vector>
 #include "common.cuh"
 #include "util.cuh"
 
@@ -310,7 +311,25 @@ __global__ void rowstack_copy_kernel(StackParts sp, int64_t n, const int64_t *ou
 }
 
 int mat_rowstack(cbgpu_ctx_impl *ctx, int parts, cbgpu_mat_impl *const *in, cbgpu_mat_impl **out) {
-  if (parts < 1 || parts > kMaxStack) return set_error(ctx, CBGPU_ERR_INVALID, "rowstack supports 1..%d parts", kMaxStack);
+  if (parts < 1) return set_error(ctx, CBGPU_ERR_INVALID, "rowstack needs at least one part");
+  if (parts > kMaxStack) {
+    // more parts than one kernel takes (grids wider than 16 process rows / more than 16 layers): stack in rounds, the
+    // running result is the first part of the next round
+    cbgpu_mat_impl *acc = nullptr;
+    int done = 0;
+    while (done < parts) {
+      std::vector<cbgpu_mat_impl *> round;
+      if (acc) round.push_back(acc);
+      while (done < parts && (int)round.size() < kMaxStack) round.push_back(in[done++]);
+      cbgpu_mat_impl *next = nullptr;
+      int rc = mat_rowstack(ctx, (int)round.size(), round.data(), &next);
+      mat_release(ctx, acc);
+      if (rc != CBGPU_OK) return rc;
+      acc = next;
+    }
+    *out = acc;
+    return CBGPU_OK;
+  }
   StackParts sp;
   memset(&sp, 0, sizeof(sp));
   sp.parts = parts;
@@ -450,6 +469,12 @@ int cbgpu_destroy(cbgpu_ctx *ctx) {
 
 const char *cbgpu_last_error(const cbgpu_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 
+int cbgpu_memory_in_use(cbgpu_ctx *ctx, int64_t *live_bytes) {
+  if (!ctx || !live_bytes) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pool_live_bytes(ctx, live_bytes);
+}
+
 int cbgpu_sync(cbgpu_ctx *ctx) {
   CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return CBGPU_OK;
@@ -492,6 +517,10 @@ int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_proc
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {
   int64_t *s = option_slot(ctx, name);
   if (!s) return set_error(ctx, CBGPU_ERR_INVALID, "unknown option %s", name);
+#ifndef CBGPU_EXPERIMENTAL_RANK_SORT
+  if (!strcmp(name, "hash_rank_sort") && value != 0)
+    return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "hash_rank_sort is not compiled in (make EXTRA=-DCBGPU_EXPERIMENTAL_RANK_SORT)");
+#endif
   if (!strcmp(name, "bitmap_cta_threads") && value != 256 && value != 512)
     return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_cta_threads must be 256 or 512");
   if (!strcmp(name, "bitmap_small_threads") && value != 128 && value != 256)
@@ -696,6 +725,11 @@ int cbgpu_spgemm_local(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const c
 }
 
 int cbgpu_spgemm_symbolic(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops, int64_t *nnz_out) {
+  return cbgpu_spgemm_symbolic_columns(ctx, A, B, flops, nnz_out, nullptr, nullptr);
+}
+
+int cbgpu_spgemm_symbolic_columns(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops, int64_t *nnz_out,
+                                  int64_t *col_flops, int64_t *col_nnz) {
   if (!ctx || !A || !B) return CBGPU_ERR_INVALID;
   if (A->n != B->m) return set_error(ctx, CBGPU_ERR_DIMMISMATCH, "dimensions do not match");
   // the pattern does not depend on the semiring: pick the instance whose operand types match in size
@@ -708,6 +742,14 @@ int cbgpu_spgemm_symbolic(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgpu_mat *B
   if (sr < 0) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "no semiring instance for operand types (%d,%d)", A->dtype, B->dtype);
   CB_CUDA(ctx, cudaSetDevice(ctx->device));
   SpgemmArgs a{ctx, const_cast<cbgpu_mat *>(A), const_cast<cbgpu_mat *>(B), nullptr, nullptr, flops, nnz_out};
+  a.col_flops_host = col_flops;
+  a.col_nnz_host = col_nnz;
+  if ((col_flops || col_nnz) && (A->nnz == 0 || B->nnz == 0)) { // isZero() operands: every column is empty
+    for (int64_t j = 0; j < B->nzc; ++j) {
+      if (col_flops) col_flops[j] = 0;
+      if (col_nnz) col_nnz[j] = 0;
+    }
+  }
   return spgemm_entry(sr)(a);
 }
 

@@ -117,6 +117,7 @@ int set_error(cbgpu_ctx_impl *ctx, int code, const char *fmt, ...);
 int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes);
 int dev_free(cbgpu_ctx_impl *ctx, void *p);
 void release_cached_blocks(cbgpu_ctx_impl *ctx);
+int pool_live_bytes(cbgpu_ctx_impl *ctx, int64_t *live);
 template <class T>
 inline int dev_alloc_t(cbgpu_ctx_impl *ctx, T **p, size_t count) {
   return dev_alloc(ctx, reinterpret_cast<void **>(p), count * sizeof(T));
@@ -133,6 +134,48 @@ int mat_release(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *M);
 int compact_columns(cbgpu_ctx_impl *ctx, const int64_t *cand_ids /*may be null: identity*/, const int64_t *cand_ptr,
                     int64_t ncand, int64_t **jc, int64_t **cp, int64_t *nzc);
 
+// ---- ownership guards: every early return gives device temporaries and half-built results back
+struct MatGuard { // releases a result block unless the call succeeds
+  cbgpu_ctx_impl *ctx;
+  cbgpu_mat_impl **m;
+  bool armed = true;
+  MatGuard(cbgpu_ctx_impl *c, cbgpu_mat_impl **mm) : ctx(c), m(mm) {}
+  ~MatGuard() {
+    if (armed && *m) mat_release(ctx, *m);
+  }
+};
+struct Scratch {
+  cbgpu_ctx_impl *ctx;
+  std::vector<void *> ptrs;
+  explicit Scratch(cbgpu_ctx_impl *c) : ctx(c) {}
+  ~Scratch() {
+    for (void *p : ptrs) dev_free(ctx, p);
+  }
+  template <class T>
+  int alloc(T **p, size_t count) {
+    int rc = dev_alloc_t(ctx, p, count);
+    if (rc == CBGPU_OK) ptrs.push_back(*p);
+    return rc;
+  }
+  void detach(void *p) { // ownership moves elsewhere
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == p) {
+        ptrs.erase(ptrs.begin() + i);
+        return;
+      }
+  }
+  void release(void *p) { // early release
+    if (!p) return;
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == p) {
+        ptrs.erase(ptrs.begin() + i);
+        dev_free(ctx, p);
+        return;
+      }
+  }
+};
+
+
 // per-semiring entry points generated from accumulate.cuh (one translation unit per semiring)
 struct SpgemmArgs {
   cbgpu_ctx_impl *ctx;
@@ -140,6 +183,7 @@ struct SpgemmArgs {
   cbgpu_mat_impl **C; // null: symbolic only
   cbgpu_stats *stats;
   int64_t *flops_out, *nnz_out;
+  int64_t *col_flops_host = nullptr, *col_nnz_host = nullptr; // per non-empty column of B (symbolic only)
 };
 struct MergeArgs {
   cbgpu_ctx_impl *ctx;

@@ -175,14 +175,18 @@ int cbgpu_comm_create(cbgpu_ctx *ctx, const cbgpu_grid *grid, const void *id128,
   c->grid = *grid;
   ncclUniqueId id;
   memcpy(&id, id128, 128);
-  CB_NCCL(ctx, nccl().CommInitRank(&c->world, grid->world, id, grid->rank));
   const int pr = grid->grid_rows, pc = grid->grid_cols;
+  ncclResult_t r = nccl().CommInitRank(&c->world, grid->world, id, grid->rank);
   // row world: same layer, same grid row, ordered by column  (src/CommGrid.cpp:66)
-  CB_NCCL(ctx, nccl().CommSplit(c->world, grid->my_layer * pr + grid->my_row, grid->my_col, &c->row, nullptr));
+  if (r == ncclSuccess) r = nccl().CommSplit(c->world, grid->my_layer * pr + grid->my_row, grid->my_col, &c->row, nullptr);
   // column world: same layer, same grid column, ordered by row (src/CommGrid.cpp:67)
-  CB_NCCL(ctx, nccl().CommSplit(c->world, grid->my_layer * pc + grid->my_col, grid->my_row, &c->col, nullptr));
+  if (r == ncclSuccess) r = nccl().CommSplit(c->world, grid->my_layer * pc + grid->my_col, grid->my_row, &c->col, nullptr);
   // fiber world: same position in every layer, ordered by layer (CommGrid3D.h:77-78)
-  CB_NCCL(ctx, nccl().CommSplit(c->world, grid->my_row * pc + grid->my_col, grid->my_layer, &c->fiber, nullptr));
+  if (r == ncclSuccess) r = nccl().CommSplit(c->world, grid->my_row * pc + grid->my_col, grid->my_layer, &c->fiber, nullptr);
+  if (r != ncclSuccess) {
+    cbgpu_comm_destroy(c); // whatever was created so far
+    return set_error(ctx, CBGPU_ERR_NCCL, "communicator setup failed: %s", nccl().GetErrorString(r));
+  }
   *out = c;
   return CBGPU_OK;
 }

@@ -90,6 +90,8 @@ inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
   return CBGPU_OK;
 }
 
+// every device temporary of a call is owned by a guard: whatever path leaves the function -- in particular a failed
+// allocation of C, the case the phased multiply exists to recover from -- gives all of them back to the pool
 #define CB_KBEGIN(id) do { used[id] = true; cudaEventRecord(ctx->kev[2 * (id)], st); } while (0)
 #define CB_KEND(id) cudaEventRecord(ctx->kev[2 * (id) + 1], st)
 
@@ -117,6 +119,7 @@ struct EngineIO {
   cbgpu_mat_impl **C; // null: symbolic only
   cbgpu_stats *stats;
   int64_t *flops_out, *nnz_out;
+  int64_t *col_flops_host, *col_nnz_host; // optional host arrays [ncol]: products / outputs per non-empty column of B
 };
 
 // symbolic kernel classes (launch order) and numeric kernel classes
@@ -139,6 +142,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   typedef typename SR::acc_t acc_t;
   typedef typename SR::out_t out_t;
   cudaStream_t st = ctx->stream;
+  Scratch scratch(ctx);
   const Options &opt = ctx->opt;
   const int64_t launches0 = ctx->launches;
   cbgpu_stats stats;
@@ -166,7 +170,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
 
   // ---- K1: products per column, then tasks
   int64_t *colflop = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &colflop, (size_t)ncol + 1));
+  CB_TRY(scratch.alloc(&colflop, (size_t)ncol + 1));
   if (ncol > 0) {
     CB_KBEGIN(CBGPU_K_FLOP);
     task_flop_kernel<SR, MERGE><<<(unsigned)((ncol + 7) / 8), 256, 0, st>>>(src, ncol, colflop);
@@ -180,22 +184,22 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   uint32_t *task_win = nullptr;
   if (nwin > 1 && ncol > 0) {
     int64_t *cnt = nullptr;
-    CB_TRY(dev_alloc_t(ctx, &cnt, (size_t)ncol));
-    CB_TRY(dev_alloc_t(ctx, &first, (size_t)ncol + 1));
+    CB_TRY(scratch.alloc(&cnt, (size_t)ncol));
+    CB_TRY(scratch.alloc(&first, (size_t)ncol + 1));
     col_task_count_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(colflop, ncol, nwin, std::min<int64_t>(std::max<int64_t>(opt.light_max, 1), 2048), cnt);
     CB_LAUNCH_CHECK(ctx);
     CB_TRY(exclusive_scan_i64(ctx, cnt, first, ncol));
     CB_CUDA(ctx, cudaMemcpyAsync(&ntask, first + ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
-    CB_TRY(dev_free(ctx, cnt));
+    scratch.release(cnt);
     if (ntask >= (int64_t)1 << 31) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many tasks");
-    CB_TRY(dev_alloc_t(ctx, &task_col, (size_t)ntask));
-    CB_TRY(dev_alloc_t(ctx, &task_win, (size_t)ntask));
+    CB_TRY(scratch.alloc(&task_col, (size_t)ntask));
+    CB_TRY(scratch.alloc(&task_win, (size_t)ntask));
     fill_tasks_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(first, ncol, nwin, task_col, task_win);
     CB_LAUNCH_CHECK(ctx);
     src.task_col = task_col;
     src.task_win = task_win;
-    CB_TRY(dev_alloc_t(ctx, &taskflop, (size_t)ntask + 1));
+    CB_TRY(scratch.alloc(&taskflop, (size_t)ntask + 1));
     task_flop_kernel<SR, MERGE><<<(unsigned)((ntask + 7) / 8), 256, 0, st>>>(src, ntask, taskflop);
     CB_LAUNCH_CHECK(ctx);
   }
@@ -205,12 +209,12 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   uint8_t *bucket = nullptr;
   int32_t *order = nullptr;
   int64_t *tasknnz = nullptr, *taskptr = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &bucket, (size_t)ntask + 1));
-  CB_TRY(dev_alloc_t(ctx, &order, (size_t)ntask + 1));
-  CB_TRY(dev_alloc_t(ctx, &tasknnz, (size_t)ntask + 1));
-  CB_TRY(dev_alloc_t(ctx, &taskptr, (size_t)ntask + 2));
+  CB_TRY(scratch.alloc(&bucket, (size_t)ntask + 1));
+  CB_TRY(scratch.alloc(&order, (size_t)ntask + 1));
+  CB_TRY(scratch.alloc(&tasknnz, (size_t)ntask + 1));
+  CB_TRY(scratch.alloc(&taskptr, (size_t)ntask + 2));
   TaskRec *recs = nullptr; // launch-order records of the bitmap classes
-  CB_TRY(dev_alloc_t(ctx, &recs, (size_t)ntask + 1));
+  CB_TRY(scratch.alloc(&recs, (size_t)ntask + 1));
   BinResult bins;
   ClassRanges sc;
   memset(&bins, 0, sizeof(bins));
@@ -251,11 +255,11 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     save_count = (int)std::min<int64_t>(sc.count[SYM_BM_L] + sc.count[SYM_BM_S], fit);
     if (save_count > 0) {
       // an optimisation only: when HBM is too full for the hand-over buffer the numeric pass marks and ranks again
-      if (dev_alloc_t(ctx, &saved, (size_t)save_count * max_words) != CBGPU_OK ||
-          dev_alloc_t(ctx, &slot_of_task, (size_t)ntask) != CBGPU_OK || dev_alloc_t(ctx, &save_counter, 4) != CBGPU_OK) {
-        dev_free(ctx, saved);
-        dev_free(ctx, slot_of_task);
-        dev_free(ctx, save_counter);
+      if (scratch.alloc(&saved, (size_t)save_count * max_words) != CBGPU_OK ||
+          scratch.alloc(&slot_of_task, (size_t)ntask) != CBGPU_OK || scratch.alloc(&save_counter, 4) != CBGPU_OK) {
+        scratch.release(saved);
+        scratch.release(slot_of_task);
+        scratch.release(save_counter);
         saved = nullptr;
         slot_of_task = nullptr;
         save_counter = nullptr;
@@ -359,6 +363,26 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
 
   int rc = CBGPU_OK;
   cbgpu_mat_impl *Cm = nullptr;
+  MatGuard cguard(ctx, &Cm);
+  // per-column results of the symbolic pass for callers that want what estimateFLOP / estimateNNZ_Hash return
+  if (io.col_flops_host && ncol > 0)
+    CB_CUDA(ctx, cudaMemcpyAsync(io.col_flops_host, colflop, sizeof(int64_t) * (size_t)ncol, cudaMemcpyDeviceToHost, st));
+  if (io.col_nnz_host && ncol > 0) {
+    std::vector<int64_t> cp((size_t)ncol + 1);
+    const int64_t *src_ptr = taskptr;
+    int64_t *colptr_sym = nullptr;
+    if (first) {
+      CB_TRY(scratch.alloc(&colptr_sym, (size_t)ncol + 1));
+      gather_ptr_kernel<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(taskptr, first, ncol, colptr_sym);
+      CB_LAUNCH_CHECK(ctx);
+      src_ptr = colptr_sym;
+    }
+    CB_CUDA(ctx, cudaMemcpyAsync(cp.data(), src_ptr, sizeof(int64_t) * ((size_t)ncol + 1), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int64_t j = 0; j < ncol; ++j) io.col_nnz_host[j] = cp[(size_t)j + 1] - cp[(size_t)j];
+    scratch.release(colptr_sym);
+  }
+  if (io.col_flops_host) CB_CUDA(ctx, cudaStreamSynchronize(st));
   if (io.C) {
     // ---- output block
     CB_TRY(mat_alloc(ctx, io.m, io.n_out, nnzC, -1, io.out_dtype, &Cm));
@@ -552,34 +576,17 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     const int64_t *cand_ptr = taskptr;
     int64_t *colptr_out = nullptr;
     if (first) {
-      CB_TRY(dev_alloc_t(ctx, &colptr_out, (size_t)ncol + 1));
+      CB_TRY(scratch.alloc(&colptr_out, (size_t)ncol + 1));
       gather_ptr_kernel<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(taskptr, first, ncol, colptr_out);
       CB_LAUNCH_CHECK(ctx);
       cand_ptr = colptr_out;
     }
     rc = compact_columns(ctx, io.out_col_ids, cand_ptr, ncol, &Cm->jc, &Cm->cp, &Cm->nzc);
-    dev_free(ctx, colptr_out);
-    stats.nzc_out = Cm->nzc;
+      stats.nzc_out = Cm->nzc;
   }
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
 
-  if (taskflop != colflop) dev_free(ctx, taskflop);
-  dev_free(ctx, colflop);
-  dev_free(ctx, first);
-  dev_free(ctx, task_col);
-  dev_free(ctx, task_win);
-  dev_free(ctx, bucket);
-  dev_free(ctx, order);
-  dev_free(ctx, tasknnz);
-  dev_free(ctx, taskptr);
-  dev_free(ctx, recs);
-  dev_free(ctx, saved);
-  dev_free(ctx, slot_of_task);
-  dev_free(ctx, save_counter);
-  if (rc != CBGPU_OK) {
-    mat_release(ctx, Cm);
-    return rc;
-  }
+  if (rc != CBGPU_OK) return rc; // the guards release C and the temporaries
   CB_CUDA(ctx, cudaStreamSynchronize(st));
   cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&stats.ms_symbolic, ctx->ev[1], ctx->ev[2]);
@@ -590,6 +597,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   stats.kernel_launches = ctx->launches - launches0;
   if (io.stats) *io.stats = stats;
   if (io.C) *io.C = Cm;
+  cguard.armed = false;
   return CBGPU_OK;
 }
 

@@ -185,13 +185,14 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
   cudaStream_t st = ctx->stream;
   const int64_t n = X->n;
   const int64_t launches0 = ctx->launches;
+  Scratch scratch(ctx); // frees the temporaries on every return
   cudaEventRecord(ctx->ev[0], st);
   CB_TRY(ensure_dense_colptr(ctx, X));
   CB_TRY(ensure_dense_colptr(ctx, Y));
   MergeCols m{X->colptr, Y->colptr, X->ir, Y->ir};
   int64_t *ntiles_col = nullptr, *first = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &ntiles_col, (size_t)n + 1));
-  CB_TRY(dev_alloc_t(ctx, &first, (size_t)n + 1));
+  CB_TRY(scratch.alloc(&ntiles_col, (size_t)n + 1));
+  CB_TRY(scratch.alloc(&first, (size_t)n + 1));
   merge_tiles_per_col<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, n, ntiles_col);
   CB_LAUNCH_CHECK(ctx);
   CB_TRY(exclusive_scan_i64(ctx, ntiles_col, first, n));
@@ -201,13 +202,13 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
   if (ntiles >= ((int64_t)1 << 31)) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many merge tiles");
   int32_t *tile_col = nullptr;
   int64_t *tile_count = nullptr, *tile_base = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &tile_col, (size_t)ntiles + 1));
-  CB_TRY(dev_alloc_t(ctx, &tile_count, (size_t)ntiles + 1));
-  CB_TRY(dev_alloc_t(ctx, &tile_base, (size_t)ntiles + 2));
+  CB_TRY(scratch.alloc(&tile_col, (size_t)ntiles + 1));
+  CB_TRY(scratch.alloc(&tile_count, (size_t)ntiles + 1));
+  CB_TRY(scratch.alloc(&tile_base, (size_t)ntiles + 2));
   merge_fill_tile_cols<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(first, n, tile_col);
   CB_LAUNCH_CHECK(ctx);
   int2 *tile_start = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &tile_start, (size_t)ntiles + 1));
+  CB_TRY(scratch.alloc(&tile_start, (size_t)ntiles + 1));
   if (ntiles > 0) {
     merge_partition_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(m, tile_col, first, ntiles, tile_start);
     CB_LAUNCH_CHECK(ctx);
@@ -224,6 +225,7 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
   cudaEventRecord(ctx->ev[2], st);
   CB_CUDA(ctx, cudaStreamSynchronize(st));
   cbgpu_mat_impl *C = nullptr;
+  MatGuard cguard(ctx, &C);
   CB_TRY(mat_alloc(ctx, X->m, n, nnz, -1, X->dtype, &C));
   if (ntiles > 0) {
     merge2_kernel<SR, true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(
@@ -232,22 +234,14 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
     CB_LAUNCH_CHECK(ctx);
   }
   int64_t *colptr = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &colptr, (size_t)n + 1));
+  CB_TRY(scratch.alloc(&colptr, (size_t)n + 1));
   merge_col_ptr<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(tile_base, first, n, colptr);
   CB_LAUNCH_CHECK(ctx);
   int rc = compact_columns(ctx, nullptr, colptr, n, &C->jc, &C->cp, &C->nzc);
+  scratch.detach(colptr);
   C->colptr = colptr; // the merged block already has its dense column index (a following merge round uses it)
   cudaEventRecord(ctx->ev[3], st);
-  dev_free(ctx, ntiles_col);
-  dev_free(ctx, first);
-  dev_free(ctx, tile_col);
-  dev_free(ctx, tile_start);
-  dev_free(ctx, tile_count);
-  dev_free(ctx, tile_base);
-  if (rc != CBGPU_OK) {
-    mat_release(ctx, C);
-    return rc;
-  }
+  if (rc != CBGPU_OK) return rc; // the guards release C and the temporaries
   CB_CUDA(ctx, cudaStreamSynchronize(st));
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -262,6 +256,7 @@ int merge2_run(cbgpu_ctx_impl *ctx, cbgpu_mat_impl *X, cbgpu_mat_impl *Y, cbgpu_
     stats->kernel_launches = ctx->launches - launches0;
   }
   *out = C;
+  cguard.armed = false;
   return CBGPU_OK;
 }
 

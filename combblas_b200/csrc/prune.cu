@@ -473,13 +473,14 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
   memset(&ps, 0, sizeof(ps));
   ps.nnz_in = A->nnz;
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+  Scratch scratch(ctx); // frees the temporaries on every return
   T *thr = nullptr;
   int64_t *keep = nullptr, *optr = nullptr;
   unsigned long long *counters = nullptr;
-  CB_TRY(dev_alloc_t(ctx, &thr, (size_t)nzc + 1));
-  CB_TRY(dev_alloc_t(ctx, &keep, (size_t)nzc + 1));
-  CB_TRY(dev_alloc_t(ctx, &optr, (size_t)nzc + 2));
-  CB_TRY(dev_alloc_t(ctx, &counters, 4));
+  CB_TRY(scratch.alloc(&thr, (size_t)nzc + 1));
+  CB_TRY(scratch.alloc(&keep, (size_t)nzc + 1));
+  CB_TRY(scratch.alloc(&optr, (size_t)nzc + 2));
+  CB_TRY(scratch.alloc(&counters, 4));
   CB_CUDA(ctx, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
   int64_t nnz_out = 0;
   unsigned long long hc[4] = {0, 0, 0, 0};
@@ -488,8 +489,8 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
   int nlong = 0;
   if (nzc >= (int64_t)1 << 31) return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "too many columns");
   if (nzc > 0) {
-    CB_TRY(dev_alloc_t(ctx, &list, (size_t)nzc));
-    CB_TRY(dev_alloc_t(ctx, &nlong_dev, 1));
+    CB_TRY(scratch.alloc(&list, (size_t)nzc));
+    CB_TRY(scratch.alloc(&nlong_dev, 1));
     CB_CUDA(ctx, cudaMemsetAsync(nlong_dev, 0, sizeof(int), st));
     long_cols_kernel<<<(unsigned)((nzc + 255) / 256), 256, 0, st>>>(A->cp, nzc, list, nlong_dev);
     CB_LAUNCH_CHECK(ctx);
@@ -513,6 +514,7 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
     CB_CUDA(ctx, cudaMemsetAsync(optr, 0, sizeof(int64_t), st));
   }
   cbgpu_mat_impl *C = nullptr;
+  MatGuard cguard(ctx, &C);
   CB_TRY(mat_alloc(ctx, A->m, A->n, nnz_out, -1, A->dtype, &C));
   int rc = CBGPU_OK;
   if (nzc > 0 && nnz_out > 0) {
@@ -528,16 +530,7 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
     if (e != cudaSuccess) rc = set_error(ctx, CBGPU_ERR_CUDA, "mcl_compact_kernel: %s", cudaGetErrorString(e));
   }
   if (rc == CBGPU_OK) rc = compact_columns(ctx, A->jc, optr, nzc, &C->jc, &C->cp, &C->nzc);
-  dev_free(ctx, thr);
-  dev_free(ctx, keep);
-  dev_free(ctx, optr);
-  dev_free(ctx, counters);
-  dev_free(ctx, list);
-  dev_free(ctx, nlong_dev);
-  if (rc != CBGPU_OK) {
-    mat_release(ctx, C);
-    return rc;
-  }
+  if (rc != CBGPU_OK) return rc; // the guards release C and the temporaries
   CB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
   CB_CUDA(ctx, cudaStreamSynchronize(st));
   cudaEventElapsedTime(&ps.ms, ctx->ev[4], ctx->ev[5]);
@@ -548,6 +541,7 @@ static int mcl_prune_typed(cbgpu_ctx_impl *ctx, const cbgpu_mat_impl *A, double 
   ps.cols_recovered_after_select = (int64_t)hc[2];
   if (stats) *stats = ps;
   *out = C;
+  cguard.armed = false;
   return CBGPU_OK;
 }
 
@@ -625,9 +619,16 @@ int cbgpu_memefficient_spgemm(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, 
   CB_CUDA(ctx, cudaSetDevice(ctx->device));
   cbgpu_memeff_stats ms;
   memset(&ms, 0, sizeof(ms));
-  cudaEvent_t e0, e1;
-  CB_CUDA(ctx, cudaEventCreate(&e0));
-  CB_CUDA(ctx, cudaEventCreate(&e1));
+  struct Events { // destroyed on every return
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } evs;
+  CB_CUDA(ctx, cudaEventCreate(&evs.a));
+  CB_CUDA(ctx, cudaEventCreate(&evs.b));
+  cudaEvent_t e0 = evs.a, e1 = evs.b;
   cudaEventRecord(e0, ctx->stream);
   if (phases <= 0) {
     // CalculateNumberOfPhases (ParFriends.h:780-843) with the exact symbolic count instead of an estimate: an unpruned
@@ -687,8 +688,6 @@ int cbgpu_memefficient_spgemm(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, 
     if (stats) *stats = ms;
     *C = out;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return rc;
 }
 

@@ -47,6 +47,8 @@ static int spgemm_impl(const SpgemmArgs &a) {
   io.stats = a.stats;
   io.flops_out = a.flops_out;
   io.nnz_out = a.nnz_out;
+  io.col_flops_host = a.col_flops_host;
+  io.col_nnz_host = a.col_nnz_host;
   return run_engine<SR, false>(ctx, src, io);
 }
 

@@ -103,6 +103,22 @@ int dev_free(cbgpu_ctx_impl *ctx, void *p) {
 
 void release_cached_blocks(cbgpu_ctx_impl *ctx) { flush_big_cache(ctx); }
 
+// bytes of the device's stream-ordered pool that are handed out right now, not counting the blocks parked in the large-block
+// cache (they are reusable): what a leak check compares before and after a failed call
+int pool_live_bytes(cbgpu_ctx_impl *ctx, int64_t *live) {
+  cudaMemPool_t pool;
+  CB_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint64_t used = 0;
+  CB_CUDA(ctx, cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+  BigCache &bc = big_cache(ctx->device);
+  std::lock_guard<std::mutex> lock(bc.mu);
+  uint64_t parked = 0;
+  for (auto &kv : bc.free_blocks) parked += kv.first;
+  *live = (int64_t)used - (int64_t)parked;
+  return CBGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ scan
 // three-phase exclusive scan of int64: per-tile sums, scan of the sums by one block, per-tile scan + offset
 constexpr int kScanThreads = 256;

@@ -152,6 +152,8 @@ SIGNATURES = {
     "cbgpu_memefficient_spgemm_dist": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_double,
                                                  C.POINTER(_P), C.POINTER(MemEffStats), C.POINTER(DistStats)]),
     "cbgpu_phase_columns": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cbgpu_spgemm_symbolic_columns": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "cbgpu_memory_in_use": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "cbgpu_summa_symbolic": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_summa_phased_global": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(SlabResult),
                                             C.POINTER(DistStats)]),
@@ -361,6 +363,21 @@ class Context:
         f, z = C.c_int64(), C.c_int64()
         self._check(self.lib.cbgpu_spgemm_symbolic(self.handle, A.handle, B.handle, C.byref(f), C.byref(z)))
         return f.value, z.value
+
+    def memory_in_use(self) -> int:
+        v = C.c_int64()
+        self._check(self.lib.cbgpu_memory_in_use(self.handle, C.byref(v)))
+        return v.value
+
+    def symbolic_columns(self, A: DeviceMatrix, B: DeviceMatrix):
+        """(products, outputs) per NON-EMPTY column of B: what estimateFLOP / estimateNNZ_Hash return (mtSpGEMM.h:1058, :807)"""
+        nzc = B.info().nzc
+        flop = np.zeros(nzc, dtype=np.int64)
+        nnz = np.zeros(nzc, dtype=np.int64)
+        f, z = C.c_int64(), C.c_int64()
+        self._check(self.lib.cbgpu_spgemm_symbolic_columns(self.handle, A.handle, B.handle, C.byref(f), C.byref(z),
+                                                           flop.ctypes.data, nnz.ctypes.data))
+        return flop, nnz
 
     def merge(self, sr: int, mats, want_stats=False):
         arr = (_P * len(mats))(*[m.handle for m in mats])

@@ -121,7 +121,14 @@ int cbgpu_create(int device, void *stream, cbgpu_ctx **ctx);
 int cbgpu_destroy(cbgpu_ctx *ctx);
 const char *cbgpu_last_error(const cbgpu_ctx *ctx);
 int cbgpu_sync(cbgpu_ctx *ctx);
-/* tunables: "hash_warp_max", "hash_cta_max", "bitmap_window_log2", "bitmap_min_nnz", "sort_output" ... */
+/* device memory the library holds for live objects right now (the device's stream-ordered pool minus the reusable blocks parked
+ * in the large-block cache); equal before and after any call that fails */
+int cbgpu_memory_in_use(cbgpu_ctx *ctx, int64_t *live_bytes);
+/* tunables (all have working defaults; unknown names are rejected): "bitmap_window_log2" rows per window of the bitmap path,
+ * "bitmap_min_nnz" smallest task the bitmap path takes, "light_max" products up to which a column stays one task,
+ * "shared_acc" / "shared_acc_max" / "shared_acc_small_max" shared-memory accumulator classes, "bitmap_save_mb" /
+ * "bitmap_save_min_flop" symbolic -> numeric hand-over, "bitmap_cta_threads", "bitmap_small_threads", "force_path" (tests:
+ * 1 hash only, 2 bitmap only), "merge_engine", "summa_fused", "fiber_fused", "fiber_pipeline" */
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value);
 int cbgpu_get_option(cbgpu_ctx *ctx, const char *name, int64_t *value);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
@@ -170,6 +177,10 @@ int cbgpu_spgemm_local(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const c
                        cbgpu_stats *stats);
 /* symbolic only: total products and nnz(C) (EstimateFLOP ParFriends.h:357; estimateNNZ_Hash) */
 int cbgpu_spgemm_symbolic(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops, int64_t *nnz_out);
+/* the same with the per-column results the reference's symbolic functions return: col_flops[j] (estimateFLOP, mtSpGEMM.h:1058)
+ * and col_nnz[j] (estimateNNZ_Hash, :807) for the j-th NON-EMPTY column of B (nzc(B) entries each, HOST arrays, either may be NULL) */
+int cbgpu_spgemm_symbolic_columns(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgpu_mat *B, int64_t *flops, int64_t *nnz_out,
+                                  int64_t *col_flops, int64_t *col_nnz);
 /* host-buffers-in, host-buffers-out form of the same call (what a LocalHybridSpGEMM overlay invokes):
  * uploads both operands, multiplies, and hands back a resident result to download. */
 int cbgpu_spgemm_local_host(cbgpu_ctx *ctx, int semiring, const cbgpu_dcsc_view *A, const cbgpu_dcsc_view *B,

@@ -200,6 +200,17 @@ def test_symbolic_matches_oracle(ctx, port_oracle):
     flop, nnz = port_oracle.symbolic(to_csc(A, np.float64), to_csc(A, np.float64))
     f, z = cb.EstimateFLOP(ctx, to_dcsc(A, np.float64), to_dcsc(A, np.float64))
     assert f == int(flop.sum()) and z == int(nnz.sum())
+    # per column, as estimateFLOP (mtSpGEMM.h:1058) and estimateNNZ_Hash (:807) return them: one entry per non-empty column of B
+    for wlog2 in (17, 10):  # one row window, and several windows per column
+        ctx.set_option("bitmap_window_log2", wlog2)
+        try:
+            dA = ctx.upload(to_dcsc(A, np.float64))
+            cf, cn = ctx.symbolic_columns(dA, dA)
+        finally:
+            ctx.set_option("bitmap_window_log2", 17)
+        nonempty = np.diff(A.indptr) > 0
+        assert np.array_equal(cf, flop[nonempty]) and np.array_equal(cn, nnz[nonempty])
+        dA.free()
 
 
 @pytest.mark.parametrize("sr", [0, 2, 3, 4, 5])
@@ -335,3 +346,24 @@ def test_experimental_hash_rank_sort(ctx, oracle, sr):
     finally:
         ctx.set_option("hash_rank_sort", 0)
         ctx.set_option("force_path", 0)
+
+
+def test_failed_allocation_leaks_nothing(ctx):
+    """a product whose result cannot be allocated (R-MAT scale 21 squared: about 350 GB) fails with NOMEM after the symbolic
+    pass and gives every temporary back: the memory the library holds is the same before and after, and the phased multiply
+    the failure calls for runs right away"""
+    from combblas_b200.lib import CbgpuError
+
+    G = ctx.gen_rmat(21, 16 << 21, 1)
+    before = ctx.memory_in_use()
+    with pytest.raises(CbgpuError) as e:
+        ctx.spgemm(0, G, G)
+    assert e.value.code == -3  # CBGPU_ERR_NOMEM
+    assert ctx.memory_in_use() == before
+    slabs = ctx.colsplit(G, 64)
+    C0 = ctx.spgemm(0, G, slabs[0])
+    assert C0.nnz > 0
+    C0.free()
+    for s in slabs:
+        s.free()
+    G.free()
