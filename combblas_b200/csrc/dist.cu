@@ -574,6 +574,12 @@ static int fiber_exchange_slabs(cbgpu_ctx *ctx, cbgpu_comm *comm, std::vector<cb
                                 int64_t *bytes) {
   return exchange_blocks(ctx, comm->fiber, comm->grid.layers, comm->grid.my_layer, slab, recv, bytes);
 }
+// all-to-all over the whole grid (csrc/reshape.cu: 2D <-> 3D redistribution)
+int exchange_blocks_world(cbgpu_ctx *ctx, cbgpu_comm *comm, std::vector<cbgpu_mat *> &send, std::vector<cbgpu_mat *> &recv,
+                          int64_t *bytes) {
+  if (!nccl().ok) return set_error(ctx, CBGPU_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  return exchange_blocks(ctx, comm->world, comm->grid.world, comm->grid.rank, send, recv, bytes);
+}
 
 // all blocks of `own` along communicator `c` (nranks ranks, this rank is `me`), in rank order; blk[me] == own
 static int allgather_blocks(cbgpu_ctx *ctx, ncclComm_t c, int nranks, int me, const cbgpu_mat *own, std::vector<cbgpu_mat *> &blk,

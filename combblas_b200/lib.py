@@ -153,6 +153,8 @@ SIGNATURES = {
                                                  C.POINTER(_P), C.POINTER(MemEffStats), C.POINTER(DistStats)]),
     "cbgpu_phase_columns": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_spgemm_symbolic_columns": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "cbgpu_mat_transpose": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "cbgpu_redistribute": (C.c_int, [_P, _P, _P, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "cbgpu_memory_in_use": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "cbgpu_summa_symbolic": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_summa_phased_global": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(SlabResult),
@@ -364,6 +366,11 @@ class Context:
         self._check(self.lib.cbgpu_spgemm_symbolic(self.handle, A.handle, B.handle, C.byref(f), C.byref(z)))
         return f.value, z.value
 
+    def transpose(self, D: DeviceMatrix) -> DeviceMatrix:
+        h = _P()
+        self._check(self.lib.cbgpu_mat_transpose(self.handle, D.handle, C.byref(h)))
+        return DeviceMatrix(self, h)
+
     def memory_in_use(self) -> int:
         v = C.c_int64()
         self._check(self.lib.cbgpu_memory_in_use(self.handle, C.byref(v)))
@@ -527,6 +534,18 @@ class Comm:
                                                                     C.c_double(hard_threshold), int(select_num), int(recover_num),
                                                                     C.c_double(recover_pct), C.byref(h), C.byref(ms), C.byref(ds)))
         return DeviceMatrix(self.ctx, h), ms, ds
+
+    def redistribute(self, D: DeviceMatrix, source, target):
+        """source / target: one (r0, r1, c0, c1) rectangle of global indices per rank -- what every rank holds now and shall hold
+        afterwards (SpParMat3D 2D -> 3D constructor / Convert2D, SpParMat3D.cpp:187, :441); returns (block, bytes moved)"""
+        src = np.ascontiguousarray(np.asarray(source, dtype=np.int64).reshape(-1))
+        dst = np.ascontiguousarray(np.asarray(target, dtype=np.int64).reshape(-1))
+        world = len(src) // 4
+        h = _P()
+        moved = C.c_int64()
+        self.ctx._check(self.ctx.lib.cbgpu_redistribute(self.ctx.handle, self.handle, D.handle, src.ctypes.data, dst.ctypes.data, world,
+                                                        self.grid.rank, C.byref(h), C.byref(moved)))
+        return DeviceMatrix(self.ctx, h), moved.value
 
     def summa_symbolic(self, sr, A: DeviceMatrix, B: DeviceMatrix):
         """(products, outputs) this rank produces in the distributed product (exact; EstPerProcessNnzSUMMA's role)"""

@@ -168,6 +168,10 @@ int cbgpu_mat_colconcat(cbgpu_ctx *ctx, int parts, cbgpu_mat *const *in, cbgpu_m
 int cbgpu_mat_submatrix(cbgpu_ctx *ctx, const cbgpu_mat *mat, int64_t row_begin, int64_t row_end, int64_t col_begin,
                         int64_t col_end, cbgpu_mat **out);
 
+/* transpose on the device: replaces SpDCCols::Transpose / TransposeConst (SpDCCols.cpp:871-905) for resident operands, so that
+ * chains like the Galerkin product R^T A R never stage through the host. The result has rows ascending in every column. */
+int cbgpu_mat_transpose(cbgpu_ctx *ctx, const cbgpu_mat *mat, cbgpu_mat **out);
+
 /* ---------------------------------------------------------------- local multiply (K1-K4)
  * replaces: LocalHybridSpGEMM (mtSpGEMM.h:213-460), LocalSpGEMMHash (:463-656), LocalSpGEMM (:74-202)
  * and, fused in, estimateFLOP (:1058), estimateNNZ_Hash (:807), prefixsum (:24) and the
@@ -281,6 +285,14 @@ int cbgpu_summa2d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_ma
  * column slabs (:3578-3612), fiber merge (:3642). A column-split, B row-split, C column-split across layers. */
 int cbgpu_summa3d(cbgpu_ctx *ctx, cbgpu_comm *comm, int semiring, const cbgpu_mat *A, const cbgpu_mat *B,
                   cbgpu_mat **C, cbgpu_dist_stats *stats);
+
+/* Redistribution between block layouts on the device: replaces the 2D -> 3D constructor SpParMat3D(const SpParMat&, nlayers,
+ * colsplit, special) (SpParMat3D.cpp:187-283) and SpParMat3D::Convert2D (:441-570), both built on ExchangeData (:51, :97).
+ * Every rank passes its block and the rectangles {row_begin, row_end, col_begin, col_end} (global indices) that EVERY rank holds
+ * now (source[4 * r ...]) and shall hold afterwards (target[4 * r ...]); cbgpu_grid_make + cbgpu_grid_local_range give them for
+ * the 2D and both 3D layouts. The pieces travel device to device (grouped ncclSend / ncclRecv over the world communicator). */
+int cbgpu_redistribute(cbgpu_ctx *ctx, cbgpu_comm *comm, const cbgpu_mat *local, const int64_t *source, const int64_t *target,
+                       int world, int rank, cbgpu_mat **out, int64_t *bytes_moved);
 
 /* Distributed symbolic pass: products and outputs THIS rank produces in the distributed product (final distribution of C).
  * replaces: EstPerProcessNnzSUMMA (ParFriends.h:1698) and the estimate loop of CalculateNumberOfPhases (:780-843); exact. */

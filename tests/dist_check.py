@@ -153,10 +153,15 @@ def main():
         tot = torch.tensor([sum(p.nnz for p in pieces), whole.nnz], device="cuda")
         dist.all_reduce(tot)
         same = int(tot[0].item()) == int(tot[1].item())
-    # the C-level phased driver (pipelined fiber stage when layers > 1) must reproduce the slab-by-slab results
+    # the C-level phased driver must reproduce the slab-by-slab results. With layers its slabs follow the reference's 3D phase
+    # plan (piece p of every fiber chunk, ParFriends.h:3774-3811), not ColSplit: there the pieces are compared through their
+    # concatenation with the unphased block (below) and through the agreement of the two fiber formulations.
     res, kept, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=True)
-    for r, kp, pc in zip(res, kept, pieces):
-        same = same and r.nnz == pc.nnz and r.pattern_sum == ctx.checksum(pc)[0] and ctx.checksum(kp) == ctx.checksum(pc)
+    if layers == 1:
+        for r, kp, pc in zip(res, kept, pieces):
+            same = same and r.nnz == pc.nnz and r.pattern_sum == ctx.checksum(pc)[0] and ctx.checksum(kp) == ctx.checksum(pc)
+    else:
+        same = same and sum(r.nnz for r in res) == whole.nnz
     res2, _, _ = comm.summa_phased(0, dA, dB, 3, want_checksum=True, keep=False)
     same = same and [(r.nnz, r.pattern_sum) for r in res2] == [(r.nnz, r.pattern_sum) for r in res]
     if layers > 1:  # the fiber-reducing phased driver (sequential and pipelined) produces the same slabs
@@ -234,6 +239,31 @@ def main():
         dist.all_reduce(t)
         if rank == 0:
             print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} HipMCL expansion with distributed pruning == reference MemEfficientSpGEMM (3 parameter sets)", flush=True)
+        failures += int(t.item())
+    # ---- 2D <-> 3D redistribution on the device (SpParMat3D 2D -> 3D constructor, SpParMat3D.cpp:187-283; Convert2D :441-570).
+    #      The reference can do this only when the rank count is a perfect square (src/CommGrid.cpp:44-54): 4 ranks, 2x2 <-> 1x1x4.
+    if world == 4:
+        Gr = rmat(12, 8, seed=31)
+        Hr = cb.SpDCCols.from_scipy(Gr, np.float64)
+        nr = Gr.shape[0]
+        okr = True
+        g2 = [cblib.make_grid(world, r, 1) for r in range(world)]
+        g3 = [cblib.make_grid(world, r, 4) for r in range(world)]
+        for split_cols in (True, False):  # A-type (column-split) and B-type (row-split) 3D layouts
+            src = [local_range(g, nr, nr, True) for g in g2]
+            dst = [local_range(g, nr, nr, split_cols) for g in g3]
+            d2 = ctx.upload(cb.partition_3d(Hr, g2[rank], True))
+            d3, moved = comm.redistribute(d2, src, dst)
+            want3 = ctx.upload(cb.partition_3d(Hr, g3[rank], split_cols))
+            okr = okr and d3.shape == want3.shape and d3.nnz == want3.nnz and ctx.checksum(d3) == ctx.checksum(want3)
+            back, _ = comm.redistribute(d3, dst, src)  # Convert2D
+            okr = okr and back.shape == d2.shape and back.nnz == d2.nnz and ctx.checksum(back) == ctx.checksum(d2)
+            for x in (d2, d3, want3, back):
+                x.free()
+        t = torch.tensor([0 if okr else 1], device="cuda")
+        dist.all_reduce(t)
+        if rank == 0:
+            print(f"{'PASS' if t.item() == 0 else 'FAIL'} world={world} 2D (2x2) <-> 3D (1x1x4) redistribution, both splits, round trip", flush=True)
         failures += int(t.item())
     comm.destroy()
     dist.barrier()

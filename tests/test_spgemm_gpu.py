@@ -355,6 +355,9 @@ def test_failed_allocation_leaks_nothing(ctx):
     from combblas_b200.lib import CbgpuError
 
     G = ctx.gen_rmat(21, 16 << 21, 1)
+    warm = ctx.colslice(G, 0, 64)  # a first multiply builds the per-matrix caches of G as an A operand (they stay, by design)
+    ctx.spgemm(0, G, warm).free()
+    warm.free()
     before = ctx.memory_in_use()
     with pytest.raises(CbgpuError) as e:
         ctx.spgemm(0, G, G)
@@ -367,3 +370,26 @@ def test_failed_allocation_leaks_nothing(ctx):
     for s in slabs:
         s.free()
     G.free()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32, np.int64, np.uint8])
+def test_device_transpose(ctx, dt):
+    """cbgpu_mat_transpose == SpDCCols::Transpose (SpDCCols.cpp:871): pattern, values, rows ascending per column"""
+    rng = np.random.default_rng(17)
+    for (m, n, d) in [(300, 170, 0.05), (1, 40, 0.5), (50, 1, 0.5), (2000, 3000, 0.002), (64, 64, 0.0)]:
+        M = typed(sp.random(m, n, density=d, random_state=rng, format="csc"), dt)
+        dM = ctx.upload(to_dcsc(M, dt))
+        dT = ctx.transpose(dM)
+        rows, cols, vals = ctx.download_coo(dT)
+        W = M.T.tocsc()
+        W.sort_indices()
+        assert dT.shape == (n, m) and len(rows) == W.nnz
+        assert np.array_equal(rows, W.indices) and np.array_equal(cols, np.repeat(np.arange(m), np.diff(W.indptr)))
+        assert np.array_equal(vals, W.data.astype(dt))
+        # and it is a usable operand: (M^T) (x) M through the multiply
+        if dt == np.float64 and M.nnz:
+            D = ctx.spgemm(0, dT, dM)
+            assert D.nnz == (M.T @ M).nnz
+            D.free()
+        dM.free()
+        dT.free()
