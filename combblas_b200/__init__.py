@@ -29,7 +29,7 @@ from .host import (  # noqa: F401
     SEMIRINGS,
     PlusTimesSRing_f64, PlusTimesSRing_f32, PlusTimesSRing_i64, SelectMaxSRing_bool_i64, MinPlusSRing_f64,
     OrAndSRing_bool, PlusTimesSRing_bool_f64, PlusTimesSRing_i32, SelectMaxSRing_i64,
-    semiring_types,
+    semiring_types, load_user_semiring,
     LocalHybridSpGEMM, LocalSpGEMMHash, LocalSpGEMM, MultiwayMerge, MultiwayMergeHash, EstimateFLOP,
     MCLPruneRecoverySelect, MemEfficientSpGEMM, CalculateNumberOfPhases,
     block_range, block_owner, partition_2d, partition_3d,

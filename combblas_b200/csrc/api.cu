@@ -1,6 +1,7 @@
 // extern "C" surface of libcbgpu.so (include/cbgpu.h): lifecycle, DCSC staging in HBM, local multiply,
 // merge, column slabs. Distributed entry points live in dist.cu, the synthetic generators in gen.cu.
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 #include "util.cuh"
@@ -14,14 +15,41 @@ namespace cbgpu {
   int merge_sr##i(const MergeArgs &);
 DECL_SR(0) DECL_SR(1) DECL_SR(2) DECL_SR(3) DECL_SR(4) DECL_SR(5) DECL_SR(6) DECL_SR(7) DECL_SR(8)
 
+// user-defined semirings (include/combblas_b200/device_semiring.cuh): entry points instantiated in a translation unit of the
+// application, registered at run time under ids from CBGPU_SR_USER_BASE on
+struct UserSemiring {
+  spgemm_fn spgemm;
+  merge_fn merge;
+  int ta, tb, tc;
+};
+static std::mutex &user_sr_mutex() {
+  static std::mutex m;
+  return m;
+}
+static std::vector<UserSemiring> &user_srs() {
+  static std::vector<UserSemiring> v;
+  return v;
+}
+static bool user_sr(int sr, UserSemiring *out) {
+  std::lock_guard<std::mutex> lock(user_sr_mutex());
+  const int i = sr - CBGPU_SR_USER_BASE;
+  if (i < 0 || i >= (int)user_srs().size()) return false;
+  *out = user_srs()[(size_t)i];
+  return true;
+}
+
 spgemm_fn spgemm_entry(int sr) {
   static const spgemm_fn t[CBGPU_SR_COUNT] = {spgemm_sr0, spgemm_sr1, spgemm_sr2, spgemm_sr3, spgemm_sr4,
                                               spgemm_sr5, spgemm_sr6, spgemm_sr7, spgemm_sr8};
+  UserSemiring u;
+  if (user_sr(sr, &u)) return u.spgemm;
   return (sr >= 0 && sr < CBGPU_SR_COUNT) ? t[sr] : nullptr;
 }
 merge_fn merge_entry(int sr) {
   static const merge_fn t[CBGPU_SR_COUNT] = {merge_sr0, merge_sr1, merge_sr2, merge_sr3, merge_sr4,
                                              merge_sr5, merge_sr6, merge_sr7, merge_sr8};
+  UserSemiring u;
+  if (user_sr(sr, &u)) return u.merge;
   return (sr >= 0 && sr < CBGPU_SR_COUNT) ? t[sr] : nullptr;
 }
 int semiring_types(int sr, int *a, int *b, int *c) {
@@ -29,9 +57,20 @@ int semiring_types(int sr, int *a, int *b, int *c) {
       {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_F32, CBGPU_F32, CBGPU_F32},  {CBGPU_I64, CBGPU_I64, CBGPU_I64},
       {CBGPU_BOOL, CBGPU_I64, CBGPU_I64}, {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL},
       {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_I32, CBGPU_I32, CBGPU_I32}, {CBGPU_I64, CBGPU_I64, CBGPU_I64}};
+  UserSemiring u;
+  if (user_sr(sr, &u)) {
+    *a = u.ta; *b = u.tb; *c = u.tc;
+    return CBGPU_OK;
+  }
   if (sr < 0 || sr >= CBGPU_SR_COUNT) return CBGPU_ERR_INVALID;
   *a = t[sr][0]; *b = t[sr][1]; *c = t[sr][2];
   return CBGPU_OK;
+}
+int register_user_semiring(spgemm_fn spgemm, merge_fn merge, int ta, int tb, int tc) {
+  if (!spgemm || !merge || dtype_size(ta) == 0 || dtype_size(tb) == 0 || dtype_size(tc) == 0) return CBGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(user_sr_mutex());
+  user_srs().push_back(UserSemiring{spgemm, merge, ta, tb, tc});
+  return CBGPU_SR_USER_BASE + (int)user_srs().size() - 1;
 }
 
 // ---- small conversion kernels for the staging path
@@ -721,6 +760,15 @@ int cbgpu_spgemm_local(cbgpu_ctx *ctx, int semiring, const cbgpu_mat *A, const c
   SpgemmArgs a{ctx, const_cast<cbgpu_mat *>(A), const_cast<cbgpu_mat *>(B), &Cm, stats, nullptr, nullptr};
   CB_TRY(spgemm_entry(semiring)(a));
   *C = (Cm);
+  return CBGPU_OK;
+}
+
+int cbgpu_semiring_types(int semiring, int *a_dtype, int *b_dtype, int *c_dtype) {
+  int ta, tb, tc;
+  if (semiring_types(semiring, &ta, &tb, &tc) != CBGPU_OK) return CBGPU_ERR_INVALID;
+  if (a_dtype) *a_dtype = ta;
+  if (b_dtype) *b_dtype = tb;
+  if (c_dtype) *c_dtype = tc;
   return CBGPU_OK;
 }
 

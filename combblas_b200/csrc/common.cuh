@@ -197,5 +197,7 @@ typedef int (*merge_fn)(const MergeArgs &);
 spgemm_fn spgemm_entry(int semiring);
 merge_fn merge_entry(int semiring);
 int semiring_types(int semiring, int *a, int *b, int *c);
+// user-defined semirings: returns the new id (>= CBGPU_SR_USER_BASE) or a negative status
+int register_user_semiring(spgemm_fn spgemm, merge_fn merge, int a_dtype, int b_dtype, int c_dtype);
 
 } // namespace cbgpu

@@ -12,6 +12,7 @@ Reference types mirrored here (paths under the CombBLAS tree):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -45,6 +46,32 @@ SEMIRINGS = {
 def semiring_types(sr: int):
     _, a, b, c = SEMIRINGS[sr]
     return a, b, c
+
+
+_DTYPE_NP = {_l.F64: np.float64, _l.F32: np.float32, _l.I64: np.int64, _l.I32: np.int32, _l.BOOL: np.uint8}
+
+
+def load_user_semiring(path: str, symbol: str, name: str = None) -> int:
+    """A semiring the application defines itself (a struct with the reference's static id/add/multiply interface,
+    Semirings.h:143-255, KTipsTest.cpp:12-20): `path` is the shared library the application built from its .cu with
+    CBGPU_DEFINE_SEMIRING(symbol, ...) (include/combblas_b200/device_semiring.cuh). Returns the semiring id to pass wherever
+    a library id goes; operand/result types come from the library's registry (cbgpu_semiring_types)."""
+    import ctypes as C
+
+    lib = _l.load_library()
+    user = C.CDLL(os.path.abspath(path), mode=C.RTLD_GLOBAL)
+    fn = getattr(user, symbol)
+    fn.restype = C.c_int
+    fn.argtypes = []
+    sr = fn()
+    if sr < 0:
+        raise _l.CbgpuError(sr, f"{symbol} did not register with libcbgpu.so (built against another version?)")
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.cbgpu_semiring_types(sr, C.byref(a), C.byref(b), C.byref(c))
+    if rc != 0:
+        raise _l.CbgpuError(rc, f"semiring {sr} unknown to libcbgpu.so")
+    SEMIRINGS[sr] = (name or symbol, _DTYPE_NP[a.value], _DTYPE_NP[b.value], _DTYPE_NP[c.value])
+    return sr
 
 
 @dataclass

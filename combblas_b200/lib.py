@@ -130,6 +130,7 @@ SIGNATURES = {
     "cbgpu_mat_submatrix": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "cbgpu_spgemm_local": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_spgemm_symbolic": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cbgpu_semiring_types": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cbgpu_spgemm_local_host": (C.c_int, [_P, C.c_int, C.POINTER(_DcscView), C.POINTER(_DcscView), C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_merge": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(Stats)]),
     "cbgpu_mcl_prune": (C.c_int, [_P, _P, C.c_double, C.c_int64, C.c_int64, C.c_double, C.POINTER(_P), C.POINTER(PruneStats)]),

@@ -50,7 +50,11 @@ typedef enum {
   CBGPU_SR_PLUS_TIMES_BOOL_F64 = 6, /* PlusTimesSRing<bool,double>     bool x f64 -> f64 */
   CBGPU_SR_PLUS_TIMES_I32 = 7,      /* PlusTimesSRing<int32,int32>     i32 x i32 -> i32 */
   CBGPU_SR_SELECT_MAX_I64 = 8,      /* SelectMaxSRing<int64,int64>     i64 x i64 -> i64 */
-  CBGPU_SR_COUNT = 9
+  CBGPU_SR_COUNT = 9,
+  /* ids from here on belong to user-defined semirings: structs with the reference's semiring interface (static id / add /
+   * multiply, Semirings.h:143-255) whose members are __host__ __device__, instantiated into the engine by a translation
+   * unit of the application (include/combblas_b200/device_semiring.cuh) and registered when that unit is loaded */
+  CBGPU_SR_USER_BASE = 64
 } cbgpu_semiring;
 
 typedef struct cbgpu_ctx cbgpu_ctx; /* one per (process, GPU): stream, workspace, tunables */
@@ -189,6 +193,9 @@ int cbgpu_spgemm_symbolic_columns(cbgpu_ctx *ctx, const cbgpu_mat *A, const cbgp
  * uploads both operands, multiplies, and hands back a resident result to download. */
 int cbgpu_spgemm_local_host(cbgpu_ctx *ctx, int semiring, const cbgpu_dcsc_view *A, const cbgpu_dcsc_view *B,
                             cbgpu_mat **C, cbgpu_stats *stats);
+
+/* operand and result value types (cbgpu_dtype) of a library or registered user semiring; CBGPU_ERR_INVALID for an unknown id */
+int cbgpu_semiring_types(int semiring, int *a_dtype, int *b_dtype, int *c_dtype);
 
 /* ---------------------------------------------------------------- k-way merge (K7/K8)
  * replaces: MultiwayMerge (MultiwayMerge.h:428-543) and MultiwayMergeHash (:553-701): column-wise union of k

@@ -23,18 +23,14 @@
 #include <type_traits>
 #include <vector>
 #include "cbgpu.h"
+#include "combblas_b200/semiring_decl.h" // dtype_of, user_semiring, CBGPU_DECLARE_SEMIRING, CBGPU_HD
 
 namespace cbgpu_overlay {
 
-template <class T> struct dtype_of { static constexpr int value = -1; };
-template <> struct dtype_of<double> { static constexpr int value = CBGPU_F64; };
-template <> struct dtype_of<float> { static constexpr int value = CBGPU_F32; };
-template <> struct dtype_of<int64_t> { static constexpr int value = CBGPU_I64; };
-template <> struct dtype_of<int32_t> { static constexpr int value = CBGPU_I32; };
-template <> struct dtype_of<bool> { static constexpr int value = CBGPU_BOOL; };
-
-// library semiring -> cbgpu_semiring id. A user-defined semiring opts in by specialising this trait with one of the ids
-// whose arithmetic it matches (e.g. an OR-AND struct -> CBGPU_SR_OR_AND_BOOL); anything else stays on the CPU path.
+// library semiring -> cbgpu_semiring id. A driver's own semiring struct reaches the device either by specialising this
+// trait with the library id whose arithmetic it matches (an OR-AND struct -> CBGPU_SR_OR_AND_BOOL), or -- any arithmetic --
+// through its own device instantiation: CBGPU_DEFINE_SEMIRING in a .cu of the application + CBGPU_DECLARE_SEMIRING here
+// (combblas_b200/semiring_decl.h). Anything else stays on the reference's CPU path.
 template <class SR> struct semiring_id { static constexpr int value = -1; };
 template <> struct semiring_id<combblas::PlusTimesSRing<double, double>> { static constexpr int value = CBGPU_SR_PLUS_TIMES_F64; };
 template <> struct semiring_id<combblas::PlusTimesSRing<float, float>> { static constexpr int value = CBGPU_SR_PLUS_TIMES_F32; };
@@ -50,14 +46,27 @@ constexpr int sr_types[CBGPU_SR_COUNT][3] = {
     {CBGPU_BOOL, CBGPU_I64, CBGPU_I64}, {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL},
     {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_I32, CBGPU_I32, CBGPU_I32}, {CBGPU_I64, CBGPU_I64, CBGPU_I64}};
 
+// value types the device instantiation of SR works on: the library's table, or what CBGPU_DECLARE_SEMIRING stated
+template <class SR, int WHICH>
+constexpr int sr_dtype() {
+  if constexpr (semiring_id<SR>::value >= 0) return sr_types[semiring_id<SR>::value][WHICH];
+  else if constexpr (user_semiring<SR>::value)
+    return WHICH == 0 ? user_semiring<SR>::a_dtype : (WHICH == 1 ? user_semiring<SR>::b_dtype : user_semiring<SR>::c_dtype);
+  else return -2;
+}
+template <class SR>
+inline int runtime_id() {
+  if constexpr (semiring_id<SR>::value >= 0) return semiring_id<SR>::value;
+  else return user_semiring<SR>::id();
+}
+
 template <class SR, class IT, class NT1, class NT2, class NTO>
-concept supported = (semiring_id<SR>::value >= 0) && (sizeof(IT) == 4 || sizeof(IT) == 8) && std::is_integral_v<IT> &&
-                    (dtype_of<NT1>::value == sr_types[semiring_id<SR>::value >= 0 ? semiring_id<SR>::value : 0][0]) &&
-                    (dtype_of<NT2>::value == sr_types[semiring_id<SR>::value >= 0 ? semiring_id<SR>::value : 0][1]) &&
-                    (dtype_of<NTO>::value == sr_types[semiring_id<SR>::value >= 0 ? semiring_id<SR>::value : 0][2]);
+concept supported = (semiring_id<SR>::value >= 0 || user_semiring<SR>::value) && (sizeof(IT) == 4 || sizeof(IT) == 8) &&
+                    std::is_integral_v<IT> && (dtype_of<NT1>::value == sr_dtype<SR, 0>()) &&
+                    (dtype_of<NT2>::value == sr_dtype<SR, 1>()) && (dtype_of<NTO>::value == sr_dtype<SR, 2>());
 template <class SR, class IT, class NT>
-concept mergeable = (semiring_id<SR>::value >= 0) && (sizeof(IT) == 4 || sizeof(IT) == 8) && std::is_integral_v<IT> &&
-                    (dtype_of<NT>::value == sr_types[semiring_id<SR>::value >= 0 ? semiring_id<SR>::value : 0][2]);
+concept mergeable = (semiring_id<SR>::value >= 0 || user_semiring<SR>::value) && (sizeof(IT) == 4 || sizeof(IT) == 8) &&
+                    std::is_integral_v<IT> && (dtype_of<NT>::value == sr_dtype<SR, 2>());
 
 inline bool disabled() {
   static const bool off = std::getenv("CBGPU_DISABLE") != nullptr;
@@ -82,6 +91,17 @@ inline void check(cbgpu_ctx *ctx, int rc) {
   if (rc == CBGPU_OK) return;
   std::fprintf(stderr, "[cbgpu overlay] %s\n", cbgpu_last_error(ctx));
   MPI_Abort(MPI_COMM_WORLD, rc == CBGPU_ERR_DIMMISMATCH ? DIMMISMATCH : INVALIDPARAMS);
+}
+
+// the id a call passes to the library; a user semiring whose device unit failed to register stops the run
+template <class SR>
+inline int semiring_of() {
+  const int id = runtime_id<SR>();
+  if (id < 0) {
+    std::fprintf(stderr, "[cbgpu overlay] the device instantiation of a user semiring did not register (status %d)\n", id);
+    MPI_Abort(MPI_COMM_WORLD, INVALIDPARAMS);
+  }
+  return id;
 }
 
 template <class IT, class NT>
@@ -128,7 +148,7 @@ combblas::SpTuples<IT, NTO> *multiply(const combblas::SpDCCols<IT, NT1> &A, cons
   cbgpu_ctx *ctx = context();
   cbgpu_dcsc_view va = view_of(A), vb = view_of(B);
   cbgpu_mat *C = nullptr;
-  check(ctx, cbgpu_spgemm_local_host(ctx, semiring_id<SR>::value, &va, &vb, &C, nullptr));
+  check(ctx, cbgpu_spgemm_local_host(ctx, semiring_of<SR>(), &va, &vb, &C, nullptr));
   combblas::SpTuples<IT, NTO> *out = tuples_of<IT, NTO>(ctx, C);
   if (clearA) delete const_cast<combblas::SpDCCols<IT, NT1> *>(&A); // mtSpGEMM.h:443-446
   if (clearB) delete const_cast<combblas::SpDCCols<IT, NT2> *>(&B);
@@ -148,7 +168,7 @@ combblas::SpTuples<IT, NT> *merge(std::vector<combblas::SpTuples<IT, NT> *> &lis
     check(ctx, cbgpu_mat_upload(ctx, &v, &dev[i]));
   }
   cbgpu_mat *C = nullptr;
-  check(ctx, cbgpu_merge(ctx, semiring_id<SR>::value, k, dev.data(), &C, nullptr));
+  check(ctx, cbgpu_merge(ctx, semiring_of<SR>(), k, dev.data(), &C, nullptr));
   for (int i = 0; i < k; ++i) cbgpu_mat_free(ctx, dev[i]);
   combblas::SpTuples<IT, NT> *out = tuples_of<IT, NT>(ctx, C);
   if (delarrs)

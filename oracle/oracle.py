@@ -364,6 +364,37 @@ def mcl_prune_recovery_select(A: Csc, hard, select: int, recover: int, pct):
     return Csc(A.m, A.n, colptr, A.rows[keep].copy(), A.vals[keep].copy()), thr
 
 
+
+def esc_spgemm(A: Csc, B: Csc, multiply, add_ufunc, out_dtype) -> Csc:
+    """Oracle for semirings outside the compiled list (a driver's own struct): expand every product
+    multiply(A(i,k), B(k,j)) (the products the column loop of mtSpGEMM.h:362-440 forms), sort them by (column, row) and fold
+    equal keys with the semiring's add. Only for associative, commutative adds whose numpy ufunc is exact (max, min,
+    logical or, integer +): the fold order then does not matter, as it does not between the reference's own heap and hash
+    kernels. `multiply` takes two numpy arrays (A values, B values of the same length)."""
+    bcols = np.repeat(np.arange(B.n, dtype=np.int64), np.diff(B.colptr))  # column of every B entry
+    k = B.rows.astype(np.int64)                                           # its row = the column of A it scales
+    lens = (A.colptr[k + 1] - A.colptr[k]).astype(np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return Csc(A.m, B.n, np.zeros(B.n + 1, np.int64), np.zeros(0, np.int64), np.zeros(0, out_dtype))
+    owner = np.repeat(np.arange(len(k), dtype=np.int64), lens)             # B entry of every product
+    first = np.cumsum(lens) - lens
+    apos = A.colptr[k][owner] + (np.arange(total, dtype=np.int64) - first[owner])
+    rows = A.rows[apos].astype(np.int64)
+    cols = bcols[owner]
+    vals = multiply(A.vals[apos], B.vals[owner]).astype(out_dtype)
+    order = np.lexsort((rows, cols))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    head = np.ones(total, bool)
+    head[1:] = (rows[1:] != rows[:-1]) | (cols[1:] != cols[:-1])
+    starts = np.flatnonzero(head)
+    out_vals = add_ufunc.reduceat(vals, starts).astype(out_dtype)
+    out_rows, out_cols = rows[starts], cols[starts]
+    colptr = np.zeros(B.n + 1, np.int64)
+    np.add.at(colptr, out_cols + 1, 1)
+    return Csc(A.m, B.n, np.cumsum(colptr), out_rows, out_vals)
+
+
 def best_oracle():
     """The reference build when present (build container and, prebuilt, the GPU box), else the port."""
     return RefOracle() if RefOracle.available() else PortOracle()

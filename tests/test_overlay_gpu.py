@@ -19,3 +19,15 @@ def test_unchanged_reference_driver_runs_on_the_device_library():
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0, r.stdout + r.stderr[-2000:]
     assert r.stdout.count("PASS") == 3 and "FAIL" not in r.stdout
+
+
+def test_driver_with_its_own_semiring_structs_runs_on_the_device_library():
+    """tests/overlay/user_semiring_driver.cpp: PSpGEMM<KTipsOrAnd> and LocalHybridSpGEMM<MaxTimesF64> with the driver's own
+    structs (device instantiation: tests/user_semiring/libmy_semirings.so) against the same structs on the reference's CPU path"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "user_semiring_driver")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/user_semiring_driver not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout + r.stderr[-2000:]
+    assert r.stdout.count("PASS") == 2 and "FAIL" not in r.stdout
