@@ -44,6 +44,59 @@ static bool same(SpTuples<int64_t, double> &x, SpTuples<int64_t, double> &y) {
   return true;
 }
 
+// where two distributed results differ (printed on failure only): first entries of the local blocks that do not match
+static void diff_report(SpParMat<int64_t, double, DCD> &X, SpParMat<int64_t, double, DCD> &Y) {
+  SpTuples<int64_t, double> x(X.seq()), y(Y.seq());
+  x.SortColBased();
+  y.SortColBased();
+  std::printf("  local nnz %lld vs %lld, shape %lldx%lld vs %lldx%lld, nzc %lld vs %lld\n", (long long)x.getnnz(), (long long)y.getnnz(),
+              (long long)X.seq().getnrow(), (long long)X.seq().getncol(), (long long)Y.seq().getnrow(), (long long)Y.seq().getncol(),
+              (long long)X.seq().getnzc(), (long long)Y.seq().getnzc());
+  if (X.seq().getnzc() == Y.seq().getnzc() && X.seq().getnnz() > 0 && Y.seq().getnnz() > 0) {
+    Dcsc<int64_t, double> *a = X.seq().GetDCSC(), *b = Y.seq().GetDCSC();
+    for (int64_t c = 0; c < a->nzc; ++c)
+      if (a->jc[c] != b->jc[c] || a->cp[c + 1] != b->cp[c + 1]) {
+        std::printf("  column slot %lld: jc %lld vs %lld, cp %lld vs %lld\n", (long long)c, (long long)a->jc[c], (long long)b->jc[c],
+                    (long long)a->cp[c + 1], (long long)b->cp[c + 1]);
+        break;
+      }
+    for (int64_t p = 0; p < a->nz; ++p)
+      if (a->ir[p] != b->ir[p] || a->numx[p] != b->numx[p]) {
+        std::printf("  position %lld: row %lld vs %lld, value %.17g vs %.17g\n", (long long)p, (long long)a->ir[p], (long long)b->ir[p],
+                    a->numx[p], b->numx[p]);
+        break;
+      }
+  }
+  int shown = 0;
+  int64_t i = 0, j = 0;
+  while ((i < x.getnnz() || j < y.getnnz()) && shown < 12) {
+    const bool hx = i < x.getnnz(), hy = j < y.getnnz();
+    const int64_t cx = hx ? x.colindex(i) : INT64_MAX, cy = hy ? y.colindex(j) : INT64_MAX;
+    const int64_t rx = hx ? x.rowindex(i) : INT64_MAX, ry = hy ? y.rowindex(j) : INT64_MAX;
+    if (cx == cy && rx == ry) {
+      if (x.numvalue(i) != y.numvalue(j)) {
+        std::printf("  (%lld,%lld): %.17g vs %.17g\n", (long long)rx, (long long)cx, x.numvalue(i), y.numvalue(j));
+        ++shown;
+      }
+      ++i, ++j;
+    } else if (cx < cy || (cx == cy && rx < ry)) {
+      std::printf("  (%lld,%lld) = %.17g only in the first\n", (long long)rx, (long long)cx, x.numvalue(i));
+      ++shown, ++i;
+    } else {
+      std::printf("  (%lld,%lld) = %.17g only in the second\n", (long long)ry, (long long)cy, y.numvalue(j));
+      ++shown, ++j;
+    }
+  }
+}
+
+// equality as matrices. MemEfficientSpGEMM multiplies with LocalSpGEMMHash(sort = false) (ParFriends.h:659), so the reference's
+// block keeps its hash-table row order inside every column and Dcsc::operator== (an array comparison, dcsc.cpp:522-568)
+// cannot be used against the device result, whose rows are ascending: compare the column-sorted tuples instead.
+static bool same_matrix(SpParMat<int64_t, double, DCD> &X, SpParMat<int64_t, double, DCD> &Y) {
+  SpTuples<int64_t, double> x(X.seq()), y(Y.seq());
+  return X.seq().getnrow() == Y.seq().getnrow() && X.seq().getncol() == Y.seq().getncol() && same(x, y);
+}
+
 int main(int argc, char **argv) {
   MPI_Init(&argc, &argv);
   int fails = 0;
@@ -69,13 +122,43 @@ int main(int argc, char **argv) {
     delete gpu; delete cpu; delete mg; delete mc; delete A; delete B;
   }
   {
-    // the distributed driver, unchanged: PSpGEMM -> Mult_AnXBn_Synch (P = 1) -> our LocalHybridSpGEMM / MultiwayMerge
+    // the distributed driver, unchanged: PSpGEMM -> our Mult_AnXBn_Synch overload (blocks resident, cbgpu_summa2d over NCCL)
     std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
     SpParMat<int64_t, double, DCD> A(random_block(4000, 4000, 60000, 5), grid), B(random_block(4000, 4000, 60000, 6), grid);
     SpParMat<int64_t, double, DCD> Cg = PSpGEMM<PTDD>(A, B);
     SpParMat<int64_t, double, DCD> Cc = PSpGEMM<MyPlusTimes>(A, B);
     bool ok = (Cg == Cc); // the reference's own equality (Dcsc::operator==, dcsc.cpp:522-568)
     std::printf("%s PSpGEMM (Mult_AnXBn_Synch) overlay vs reference: nnz %lld\n", ok ? "PASS" : "FAIL", (long long)Cg.getnnz());
+    fails += !ok;
+  }
+  {
+    // HipMCL's expansion, unchanged: MemEfficientSpGEMM (phases + MCLPruneRecoverySelect per phase) -> one device call
+    std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+    SpParMat<int64_t, double, DCD> A(random_block(3000, 3000, 90000, 7), grid), B(random_block(3000, 3000, 90000, 8), grid);
+    SpParMat<int64_t, double, DCD> Cg = MemEfficientSpGEMM<PTDD, double, DCD>(A, B, 3, 2.0, (int64_t)20, (int64_t)30, 0.9, 1, 1, (int64_t)0);
+    SpParMat<int64_t, double, DCD> Cc = MemEfficientSpGEMM<MyPlusTimes, double, DCD>(A, B, 3, 2.0, (int64_t)20, (int64_t)30, 0.9, 1, 1, (int64_t)0);
+    bool ok = same_matrix(Cg, Cc) && Cg.getnnz() > 0;
+    std::printf("%s MemEfficientSpGEMM overlay vs reference: nnz %lld (unpruned product would be larger)\n", ok ? "PASS" : "FAIL", (long long)Cg.getnnz());
+    if (!ok) diff_report(Cg, Cc);
+    fails += !ok;
+  }
+  {
+    // the 3D drivers, unchanged: SpParMat3D operands, Mult_AnXBn_SUMMA3D and MemEfficientSpGEMM3D, compared after Convert2D
+    std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+    SpParMat<int64_t, double, DCD> A(random_block(3000, 3000, 80000, 9), grid), B(random_block(3000, 3000, 80000, 10), grid);
+    SpParMat3D<int64_t, double, DCD> A3(A, 1, true, false), B3(B, 1, false, false);
+    SpParMat3D<int64_t, double, DCD> Cg3 = Mult_AnXBn_SUMMA3D<PTDD, double, DCD>(A3, B3);
+    SpParMat3D<int64_t, double, DCD> Cc3 = Mult_AnXBn_SUMMA3D<MyPlusTimes, double, DCD>(A3, B3);
+    SpParMat<int64_t, double, DCD> Cg = Cg3.Convert2D(), Cc = Cc3.Convert2D();
+    bool ok = (Cg == Cc) && Cg.getnnz() > 0;
+    std::printf("%s Mult_AnXBn_SUMMA3D overlay vs reference: nnz %lld\n", ok ? "PASS" : "FAIL", (long long)Cg.getnnz());
+    fails += !ok;
+    SpParMat3D<int64_t, double, DCD> Pg3 = MemEfficientSpGEMM3D<PTDD, double, DCD>(A3, B3, 2, 2.0, (int64_t)20, (int64_t)30, 0.9, 1, 1, (int64_t)0);
+    SpParMat3D<int64_t, double, DCD> Pc3 = MemEfficientSpGEMM3D<MyPlusTimes, double, DCD>(A3, B3, 2, 2.0, (int64_t)20, (int64_t)30, 0.9, 1, 1, (int64_t)0);
+    SpParMat<int64_t, double, DCD> Pg = Pg3.Convert2D(), Pc = Pc3.Convert2D();
+    ok = same_matrix(Pg, Pc) && Pg.getnnz() > 0;
+    std::printf("%s MemEfficientSpGEMM3D overlay vs reference: nnz %lld\n", ok ? "PASS" : "FAIL", (long long)Pg.getnnz());
+    if (!ok) diff_report(Pg, Pc);
     fails += !ok;
   }
   MPI_Finalize();
