@@ -534,6 +534,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "bitmap_small_minblocks")) return &o.bitmap_small_minblocks;
   if (!strcmp(name, "force_path")) return &o.force_path;
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
+  if (!strcmp(name, "regsort")) return &o.regsort;
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "fiber_fused")) return &o.fiber_fused;
   if (!strcmp(name, "fiber_pipeline")) return &o.fiber_pipeline;

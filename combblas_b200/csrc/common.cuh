@@ -35,6 +35,7 @@ struct Options {
   int64_t bitmap_save_min_flop = 8192; // tasks with at least this many products are handed over (4 bytes per 32 rows of the window)
   int64_t light_max = 256;         // with several row windows, columns up to this many products stay one task (<= 2048)
   int64_t bitmap_small_minblocks = 8; // resident CTAs per SM the 128-thread numeric bitmap kernel is compiled for (8 or 12)
+  int64_t regsort = 1;             // tasks with <= 256 products and segments sorted in registers (regsort_kernel): 1 = numeric pass, 2 = symbolic pass too, 0 = per-warp hash classes
   int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only
   int64_t summa_fused = 1;         // 1 = all SUMMA stages as one stacked local multiply, 0 = stage loop + merge
   int64_t hash_rank_sort = 0;      // per-warp hash classes: rank the hits by counting instead of sorting them (to be validated)

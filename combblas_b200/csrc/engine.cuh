@@ -911,6 +911,223 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ register-sort path
+// Tasks with at most 8 G products AND at most 8 G segments, G = 8 / 16 / 32 lanes per task (4 / 2 / 1 tasks per warp). These are
+// the columns the reference's kernel picks its heap for (compression close to 1, mtSpGEMM.h:276-279) and all of an
+// Erdos-Renyi product (d^2 = 64 products per column). A hash table + compaction + sort in shared memory cost them about
+// 2500 warp instructions per task (a 64-product task!); here the products of a task go, 8 per lane, through a bitonic
+// network held in REGISTERS: exchanges below distance 8 are register to register, the others one shuffle inside the
+// group; equal rows are then neighbours and are folded by a sweep inside the lane plus a segmented scan over the lanes of
+// the group. No table, no probing, no barrier; shared memory only hands the products from the lane that loaded a
+// segment to the lane that sorts them. The symbolic variant sorts the rows alone and counts the distinct ones.
+constexpr int kRsItems = 8;
+constexpr unsigned kRsPad = 0xFFFFFFFFu; // sorts behind every row id
+
+template <class T>
+__device__ __forceinline__ T rs_shfl_xor(unsigned mask, T v, int d, int width) {
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    unsigned lo = __shfl_xor_sync(mask, (unsigned)u, d, width), hi = __shfl_xor_sync(mask, (unsigned)(u >> 32), d, width);
+    u = ((unsigned long long)hi << 32) | lo;
+    memcpy(&v, &u, 8);
+    return v;
+  } else {
+    unsigned u;
+    memcpy(&u, &v, 4);
+    u = __shfl_xor_sync(mask, u, d, width);
+    memcpy(&v, &u, 4);
+    return v;
+  }
+}
+template <class T>
+__device__ __forceinline__ T rs_shfl_up(unsigned mask, T v, int d, int width) {
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    unsigned lo = __shfl_up_sync(mask, (unsigned)u, d, width), hi = __shfl_up_sync(mask, (unsigned)(u >> 32), d, width);
+    u = ((unsigned long long)hi << 32) | lo;
+    memcpy(&v, &u, 8);
+    return v;
+  } else {
+    unsigned u;
+    memcpy(&u, &v, 4);
+    u = __shfl_up_sync(mask, u, d, width);
+    memcpy(&v, &u, 4);
+    return v;
+  }
+}
+
+template <class SR, bool MERGE, int G, bool NUMERIC>
+__global__ void __launch_bounds__(256, NUMERIC ? 4 : 6)
+regsort_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t *tasknnz, int32_t *Cir, typename SR::out_t *Cval) {
+  typedef typename SR::acc_t acc_t;
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  typedef typename SR::b_t mult_t;
+  constexpr int E = kRsItems, CAP = G * E, GROUPS = 256 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned *skey_all = reinterpret_cast<unsigned *>(smem_raw);             // [GROUPS * CAP] = 2048 rows
+  acc_t *sval_all = reinterpret_cast<acc_t *>(skey_all + GROUPS * CAP);    // [GROUPS * CAP] (numeric only)
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), group = threadIdx.x / G;
+  const unsigned gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const int64_t ti = (int64_t)blockIdx.x * GROUPS + group;
+  if (ti >= count) return; // whole group; every collective below names the lanes of the group only
+  unsigned *skey = skey_all + group * CAP;
+  acc_t *sval = sval_all + group * CAP;
+  const TaskRec r = recs[ti]; // launch-order record: segment range, window, output offset (symbolic: the task id) in one load
+  const Task k = task_from_record(s, r);
+  const int nseg = (int)(k.seg_end - k.seg_begin); // <= CAP by classification, and so is the number of products
+  // ---- load: lane gl takes segments gl, gl + G, ...; their products land in segment order in the group's staging area
+  int base = 0;
+  for (int s0 = 0; s0 < nseg; s0 += G) { // uniform per group
+    const int si = s0 + gl;
+    int64_t beg = 0;
+    int len = 0;
+    mult_t mult = mult_t();
+    if (si < nseg) load_segment<SR, MERGE, NUMERIC>(s, k, k.seg_begin + si, beg, len, mult);
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const int v = __shfl_up_sync(gmask, incl, d, G);
+      if (gl >= d) incl += v;
+    }
+    const int pos = base + incl - len;
+    const int32_t *__restrict__ rp = k.rows + beg;
+    const aval_t *__restrict__ vp = reinterpret_cast<const aval_t *>(k.vals) + beg;
+    for (int i0 = 0; i0 < len; i0 += 4) { // four loads in flight before the first store (the stores may alias for all the compiler knows)
+      int r[4];
+      aval_t a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u < len) {
+          r[u] = rp[i0 + u];
+          if (NUMERIC) a[u] = vp[i0 + u];
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u < len) {
+          skey[pos + i0 + u] = (unsigned)r[u];
+          if (NUMERIC) sval[pos + i0 + u] = MERGE ? SR::from_out((typename SR::out_t)a[u]) : SR::mul((typename SR::a_t)a[u], mult);
+        }
+    }
+    base += __shfl_sync(gmask, incl, G - 1, G);
+  }
+  const int P = base;
+  __syncwarp(gmask);
+  // ---- sort: element e = gl * E + slot, ascending by row; pads behind
+  unsigned key[E];
+  acc_t val[E];
+#pragma unroll
+  for (int q = 0; q < E; ++q) {
+    const int e = gl * E + q;
+    key[q] = e < P ? skey[e] : kRsPad;
+    if (NUMERIC) val[q] = e < P ? sval[e] : SR::identity();
+  }
+#pragma unroll
+  for (int kk = 2; kk <= CAP; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= E) { // partner in lane gl ^ (j / E), same slot
+        const int lj = j / E;
+        const bool up = ((gl * E) & kk) == 0;
+        const bool keep_min = ((gl & lj) == 0) == up;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const unsigned ok = __shfl_xor_sync(gmask, key[q], lj, G);
+          acc_t ov;
+          if (NUMERIC) ov = rs_shfl_xor<acc_t>(gmask, val[q], lj, G);
+          const bool take = keep_min ? (ok < key[q]) : (ok > key[q]);
+          if (take) {
+            key[q] = ok;
+            if (NUMERIC) val[q] = ov;
+          }
+        }
+      } else { // partner in the same lane
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int p = q ^ j;
+          if (p > q) {
+            const bool up = ((gl * E + q) & kk) == 0;
+            if ((key[q] > key[p]) == up) {
+              const unsigned tk = key[q];
+              key[q] = key[p];
+              key[p] = tk;
+              if (NUMERIC) {
+                const acc_t tv = val[q];
+                val[q] = val[p];
+                val[p] = tv;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- fold equal rows
+  unsigned prev_last = __shfl_up_sync(gmask, key[E - 1], 1, G);  // last row of the lane before
+  unsigned next_first = __shfl_down_sync(gmask, key[0], 1, G);   // first row of the lane after
+  const bool from_prev = gl > 0 && prev_last == key[0];          // my first run started in an earlier lane
+  const bool into_next = gl < G - 1 && next_first == key[E - 1]; // my last run goes on in the next lane
+  if (!NUMERIC) {
+    int heads = 0;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const bool head = key[q] != kRsPad && (q == 0 ? !from_prev : key[q] != key[q - 1]);
+      heads += head ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = G >> 1; d >= 1; d >>= 1) heads += __shfl_xor_sync(gmask, heads, d, G);
+    if (gl == 0) tasknnz[r.obase] = heads;
+    return;
+  } else {
+    // inside the lane: the last element of every run collects the run
+#pragma unroll
+    for (int q = 1; q < E; ++q)
+      if (key[q] == key[q - 1]) val[q] = SR::acc_add(val[q - 1], val[q]);
+    // across lanes: C(l) = what the run that ends lane l has collected up to the end of lane l. A lane chains to the left only
+    // if it is one single run that started before it; segmented inclusive scan over the lanes of the group.
+    acc_t sum = val[E - 1];
+    bool open = from_prev && key[0] == key[E - 1];
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const acc_t os = rs_shfl_up<acc_t>(gmask, sum, d, G);
+      const int oo = __shfl_up_sync(gmask, (int)open, d, G);
+      if (gl >= d && open) {
+        sum = SR::acc_add(os, sum);
+        open = oo != 0;
+      }
+    }
+    const acc_t carry = rs_shfl_up<acc_t>(gmask, sum, 1, G); // C(l - 1): goes into my first run when it started earlier
+    bool pending = from_prev;
+    int tails = 0;
+    bool tail[E];
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const bool lane_tail = (q == E - 1) || key[q] != key[q + 1];
+      if (pending && lane_tail) {
+        val[q] = SR::acc_add(carry, val[q]);
+        pending = false;
+      }
+      tail[q] = lane_tail && key[q] != kRsPad && !(q == E - 1 && into_next);
+      tails += tail[q] ? 1 : 0;
+    }
+    int incl = tails;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const int v = __shfl_up_sync(gmask, incl, d, G);
+      if (gl >= d) incl += v;
+    }
+    int64_t o = r.obase + (incl - tails);
+#pragma unroll
+    for (int q = 0; q < E; ++q)
+      if (tail[q]) {
+        Cir[o] = (int32_t)key[q];
+        Cval[o] = SR::to_out(val[q]);
+        ++o;
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ bitmap path
 // The presence bitmap of a row window is an array of 32-row WORDS in shared memory; after the scan a second array holds
 // for every word the number of present rows in all earlier words, so the output slot of a product is
@@ -1083,6 +1300,22 @@ num_bitmap_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64
   bitmap_walk<SR, MERGE, true>(s, k, &queue, use); // starts with __syncthreads: the identities are in place
 }
 
+#ifdef CBGPU_PHASE_TIMING // tuning builds only (make EXTRA=-DCBGPU_PHASE_TIMING): cycles of thread 0 per phase and CTA shape
+static __device__ unsigned long long g_phase_cycles[3][8];
+#define CB_PHASE_BEGIN() long long cb_tprev = clock64()
+#define CB_PHASE(idx)                                                                                                  \
+  do {                                                                                                                 \
+    if (threadIdx.x == 0) {                                                                                            \
+      const long long cb_now = clock64();                                                                              \
+      atomicAdd(&g_phase_cycles[THREADS == 1024 ? 0 : (THREADS == 512 ? 1 : 2)][idx], (unsigned long long)(cb_now - cb_tprev)); \
+      cb_tprev = cb_now;                                                                                               \
+    }                                                                                                                  \
+  } while (0)
+#else
+#define CB_PHASE_BEGIN() do {} while (0)
+#define CB_PHASE(idx) do {} while (0)
+#endif
+
 // K4 (bitmap, accumulators in shared memory): the numeric kernel of every task whose outputs fit the CTA's shared memory.
 // Ranked words as above; the sorted rows are unpacked by rank into a staging area and leave with coalesced stores; every
 // product then finds its slot with two shared loads and a popcount and is added to a shared-memory accumulator with the
@@ -1111,7 +1344,24 @@ num_sacc_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wor
   const int nnz = r.nnz;
   // a task whose segments fit one chunk stages them once for both of its walks (mark, accumulate)
   const bool restage = !MERGE && r.slot < 0 && r.nseg <= THREADS;
+  CB_PHASE_BEGIN();
+#ifdef CBGPU_PHASE_TIMING
+  if (r.slot >= 0) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(saved + (int64_t)r.slot * save_stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(bits);
+    const int nvec = (w.nword + 3) >> 2;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    CB_PHASE(0); // presence words from the symbolic pass
+  } else {
+    bitmap_mark(s, k, &queue, bits, w.nword, w.rbase, restage);
+    CB_PHASE(1); // staging + mark walk
+  }
+  bitmap_scan<true>(bits, rank, w.nword, warp_sums);
+  CB_PHASE(2); // scan + rank prefixes
+#else
   bitmap_obtain(s, k, &queue, bits, rank, w, warp_sums, saved, save_stride, r.slot, restage);
+#endif
   // rows: unpacked into the staging area (the accumulator array, not yet in use) at their ranks, then copied out
   int32_t *stage = reinterpret_cast<int32_t *>(acc);
   for (int c = threadIdx.x; c < w.nword; c += THREADS) {
@@ -1124,6 +1374,7 @@ num_sacc_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wor
     }
   }
   __syncthreads();
+  CB_PHASE(3); // rows unpacked
   for (int i = threadIdx.x; i < nnz; i += THREADS) Cir[obase + i] = stage[i];
   __syncthreads();
   for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity();
@@ -1137,8 +1388,14 @@ num_sacc_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wor
     SR::template accumulate_shared<FIRST>(&acc[slot], v);
   };
   __syncthreads(); // accumulators initialised (the walk itself only synchronises when it stages)
+  CB_PHASE(4); // rows stored, accumulators initialised
   bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
+  CB_PHASE(5); // accumulate walk
   for (int i = threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(acc[i]);
+  CB_PHASE(6); // values stored
+#ifdef CBGPU_PHASE_TIMING
+  if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[THREADS == 1024 ? 0 : (THREADS == 512 ? 1 : 2)][7], 1ull);
+#endif
 }
 
 } // namespace cbgpu

@@ -21,11 +21,35 @@ __device__ __forceinline__ bool task_is_one_window(const uint32_t *task_win, int
 }
 
 // symbolic path choice per task: bucket = size bucket of the products (+0 hash, +40 bitmap)
+// Register-sort classes (engine.cuh regsort_kernel): tasks with at most 8 G products and at most 8 G segments, G = 8 / 16 / 32
+// lanes per task; buckets 240 / 241 / 242. Both passes classify by the same two numbers, so a task keeps its class.
+struct TinyRule {
+  const int32_t *task_col; // null: task i is column i
+  const int64_t *Bcp;      // multiply: column pointers of B (segments of a task = entries of its column of B); null: merge
+  int merge_k;             // merge: segments per task
+  int enabled;
+};
+__device__ __forceinline__ int tiny_bucket(const TinyRule &r, int64_t i, int64_t flop) {
+  if (!r.enabled || flop < 1 || flop > 256) return 0;
+  int64_t nseg = r.merge_k;
+  if (r.Bcp) {
+    const int64_t c = r.task_col ? r.task_col[i] : i;
+    nseg = r.Bcp[c + 1] - r.Bcp[c];
+  }
+  if (nseg > 256) return 0;
+  const int64_t m = flop > nseg ? flop : nseg;
+  return m <= 64 ? 240 : (m <= 128 ? 241 : 242);
+}
+
 static __global__ void sym_bucket_kernel(const int64_t *flop, const uint32_t *task_win, int nwin, int64_t ntask,
-                                         int64_t bitmap_min_flop, int force_path, uint8_t *bucket) {
+                                         int64_t bitmap_min_flop, int force_path, TinyRule tiny, uint8_t *bucket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntask) return;
   int64_t v = flop[i];
+  if (const int tb = tiny_bucket(tiny, i, v)) {
+    bucket[i] = (uint8_t)tb;
+    return;
+  }
   int sb = size_bucket(v);
   bool can_bitmap = task_is_one_window(task_win, nwin, i);
   bool use_bitmap = can_bitmap && (v >= bitmap_min_flop || v > 2048);
@@ -38,13 +62,17 @@ static __global__ void sym_bucket_kernel(const int64_t *flop, const uint32_t *ta
 // +120 / +160 / +200 bitmap with shared-memory accumulators in the small / medium / large CTA shape)
 static __global__ void num_bucket_kernel(const int64_t *nnz, const uint32_t *task_win, int nwin, int64_t ntask,
                                          int64_t bitmap_min_nnz, int64_t hash_max_nnz, int64_t cap_s, int64_t cap_m,
-                                         int64_t cap_l, int force_path, uint8_t *bucket) {
+                                         int64_t cap_l, int force_path, TinyRule tiny, const int64_t *flop, uint8_t *bucket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntask) return;
   int64_t v = nnz[i];
   int sb = size_bucket(v);
   if (sb == 0) {
     bucket[i] = 0;
+    return;
+  }
+  if (const int tb = tiny_bucket(tiny, i, flop[i])) {
+    bucket[i] = (uint8_t)tb;
     return;
   }
   bool can_bitmap = task_is_one_window(task_win, nwin, i);
@@ -123,8 +151,8 @@ struct EngineIO {
 };
 
 // symbolic kernel classes (launch order) and numeric kernel classes
-enum { SYM_BM_L = 0, SYM_BM_S = 1, SYM_H_CTA = 2, SYM_H_WARP = 3, SYM_H_WARP_S = 4 };
-enum { NUM_BM_G = 0, NUM_SA_L = 1, NUM_SA_M = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_M2 = 5, NUM_H_WARP_M = 6, NUM_H_WARP_S = 7, NUM_SA_S = 8 };
+enum { SYM_BM_L = 0, SYM_BM_S = 1, SYM_H_CTA = 2, SYM_H_WARP = 3, SYM_H_WARP_S = 4, SYM_RS_8 = 5, SYM_RS_16 = 6, SYM_RS_32 = 7 };
+enum { NUM_BM_G = 0, NUM_SA_L = 1, NUM_SA_M = 2, NUM_H_CTA = 3, NUM_H_WARP = 4, NUM_H_WARP_M2 = 5, NUM_H_WARP_M = 6, NUM_H_WARP_S = 7, NUM_SA_S = 8, NUM_RS_8 = 9, NUM_RS_16 = 10, NUM_RS_32 = 11 };
 
 // shape of the shared-accumulator numeric classes: CTA size and resident CTAs per SM (32 warps per SM in every shape)
 constexpr int kSaccThreadsS = 256, kSaccBlocksS = 4, kSaccThreadsM = 512, kSaccBlocksM = 2, kSaccThreadsL = 1024, kSaccBlocksL = 1;
@@ -227,13 +255,21 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     else if (b >= 10 && b <= 39) c = SYM_H_CTA;
     else if (b >= 41 && b <= 54) c = SYM_BM_S;
     else if (b >= 55 && b <= 79) c = SYM_BM_L;
+    else if (b >= 240 && b <= 242) c = (uint8_t)(SYM_RS_8 + (b - 240));
     sym_class[b] = c;
   }
+  TinyRule tiny;
+  tiny.task_col = task_col;
+  tiny.Bcp = MERGE ? nullptr : src.Bcp;
+  tiny.merge_k = src.k;
+  tiny.enabled = (opt.regsort && opt.force_path == 0 && (MERGE ? src.k <= 256 : true)) ? 1 : 0;
+  TinyRule tiny_sym = tiny; // the symbolic pass keeps its per-warp tables unless asked (they only hold rows; measured faster)
+  tiny_sym.enabled = tiny.enabled && opt.regsort >= 2;
   if (ntask > 0) {
     CB_CUDA(ctx, cudaMemsetAsync(tasknnz, 0, sizeof(int64_t) * (size_t)ntask, st));
     int64_t sym_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 256, 64), 2048);
     sym_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(taskflop, task_win, nwin, ntask, sym_min,
-                                                                      (int)opt.force_path, bucket);
+                                                                      (int)opt.force_path, tiny_sym, bucket);
     CB_LAUNCH_CHECK(ctx);
     CB_TRY(bin_tasks(ctx, bucket, taskflop, nullptr, ntask, task_win, sym_class, order, &bins, &sc));
   }
@@ -351,6 +387,26 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     CB_KEND(CBGPU_K_SYM_HASH_WARP_S);
     stats.flops_sym[4] = class_weight(bins, sym_class, SYM_H_WARP_S, false);
   }
+  // register sort: rows only, count the distinct ones
+  {
+    const size_t sm = 2048 * sizeof(unsigned);
+    auto launch = [&](auto kern, int cls, int G) -> int {
+      if (sc.count[cls] <= 0) return CBGPU_OK;
+      const int64_t groups = 256 / G;
+      kern<<<(unsigned)((sc.count[cls] + groups - 1) / groups), 256, sm, st>>>(src, recs + sc.begin[cls], sc.count[cls], tasknnz, nullptr,
+                                                                             nullptr);
+      CB_LAUNCH_CHECK(ctx);
+      return CBGPU_OK;
+    };
+    if (sc.count[SYM_RS_8] + sc.count[SYM_RS_16] + sc.count[SYM_RS_32] > 0) {
+      CB_KBEGIN(CBGPU_K_SYM_REGSORT);
+      CB_TRY(launch(regsort_kernel<SR, MERGE, 8, false>, SYM_RS_8, 8));
+      CB_TRY(launch(regsort_kernel<SR, MERGE, 16, false>, SYM_RS_16, 16));
+      CB_TRY(launch(regsort_kernel<SR, MERGE, 32, false>, SYM_RS_32, 32));
+      CB_KEND(CBGPU_K_SYM_REGSORT);
+      for (int c = SYM_RS_8; c <= SYM_RS_32; ++c) note_class(CBGPU_K_SYM_REGSORT, sc.count[c], class_weight(bins, sym_class, c, false), 0);
+    }
+  }
   // ---- K3: scan -> output offsets
   CB_TRY(exclusive_scan_i64(ctx, tasknnz, taskptr, ntask));
   int64_t nnzC = 0;
@@ -403,6 +459,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       else if (b >= 121 && b <= 159) c = NUM_SA_S;
       else if (b >= 161 && b <= 199) c = NUM_SA_M;
       else if (b >= 201 && b <= 239) c = NUM_SA_L;
+      else if (b >= 240 && b <= 242) c = (uint8_t)(NUM_RS_8 + (b - 240));
       num_class[b] = c;
     }
     // capacity (outputs per task) of the three shared-accumulator shapes
@@ -422,7 +479,7 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       int64_t auto_min = std::min<int64_t>(std::max<int64_t>(std::min<int64_t>(io.m, W) / 512, 32), 256);
       int64_t bmin = opt.bitmap_min_nnz > 0 ? opt.bitmap_min_nnz : auto_min;
       num_bucket_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(tasknnz, task_win, nwin, ntask, bmin, 2048, cap_s, cap_m,
-                                                                        cap_l, (int)opt.force_path, bucket);
+                                                                        cap_l, (int)opt.force_path, tiny, taskflop, bucket);
       CB_LAUNCH_CHECK(ctx);
       CB_TRY(bin_tasks(ctx, bucket, taskflop, tasknnz, ntask, task_win, num_class, order, &nb, &nc));
       if (nb.listed > 0) {
@@ -571,6 +628,31 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       stats.tasks_hash_warp += nc.count[NUM_H_WARP_S];
       stats.flops_hash_warp += class_weight(nb, num_class, NUM_H_WARP_S, false);
       stats.nnz_hash_warp += class_weight(nb, num_class, NUM_H_WARP_S, true);
+    }
+    // register sort: products sorted by row in registers, equal rows folded, no table
+    {
+      const size_t sm = 2048 * (sizeof(unsigned) + sizeof(acc_t));
+      auto launch = [&](auto kern, int cls, int G) -> int {
+        if (nc.count[cls] <= 0) return CBGPU_OK;
+        const int64_t groups = 256 / G;
+        kern<<<(unsigned)((nc.count[cls] + groups - 1) / groups), 256, sm, st>>>(src, recs + nc.begin[cls], nc.count[cls], nullptr, Cm->ir,
+                                                                               Cval);
+        CB_LAUNCH_CHECK(ctx);
+        return CBGPU_OK;
+      };
+      if (nc.count[NUM_RS_8] + nc.count[NUM_RS_16] + nc.count[NUM_RS_32] > 0) {
+        CB_KBEGIN(CBGPU_K_NUM_REGSORT);
+        CB_TRY(launch(regsort_kernel<SR, MERGE, 8, true>, NUM_RS_8, 8));
+        CB_TRY(launch(regsort_kernel<SR, MERGE, 16, true>, NUM_RS_16, 16));
+        CB_TRY(launch(regsort_kernel<SR, MERGE, 32, true>, NUM_RS_32, 32));
+        CB_KEND(CBGPU_K_NUM_REGSORT);
+        for (int c = NUM_RS_8; c <= NUM_RS_32; ++c) {
+          note_class(CBGPU_K_NUM_REGSORT, nc.count[c], class_weight(nb, num_class, c, false), class_weight(nb, num_class, c, true));
+          stats.tasks_hash_warp += nc.count[c]; // census: the per-warp classes they replace
+          stats.flops_hash_warp += class_weight(nb, num_class, c, false);
+          stats.nnz_hash_warp += class_weight(nb, num_class, c, true);
+        }
+      }
     }
     // ---- DCSC assembly: column pointers of the candidate columns, then drop the empty ones
     const int64_t *cand_ptr = taskptr;

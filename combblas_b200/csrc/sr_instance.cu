@@ -23,3 +23,13 @@ int CB_CAT(spgemm_sr, CB_SR)(const SpgemmArgs &a) { return spgemm_impl<SR>(a, li
 int CB_CAT(merge_sr, CB_SR)(const MergeArgs &a) { return merge_impl<SR>(a); }
 
 } // namespace cbgpu
+
+#if defined(CBGPU_PHASE_TIMING) && CB_SR == 0
+// tuning builds only: read (and clear) the per-phase cycle counters of the shared-accumulator kernels of semiring 0
+extern "C" int cbgpu_debug_phase_cycles(unsigned long long *out /* 3 x 8 */) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, cbgpu::g_phase_cycles, sizeof(unsigned long long) * 24) != cudaSuccess) return -2;
+  unsigned long long zero[24] = {0};
+  return cudaMemcpyToSymbol(cbgpu::g_phase_cycles, zero, sizeof(zero)) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libcbgpu.so")
+    # CBGPU_LIB: a tuning build of the same library (tools/phase_timing.py); the product is always libcbgpu.so next to this file
+    return os.environ.get("CBGPU_LIB") or os.path.join(_HERE, "libcbgpu.so")
 
 
 class CbgpuError(RuntimeError):
@@ -49,9 +50,9 @@ class Stats(C.Structure):
                 ("nnz_bitmap_gmem", C.c_int64), ("ms_kernel", C.c_float * 16), ("flops_sym", C.c_int64 * 5),
                 ("class_tasks", C.c_int64 * 16), ("class_flops", C.c_int64 * 16), ("class_nnz", C.c_int64 * 16)]
 
-    KERNELS = ["sym_bitmap", "sym_hash_cta_large", "sym_hash_cta", "sym_hash_warp", "sym_hash_warp_small",
+    KERNELS = ["sym_bitmap", "sym_regsort", "sym_hash_cta", "sym_hash_warp", "sym_hash_warp_small",
                "num_bitmap_gmem", "num_bitmap_smem", "num_hash_cta", "num_hash_warp", "num_hash_warp_small", "flop",
-               "num_hash_warp_mid", "num_sacc_medium", "num_sacc_small", "sym_bitmap_small", "-"]
+               "num_hash_warp_mid", "num_sacc_medium", "num_sacc_small", "sym_bitmap_small", "num_regsort"]
 
     def as_dict(self):
         skip = ("ms_kernel", "flops_sym", "class_tasks", "class_flops", "class_nnz")

@@ -114,6 +114,8 @@ enum {
   CBGPU_K_NUM_HASH_WARP = 8, CBGPU_K_NUM_HASH_WARP_S = 9, CBGPU_K_FLOP = 10, CBGPU_K_NUM_HASH_WARP_M = 11,
   /* CBGPU_K_NUM_BITMAP_SMEM is the large (1024-thread) shape of the shared-accumulator kernel; medium and small: */
   CBGPU_K_NUM_SACC_M = 12, CBGPU_K_NUM_SACC_S = 13, CBGPU_K_SYM_BITMAP_S = 14,
+  /* register-sort classes (tasks with <= 256 products and segments): symbolic reuses the retired slot 1 */
+  CBGPU_K_SYM_REGSORT = 1, CBGPU_K_NUM_REGSORT = 15,
   CBGPU_K_COUNT = 16
 };
 
@@ -132,7 +134,8 @@ int cbgpu_memory_in_use(cbgpu_ctx *ctx, int64_t *live_bytes);
  * "bitmap_min_nnz" smallest task the bitmap path takes, "light_max" products up to which a column stays one task,
  * "shared_acc" / "shared_acc_max" / "shared_acc_small_max" shared-memory accumulator classes, "bitmap_save_mb" /
  * "bitmap_save_min_flop" symbolic -> numeric hand-over, "bitmap_cta_threads", "bitmap_small_threads", "force_path" (tests:
- * 1 hash only, 2 bitmap only), "merge_engine", "summa_fused", "fiber_fused", "fiber_pipeline" */
+ * 1 hash only, 2 bitmap only), "regsort" (1: tasks with <= 256 products and segments sorted in registers), "merge_engine",
+ * "summa_fused", "fiber_fused", "fiber_pipeline" */
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value);
 int cbgpu_get_option(cbgpu_ctx *ctx, const char *name, int64_t *value);
 /* kernels launched by this context so far (bench.py's gpu_launches) */

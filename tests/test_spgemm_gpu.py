@@ -125,6 +125,47 @@ def test_shared_accumulator_classes_every_semiring(ctx, oracle, sr):
         ctx.set_option("shared_acc_small_max", -1)
 
 
+@pytest.mark.parametrize("sr", [0, 2, 3, 4, 5, 7])
+def test_register_sort_runs_across_lanes(ctx, oracle, sr):
+    """register-sort classes (engine.cuh regsort_kernel): r dense rows of A times a column of B with k entries gives r runs of k
+    equal rows each -- runs that start and end inside a lane, fill whole lanes, and span up to all lanes of a group (k = 256:
+    one output from 256 products) -- next to columns with distinct rows only; group sizes 8, 16 and 32 lanes"""
+    rng = np.random.default_rng(40 + sr)
+    ta, tb, _ = SR_DTYPES[sr]
+    for (r, k) in [(1, 256), (2, 128), (4, 60), (3, 85), (7, 9), (64, 1), (1, 64), (5, 51), (16, 16), (9, 7), (1, 9), (2, 33)]:
+        m, inner, n = 300, 400, 40
+        A = sp.lil_matrix((m, inner))
+        rows = rng.choice(m, size=r, replace=False)
+        cols = rng.choice(inner, size=k, replace=False)
+        for i in rows:
+            A[i, cols] = rng.integers(1, 5, size=k)
+        B = sp.lil_matrix((inner, n))
+        for j in range(n):
+            # even columns: the k columns of A that hold the dense rows (long runs); odd ones: some of them plus empty columns of A
+            pick = cols if j % 2 == 0 else np.concatenate([cols[: max(1, k // 3)], rng.choice(inner, size=5, replace=False)])
+            B[np.unique(pick), j] = rng.integers(1, 4, size=len(np.unique(pick)))
+        for mode in (1, 2):  # 1: numeric pass (default), 2: the symbolic pass counts with the same network
+            ctx.set_option("regsort", mode)
+            try:
+                check_pair(ctx, oracle, sr, typed(A.tocsc(), ta), typed(B.tocsc(), tb))
+            finally:
+                ctx.set_option("regsort", 1)
+
+
+@pytest.mark.parametrize("sr", range(9))
+def test_register_sort_off_keeps_the_hash_classes_covered(ctx, oracle, sr):
+    """option regsort = 0 sends the small tasks to the per-warp hash classes again: same product"""
+    ctx.set_option("regsort", 0)
+    try:
+        ta, tb, _ = SR_DTYPES[sr]
+        A, B = random_pair(300, 220, 260, 0.05, 0.04, 77 + sr, SR_DTYPES[sr])
+        check_pair(ctx, oracle, sr, A, B)
+        G = rmat(11, 8, seed=30 + sr)
+        check_pair(ctx, oracle, sr, typed(G, ta), typed(G, tb))
+    finally:
+        ctx.set_option("regsort", 1)
+
+
 @pytest.mark.parametrize("wlog2", [10, 12])
 @pytest.mark.parametrize("sr", [0, 3, 5])
 def test_row_windows(ctx, oracle, wlog2, sr):
