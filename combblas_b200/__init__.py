@@ -29,6 +29,7 @@ from .host import (  # noqa: F401
     SEMIRINGS,
     PlusTimesSRing_f64, PlusTimesSRing_f32, PlusTimesSRing_i64, SelectMaxSRing_bool_i64, MinPlusSRing_f64,
     OrAndSRing_bool, PlusTimesSRing_bool_f64, PlusTimesSRing_i32, SelectMaxSRing_i64,
+    BoolCopy2ndSRing_f64, BoolCopy1stSRing_f64, BoolCopy2ndSRing_i64, BoolCopy1stSRing_i64, BoolCopy2ndSRing_bool, BoolCopy1stSRing_bool,
     semiring_types, load_user_semiring,
     LocalHybridSpGEMM, LocalSpGEMMHash, LocalSpGEMM, MultiwayMerge, MultiwayMergeHash, EstimateFLOP,
     MCLPruneRecoverySelect, MemEfficientSpGEMM, CalculateNumberOfPhases,

@@ -14,6 +14,7 @@ namespace cbgpu {
   int spgemm_sr##i(const SpgemmArgs &);                                                                                \
   int merge_sr##i(const MergeArgs &);
 DECL_SR(0) DECL_SR(1) DECL_SR(2) DECL_SR(3) DECL_SR(4) DECL_SR(5) DECL_SR(6) DECL_SR(7) DECL_SR(8)
+DECL_SR(9) DECL_SR(10) DECL_SR(11) DECL_SR(12) DECL_SR(13) DECL_SR(14)
 
 // user-defined semirings (include/combblas_b200/device_semiring.cuh): entry points instantiated in a translation unit of the
 // application, registered at run time under ids from CBGPU_SR_USER_BASE on
@@ -40,14 +41,16 @@ static bool user_sr(int sr, UserSemiring *out) {
 
 spgemm_fn spgemm_entry(int sr) {
   static const spgemm_fn t[CBGPU_SR_COUNT] = {spgemm_sr0, spgemm_sr1, spgemm_sr2, spgemm_sr3, spgemm_sr4,
-                                              spgemm_sr5, spgemm_sr6, spgemm_sr7, spgemm_sr8};
+                                              spgemm_sr5, spgemm_sr6, spgemm_sr7, spgemm_sr8, spgemm_sr9,
+                                              spgemm_sr10, spgemm_sr11, spgemm_sr12, spgemm_sr13, spgemm_sr14};
   UserSemiring u;
   if (user_sr(sr, &u)) return u.spgemm;
   return (sr >= 0 && sr < CBGPU_SR_COUNT) ? t[sr] : nullptr;
 }
 merge_fn merge_entry(int sr) {
   static const merge_fn t[CBGPU_SR_COUNT] = {merge_sr0, merge_sr1, merge_sr2, merge_sr3, merge_sr4,
-                                             merge_sr5, merge_sr6, merge_sr7, merge_sr8};
+                                             merge_sr5, merge_sr6, merge_sr7, merge_sr8, merge_sr9,
+                                             merge_sr10, merge_sr11, merge_sr12, merge_sr13, merge_sr14};
   UserSemiring u;
   if (user_sr(sr, &u)) return u.merge;
   return (sr >= 0 && sr < CBGPU_SR_COUNT) ? t[sr] : nullptr;
@@ -56,7 +59,9 @@ int semiring_types(int sr, int *a, int *b, int *c) {
   static const int t[CBGPU_SR_COUNT][3] = {
       {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_F32, CBGPU_F32, CBGPU_F32},  {CBGPU_I64, CBGPU_I64, CBGPU_I64},
       {CBGPU_BOOL, CBGPU_I64, CBGPU_I64}, {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL},
-      {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_I32, CBGPU_I32, CBGPU_I32}, {CBGPU_I64, CBGPU_I64, CBGPU_I64}};
+      {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_I32, CBGPU_I32, CBGPU_I32}, {CBGPU_I64, CBGPU_I64, CBGPU_I64},
+      {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_F64, CBGPU_BOOL, CBGPU_F64}, {CBGPU_BOOL, CBGPU_I64, CBGPU_I64},
+      {CBGPU_I64, CBGPU_BOOL, CBGPU_I64}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL}};
   UserSemiring u;
   if (user_sr(sr, &u)) {
     *a = u.ta; *b = u.tb; *c = u.tc;
@@ -535,6 +540,9 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "force_path")) return &o.force_path;
   if (!strcmp(name, "merge_engine")) return &o.merge_engine;
   if (!strcmp(name, "regsort")) return &o.regsort;
+  if (!strcmp(name, "merge_tma")) return &o.merge_tma;
+  if (!strcmp(name, "validate_uploads")) return &o.validate_uploads;
+  if (!strcmp(name, "sacc_v2")) return &o.sacc_v2;
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "fiber_fused")) return &o.fiber_fused;
   if (!strcmp(name, "fiber_pipeline")) return &o.fiber_pipeline;
@@ -576,6 +584,57 @@ int cbgpu_get_option(cbgpu_ctx *ctx, const char *name, int64_t *value) {
 }
 int64_t cbgpu_launch_count(const cbgpu_ctx *ctx) { return ctx->launches; }
 
+// ---- structural validation of a resident block (the engine's window searches and merges assume it)
+static __global__ void validate_cols_kernel(const int64_t *jc, const int64_t *cp, int64_t nzc, int64_t n, int64_t nnz, int *bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nzc) return;
+  if (i == 0 && cp[0] != 0) atomicOr(bad, 1);
+  if (i == nzc) {
+    if (cp[nzc] != nnz) atomicOr(bad, 1);
+    return;
+  }
+  if (cp[i + 1] <= cp[i]) atomicOr(bad, 1);                       // a listed column is non-empty (dcsc.h:125-132), pointers ascend
+  if (jc[i] < 0 || jc[i] >= n || (i > 0 && jc[i] <= jc[i - 1])) atomicOr(bad, 2); // column ids ascending, in range
+}
+static __global__ void validate_rows_kernel(const int64_t *cp, int64_t nzc, const int32_t *ir, int64_t m, int *bad) {
+  // one warp per listed column: rows in range and strictly ascending
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nzc) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = cp[c], e = cp[c + 1];
+  for (int64_t p = b + lane; p < e; p += 32) {
+    const int32_t r = ir[p];
+    if (r < 0 || (int64_t)r >= m) atomicOr(bad, 4);
+    if (p > b && ir[p - 1] >= r) atomicOr(bad, 8);
+  }
+}
+
+int cbgpu_mat_validate(cbgpu_ctx *ctx, const cbgpu_mat *M) {
+  if (!ctx || !M) return CBGPU_ERR_INVALID;
+  CB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (M->nnz == 0 && M->nzc == 0) return CBGPU_OK;
+  if (M->nzc <= 0 || M->nnz < M->nzc) return set_error(ctx, CBGPU_ERR_INVALID, "block with nnz=%lld, nzc=%lld", (long long)M->nnz, (long long)M->nzc);
+  Scratch scratch(ctx);
+  int *bad = nullptr;
+  CB_TRY(scratch.alloc(&bad, 1));
+  CB_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  validate_cols_kernel<<<(unsigned)((M->nzc + 1 + 255) / 256), 256, 0, ctx->stream>>>(M->jc, M->cp, M->nzc, M->n, M->nnz, bad);
+  CB_LAUNCH_CHECK(ctx);
+  int h = 0;
+  CB_CUDA(ctx, cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h == 0) { // the row check follows the column pointers, so they must be sound first
+    validate_rows_kernel<<<(unsigned)((M->nzc * 32 + 255) / 256), 256, 0, ctx->stream>>>(M->cp, M->nzc, M->ir, M->m, bad);
+    CB_LAUNCH_CHECK(ctx);
+    CB_CUDA(ctx, cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (h == 0) return CBGPU_OK;
+  return set_error(ctx, CBGPU_ERR_INVALID, "block is not a valid DCSC:%s%s%s%s", (h & 1) ? " column pointers not ascending from 0 to nnz;" : "",
+                   (h & 2) ? " column ids not ascending or out of range;" : "", (h & 4) ? " row ids out of range;" : "",
+                   (h & 8) ? " row ids not strictly ascending inside a column (sort the block: the reference's sort=false paths leave them unordered);" : "");
+}
+
 int cbgpu_mat_upload(cbgpu_ctx *ctx, const cbgpu_dcsc_view *h, cbgpu_mat **out) {
   if (!ctx || !h || !out) return CBGPU_ERR_INVALID;
   if (h->idx_bytes != 4 && h->idx_bytes != 8) return set_error(ctx, CBGPU_ERR_INVALID, "idx_bytes must be 4 or 8");
@@ -599,6 +658,7 @@ int cbgpu_mat_upload(cbgpu_ctx *ctx, const cbgpu_dcsc_view *h, cbgpu_mat **out) 
   }
   // the caller's buffers may be reused as soon as we return
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = set_error(ctx, CBGPU_ERR_CUDA, "upload failed"); goto fail; }
+  if (ctx->opt.validate_uploads && (rc = cbgpu_mat_validate(ctx, M)) != CBGPU_OK) goto fail;
   *out = (M);
   return CBGPU_OK;
 fail:

@@ -42,6 +42,9 @@ struct Options {
   int64_t fiber_fused = 1;         // 3D: replicate the inputs along the fiber instead of reducing partial results (see dist.cu); 0 = the reference's fiber reduction
   int64_t fiber_pipeline = 0;      // fiber_fused == 0 only: second host thread + stream overlaps the fiber reduction of slab p with the multiply of slab p+1
   int64_t merge_engine = 0;        // 1 = k-way merges through the accumulation engine instead of streaming 2-way rounds
+  int64_t validate_uploads = 0;    // 1 = every cbgpu_mat_upload checks the block on the device (cbgpu_mat_validate) before handing it out
+  int64_t merge_tma = 1;           // streaming 2-way merge: 1 = persistent CTAs with double-buffered bulk (TMA) tile copies, 0 = one tile per CTA with load/store loops
+  int64_t sacc_v2 = 31;            // shared-accumulator numeric classes, second version (16-bit ranks, vector scan, bulk hand-over): bit 0 small, 1 medium, 2 large shape; bit 3: the large shape keeps a row array too, bit 4: the medium shape does not (measured best at R-MAT scale 22: 31)
 };
 
 } // namespace cbgpu

@@ -22,6 +22,7 @@
 #pragma once
 #include "common.cuh"
 #include "semiring.cuh"
+#include "bulk.cuh"
 
 namespace cbgpu {
 
@@ -1396,6 +1397,130 @@ num_sacc_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wor
 #ifdef CBGPU_PHASE_TIMING
   if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[THREADS == 1024 ? 0 : (THREADS == 512 ? 1 : 2)][7], 1ull);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------ shared accumulators, second version
+// What the per-phase cycle counts of the kernel above showed (profiles/r2_phase_cycles.txt): a task of the small shape spends
+// three quarters of its time in passes over the 4096 words of the window -- scan + rank 15 %, unpacking the sorted rows 24 %
+// -- although six words in seven are empty. This version
+//  * keeps the rank prefixes as 16-bit numbers (a task of these classes has < 65536 outputs): 8 KB less shared memory per task
+//    at 2^17-row windows, which pays for
+//  * a row array next to the accumulators: every product stores its row id at its slot (all products of a slot store the same
+//    value), so the sorted rows fall out of the accumulate walk and the unpack pass over the words disappears (ROWS_BY_WALK);
+//  * scans the words with 16-byte loads, thread t taking vectors t, t + THREADS, ...: the up to four per-thread counts travel
+//    through ONE block scan as 16-bit fields of a 64-bit word, and the four ranks of a vector leave as one 8-byte store;
+//  * fetches handed-over presence words with one bulk copy of the TMA unit instead of a load/store loop of the whole CTA.
+template <int THREADS>
+__device__ __forceinline__ void bitmap_scan16(const unsigned *bits, unsigned short *rank, int nword, unsigned long long *wtot /*[32]*/) {
+  constexpr int nwarp = THREADS >> 5;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int nvec = (nword + 3) >> 2; // <= 4 * THREADS (checked by the host)
+  const uint4 *b4 = reinterpret_cast<const uint4 *>(bits);
+  uint4 w[4];
+  unsigned long long x = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = j * THREADS + (int)threadIdx.x;
+    w[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (v < nvec) w[j] = b4[v];
+    x |= (unsigned long long)(unsigned)(__popc(w[j].x) + __popc(w[j].y) + __popc(w[j].z) + __popc(w[j].w)) << (16 * j);
+  }
+  unsigned long long incl = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  unsigned long long wv = lane < nwarp ? wtot[lane] : 0ull, winc = wv;
+#pragma unroll
+  for (int d = 1; d < nwarp; d <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+    if (lane >= d) winc += v;
+  }
+  const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, nwarp - 1);
+  const unsigned long long excl = __shfl_sync(0xFFFFFFFFu, winc - wv, warp) + incl - x;
+  unsigned base = 0; // outputs of the vector blocks before block j
+  uint2 *r2 = reinterpret_cast<uint2 *>(rank);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = j * THREADS + (int)threadIdx.x;
+    if (v < nvec) {
+      const unsigned r0 = base + (unsigned)((excl >> (16 * j)) & 0xFFFFull);
+      const unsigned r1 = r0 + (unsigned)__popc(w[j].x), r2v = r1 + (unsigned)__popc(w[j].y), r3 = r2v + (unsigned)__popc(w[j].z);
+      r2[v] = make_uint2(r0 | (r1 << 16), r2v | (r3 << 16));
+    }
+    base += (unsigned)((total >> (16 * j)) & 0xFFFFull);
+  }
+  __syncthreads();
+}
+
+template <class SR, bool MERGE, int THREADS, int MINB, bool FIRST, bool ROWS_BY_WALK>
+__global__ void __launch_bounds__(THREADS, MINB)
+num_sacc2_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_words, int cap, int32_t *Cir, typename SR::out_t *Cval,
+                 const unsigned *saved, int64_t save_stride) {
+  typedef typename SR::acc_t acc_t;
+  typedef typename SR::out_t out_t;
+  typedef typename Source<SR, MERGE>::aval_t aval_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: bits[max_words] u32 | acc[cap] acc_t | rows[cap] i32 (ROWS_BY_WALK) | rank[max_words] u16; cap is a multiple of 4
+  unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
+  acc_t *acc = reinterpret_cast<acc_t *>(bits + max_words);
+  int32_t *srow = reinterpret_cast<int32_t *>(acc + cap);
+  unsigned short *rank = reinterpret_cast<unsigned short *>(ROWS_BY_WALK ? (void *)(srow + cap) : (void *)srow);
+  __shared__ FlatQueueT<THREADS> queue;
+  __shared__ unsigned long long wtot[32];
+  __shared__ __align__(8) unsigned long long bar;
+  const TaskRec r = recs[blockIdx.x];
+  const Task k = task_from_record(s, r);
+  const Window w = task_window(s, k, m);
+  const int rbase = w.rbase;
+  const int64_t obase = r.obase;
+  const int nnz = r.nnz;
+  const bool restage = !MERGE && r.slot < 0 && r.nseg <= THREADS;
+  if (r.slot >= 0) { // uniform per CTA: the presence words of the symbolic pass arrive as one bulk copy
+    const unsigned bytes = (unsigned)((w.nword + 3) >> 2) * 16u;
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+      mbar_arrive_expect_tx(&bar, bytes);
+      bulk_load(bits, saved + (int64_t)r.slot * save_stride, bytes, &bar);
+    }
+    for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity(); // while the words are in flight
+    __syncthreads(); // the barrier is initialised for everybody
+    mbar_wait(&bar, 0);
+  } else {
+    bitmap_mark(s, k, &queue, bits, w.nword, w.rbase, restage);
+    for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity();
+  }
+  bitmap_scan16<THREADS>(bits, rank, w.nword, wtot); // ends with __syncthreads: ranks and identities in place
+  if (!ROWS_BY_WALK) {
+    // rows unpacked from the words into Cir directly (the large shape: few words are empty, the walk dominates)
+    for (int c = threadIdx.x; c < w.nword; c += THREADS) {
+      unsigned b = bits[c];
+      int32_t *o = Cir + obase + rank[c];
+      const int rowbase = rbase + (c << 5);
+      while (b) {
+        *o++ = rowbase + __ffs(b) - 1;
+        b &= b - 1;
+      }
+    }
+  }
+  auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
+    const unsigned rr = (unsigned)(row - rbase);
+    const unsigned wd = rr >> 5;
+    const unsigned slot = (unsigned)rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (rr & 31u)) - 1u));
+    if (ROWS_BY_WALK) srow[slot] = row;
+    acc_t v;
+    if (MERGE) v = SR::from_out((out_t)aval);
+    else v = SR::mul((typename SR::a_t)aval, mu);
+    SR::template accumulate_shared<FIRST>(&acc[slot], v);
+  };
+  bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
+  if (ROWS_BY_WALK)
+    for (int i = threadIdx.x; i < nnz; i += THREADS) Cir[obase + i] = srow[i];
+  for (int i = threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(acc[i]);
 }
 
 } // namespace cbgpu

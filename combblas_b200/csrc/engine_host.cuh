@@ -111,8 +111,10 @@ static __global__ void gather_ptr_kernel(const int64_t *taskptr, const int64_t *
   if (j <= ncol) colptr_out[j] = taskptr[first[j]];
 }
 
+// static: an application's own semiring unit (device_semiring.cuh) carries its own copy of every host helper that takes a kernel
+// pointer, whatever CUDA runtime instance it was linked with (a kernel handle is only valid in the runtime that registered it)
 template <class K>
-inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
+static inline int optin_smem(cbgpu_ctx_impl *ctx, K kernel, size_t bytes) {
   // static + dynamic shared memory above 48 KiB needs the opt-in; the kernels here also carry static workspaces
   if (bytes > 16 * 1024) CB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return CBGPU_OK;
@@ -416,6 +418,9 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   stats.nnz_out = nnzC;
   if (io.flops_out) *io.flops_out = stats.flops;
   if (io.nnz_out) *io.nnz_out = nnzC;
+  if (add_forbidden<SR>::value && io.C && nnzC != stats.flops) // BoolCopy1st/2ndSRing::add throws (Semirings.h:56-62)
+    return set_error(ctx, CBGPU_ERR_INVALID, "Add should not happen (BoolCopy semiring): %lld products for %lld outputs",
+                     (long long)stats.flops, (long long)nnzC);
 
   int rc = CBGPU_OK;
   cbgpu_mat_impl *Cm = nullptr;
@@ -466,11 +471,19 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     const int64_t dyn_s = sacc_dynamic_smem(ctx, kSaccThreadsS, kSaccBlocksS, sizeof(FlatQueueT<kSaccThreadsS>));
     const int64_t dyn_m = sacc_dynamic_smem(ctx, kSaccThreadsM, kSaccBlocksM, sizeof(FlatQueueT<kSaccThreadsM>));
     const int64_t dyn_l = sacc_dynamic_smem(ctx, kSaccThreadsL, kSaccBlocksL, sizeof(FlatQueueT<kSaccThreadsL>));
-    auto cap_of = [&](int64_t dyn) -> int64_t {
-      const int64_t c = (dyn - (int64_t)bm_bytes) / (int64_t)sizeof(acc_t);
+    // second version of the kernel (option sacc_v2, bit per shape): 16-bit ranks, and for the small and medium shape (bit 3: the
+    // large one too, bit 4: not the medium one) a row array beside the accumulators; needs max_words <= 16 * THREADS (vector scan)
+    const bool v2_s = (opt.sacc_v2 & 1) && max_words <= 16 * kSaccThreadsS, v2_m = (opt.sacc_v2 & 2) && max_words <= 16 * kSaccThreadsM,
+               v2_l = (opt.sacc_v2 & 4) && max_words <= 16 * kSaccThreadsL;
+    const bool rbw_s = true, rbw_m = !(opt.sacc_v2 & 16), rbw_l = (opt.sacc_v2 & 8) != 0;
+    auto cap_of = [&](int64_t dyn, bool v2, bool rbw) -> int64_t {
+      int64_t c = (dyn - (int64_t)bm_bytes) / (int64_t)sizeof(acc_t);
+      if (v2) // 256 bytes of the budget go to the static workspace the second version adds (64-bit warp totals, the mbarrier)
+        c = std::min<int64_t>(((dyn - 256 - (int64_t)max_words * 6) / (int64_t)(sizeof(acc_t) + (rbw ? 4 : 0))) & ~(int64_t)3, 65532);
       return (opt.shared_acc && c >= 64) ? c : 0;
     };
-    int64_t cap_s = cap_of(dyn_s), cap_m = cap_of(dyn_m), cap_l = cap_of(dyn_l);
+    const int64_t lay_s = cap_of(dyn_s, v2_s, rbw_s), lay_m = cap_of(dyn_m, v2_m, rbw_m), lay_l = cap_of(dyn_l, v2_l, rbw_l);
+    int64_t cap_s = lay_s, cap_m = lay_m, cap_l = lay_l;
     if (opt.shared_acc_max > 0) // tests and tuning: shrink the three capacities together so that small inputs reach every shape
       cap_l = std::min(cap_l, opt.shared_acc_max), cap_m = std::min(cap_m, opt.shared_acc_max / 2), cap_s = std::min(cap_s, opt.shared_acc_max / 4);
     if (opt.shared_acc_small_max >= 0) cap_s = std::min(cap_s, opt.shared_acc_small_max);
@@ -512,31 +525,55 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       stats.nnz_bitmap_gmem = class_weight(nb, num_class, NUM_BM_G, true);
     }
     // bitmap, accumulators in shared memory (exchange protocol): three CTA shapes by output count
-    if (nc.count[NUM_SA_L] > 0) {
-      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false>;
-      CB_TRY(optin_smem(ctx, kern, (size_t)dyn_l));
-      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
-      kern<<<(unsigned)nc.count[NUM_SA_L], kSaccThreadsL, (size_t)dyn_l, st>>>(src, recs + nc.begin[NUM_SA_L], io.m, max_words, Cm->ir, Cval,
-                                                                              saved, max_words);
+    // second version: same task records and shared-memory budget, its own layout (capacity lay_*)
+    auto launch_v2 = [&](auto kern, int cls, int threads, int64_t dyn, int64_t lay) -> int {
+      CB_TRY(optin_smem(ctx, kern, (size_t)dyn - 256));
+      kern<<<(unsigned)nc.count[cls], threads, (size_t)dyn - 256, st>>>(src, recs + nc.begin[cls], io.m, max_words, (int)lay, Cm->ir, Cval,
+                                                                       saved, max_words);
       CB_LAUNCH_CHECK(ctx);
+      return CBGPU_OK;
+    };
+    if (nc.count[NUM_SA_L] > 0) {
+      CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
+      if (v2_l && rbw_l) {
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false, true>, NUM_SA_L, kSaccThreadsL, dyn_l, lay_l));
+      } else if (v2_l) {
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false, false>, NUM_SA_L, kSaccThreadsL, dyn_l, lay_l));
+      } else {
+        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false>;
+        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_l));
+        kern<<<(unsigned)nc.count[NUM_SA_L], kSaccThreadsL, (size_t)dyn_l, st>>>(src, recs + nc.begin[NUM_SA_L], io.m, max_words, Cm->ir,
+                                                                                Cval, saved, max_words);
+        CB_LAUNCH_CHECK(ctx);
+      }
       CB_KEND(CBGPU_K_NUM_BITMAP_SMEM);
     }
     if (nc.count[NUM_SA_M] > 0) {
-      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, true>; // compression 1.6: most slots see one product
-      CB_TRY(optin_smem(ctx, kern, (size_t)dyn_m));
       CB_KBEGIN(CBGPU_K_NUM_SACC_M);
-      kern<<<(unsigned)nc.count[NUM_SA_M], kSaccThreadsM, (size_t)dyn_m, st>>>(src, recs + nc.begin[NUM_SA_M], io.m, max_words, Cm->ir, Cval,
-                                                                              saved, max_words);
-      CB_LAUNCH_CHECK(ctx);
+      if (v2_m && rbw_m) {
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, true, true>, NUM_SA_M, kSaccThreadsM, dyn_m, lay_m));
+      } else if (v2_m) {
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, true, false>, NUM_SA_M, kSaccThreadsM, dyn_m, lay_m));
+      } else {
+        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsM, kSaccBlocksM, true>; // compression 1.6: most slots see one product
+        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_m));
+        kern<<<(unsigned)nc.count[NUM_SA_M], kSaccThreadsM, (size_t)dyn_m, st>>>(src, recs + nc.begin[NUM_SA_M], io.m, max_words, Cm->ir,
+                                                                                Cval, saved, max_words);
+        CB_LAUNCH_CHECK(ctx);
+      }
       CB_KEND(CBGPU_K_NUM_SACC_M);
     }
     if (nc.count[NUM_SA_S] > 0) {
-      auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsS, kSaccBlocksS, true>;
-      CB_TRY(optin_smem(ctx, kern, (size_t)dyn_s));
       CB_KBEGIN(CBGPU_K_NUM_SACC_S);
-      kern<<<(unsigned)nc.count[NUM_SA_S], kSaccThreadsS, (size_t)dyn_s, st>>>(src, recs + nc.begin[NUM_SA_S], io.m, max_words, Cm->ir, Cval,
-                                                                              saved, max_words);
-      CB_LAUNCH_CHECK(ctx);
+      if (v2_s) {
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsS, kSaccBlocksS, true, rbw_s>, NUM_SA_S, kSaccThreadsS, dyn_s, lay_s));
+      } else {
+        auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsS, kSaccBlocksS, true>;
+        CB_TRY(optin_smem(ctx, kern, (size_t)dyn_s));
+        kern<<<(unsigned)nc.count[NUM_SA_S], kSaccThreadsS, (size_t)dyn_s, st>>>(src, recs + nc.begin[NUM_SA_S], io.m, max_words, Cm->ir,
+                                                                                Cval, saved, max_words);
+        CB_LAUNCH_CHECK(ctx);
+      }
       CB_KEND(CBGPU_K_NUM_SACC_S);
     }
     {

@@ -210,4 +210,36 @@ struct Semiring<8> {
   __device__ static __forceinline__ acc_t from_out(out_t v) { return v; }
 };
 
+// 9..14: BoolCopy2ndSRing<OUT> / BoolCopy1stSRing<OUT> (Semirings.h:51-138), the pair SpParMat::SubsRef_SR multiplies with
+// (S * A * T with boolean selection matrices, SpParMat.cpp:2515-2566): multiply copies the non-boolean operand, and add
+// "should not happen" -- the reference throws from it, because a selection matrix has one entry per row / column and every
+// output therefore receives exactly one product. The device path stores the product (bit-exact, no arithmetic); the engine
+// and the merge compare products with outputs afterwards and fail with the reference's message if an add would have happened.
+template <class A, class B, class ACC, class OUT, bool SECOND>
+struct BoolCopySemiring {
+  typedef A a_t; typedef B b_t; typedef ACC acc_t; typedef OUT out_t;
+  static constexpr bool kAddForbidden = true;
+  __device__ static __forceinline__ acc_t mul(a_t a, b_t b) { return SECOND ? (acc_t)b : (acc_t)a; }
+  __device__ static __forceinline__ acc_t identity() { return acc_t(); } // OUT(): BoolCopy*SRing::id()
+  __device__ static __forceinline__ void accumulate(acc_t *p, acc_t v) { *p = v; }
+  __device__ static __forceinline__ void accumulate_out(out_t *p, acc_t v) { *p = (out_t)v; }
+  __device__ static __forceinline__ out_t add(out_t, out_t b) { return b; } // unreachable in a valid product
+  __device__ static __forceinline__ acc_t acc_add(acc_t, acc_t b) { return b; }
+  template <bool FIRST> __device__ static __forceinline__ void accumulate_shared(acc_t *p, acc_t v) { *p = v; }
+  __device__ static __forceinline__ out_t to_out(acc_t v) { return (out_t)v; }
+  __device__ static __forceinline__ acc_t from_out(out_t v) { return (acc_t)v; }
+};
+template <> struct Semiring<9> : BoolCopySemiring<uint8_t, double, double, double, true> {};                    // BoolCopy2ndSRing<double>
+template <> struct Semiring<10> : BoolCopySemiring<double, uint8_t, double, double, false> {};                  // BoolCopy1stSRing<double>
+template <> struct Semiring<11> : BoolCopySemiring<uint8_t, long long, long long, long long, true> {};          // BoolCopy2ndSRing<int64_t>
+template <> struct Semiring<12> : BoolCopySemiring<long long, uint8_t, long long, long long, false> {};         // BoolCopy1stSRing<int64_t>
+template <> struct Semiring<13> : BoolCopySemiring<uint8_t, uint8_t, unsigned int, uint8_t, true> {};           // BoolCopy2ndSRing<bool>
+template <> struct Semiring<14> : BoolCopySemiring<uint8_t, uint8_t, unsigned int, uint8_t, false> {};          // BoolCopy1stSRing<bool>
+
+// semirings whose add must never run (kAddForbidden): checked by the host code after the symbolic pass / the merge count
+template <class SR, class = void>
+struct add_forbidden : std::false_type {};
+template <class SR>
+struct add_forbidden<SR, typename std::enable_if<SR::kAddForbidden>::type> : std::true_type {};
+
 } // namespace cbgpu

@@ -29,6 +29,13 @@ OrAndSRing_bool = 5
 PlusTimesSRing_bool_f64 = 6
 PlusTimesSRing_i32 = 7
 SelectMaxSRing_i64 = 8
+# the indexing pair of SpParMat::SubsRef_SR (Semirings.h:51-138): add must not happen
+BoolCopy2ndSRing_f64 = 9
+BoolCopy1stSRing_f64 = 10
+BoolCopy2ndSRing_i64 = 11
+BoolCopy1stSRing_i64 = 12
+BoolCopy2ndSRing_bool = 13
+BoolCopy1stSRing_bool = 14
 
 SEMIRINGS = {
     0: ("PlusTimesSRing<double,double>", np.float64, np.float64, np.float64),
@@ -40,6 +47,12 @@ SEMIRINGS = {
     6: ("PlusTimesSRing<bool,double>", np.uint8, np.float64, np.float64),
     7: ("PlusTimesSRing<int32_t,int32_t>", np.int32, np.int32, np.int32),
     8: ("SelectMaxSRing<int64_t,int64_t>", np.int64, np.int64, np.int64),
+    9: ("BoolCopy2ndSRing<double>", np.uint8, np.float64, np.float64),
+    10: ("BoolCopy1stSRing<double>", np.float64, np.uint8, np.float64),
+    11: ("BoolCopy2ndSRing<int64_t>", np.uint8, np.int64, np.int64),
+    12: ("BoolCopy1stSRing<int64_t>", np.int64, np.uint8, np.int64),
+    13: ("BoolCopy2ndSRing<bool>", np.uint8, np.uint8, np.uint8),
+    14: ("BoolCopy1stSRing<bool>", np.uint8, np.uint8, np.uint8),
 }
 
 

@@ -156,6 +156,7 @@ SIGNATURES = {
     "cbgpu_phase_columns": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cbgpu_spgemm_symbolic_columns": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "cbgpu_mat_transpose": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "cbgpu_mat_validate": (C.c_int, [_P, _P]),
     "cbgpu_redistribute": (C.c_int, [_P, _P, _P, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "cbgpu_memory_in_use": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "cbgpu_summa_symbolic": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -367,6 +368,10 @@ class Context:
         f, z = C.c_int64(), C.c_int64()
         self._check(self.lib.cbgpu_spgemm_symbolic(self.handle, A.handle, B.handle, C.byref(f), C.byref(z)))
         return f.value, z.value
+
+    def validate(self, D: DeviceMatrix) -> None:
+        """structural check of a resident block on the device (cbgpu_mat_validate); raises CbgpuError naming what is wrong"""
+        self._check(self.lib.cbgpu_mat_validate(self.handle, D.handle))
 
     def transpose(self, D: DeviceMatrix) -> DeviceMatrix:
         h = _P()

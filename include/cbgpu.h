@@ -50,7 +50,16 @@ typedef enum {
   CBGPU_SR_PLUS_TIMES_BOOL_F64 = 6, /* PlusTimesSRing<bool,double>     bool x f64 -> f64 */
   CBGPU_SR_PLUS_TIMES_I32 = 7,      /* PlusTimesSRing<int32,int32>     i32 x i32 -> i32 */
   CBGPU_SR_SELECT_MAX_I64 = 8,      /* SelectMaxSRing<int64,int64>     i64 x i64 -> i64 */
-  CBGPU_SR_COUNT = 9,
+  /* BoolCopy2ndSRing<OUT> / BoolCopy1stSRing<OUT> (Semirings.h:51-138): the pair SpParMat::SubsRef_SR multiplies with
+   * (SpParMat.cpp:2515-2566). multiply copies the non-boolean operand; add must not happen (the reference throws): a product
+   * or merge in which an output would receive two values fails with CBGPU_ERR_INVALID. */
+  CBGPU_SR_BOOL_COPY_2ND_F64 = 9,   /* bool x f64 -> f64 */
+  CBGPU_SR_BOOL_COPY_1ST_F64 = 10,  /* f64 x bool -> f64 */
+  CBGPU_SR_BOOL_COPY_2ND_I64 = 11,  /* bool x i64 -> i64 */
+  CBGPU_SR_BOOL_COPY_1ST_I64 = 12,  /* i64 x bool -> i64 */
+  CBGPU_SR_BOOL_COPY_2ND_BOOL = 13, /* bool x bool -> bool */
+  CBGPU_SR_BOOL_COPY_1ST_BOOL = 14, /* bool x bool -> bool */
+  CBGPU_SR_COUNT = 15,
   /* ids from here on belong to user-defined semirings: structs with the reference's semiring interface (static id / add /
    * multiply, Semirings.h:143-255) whose members are __host__ __device__, instantiated into the engine by a translation
    * unit of the application (include/combblas_b200/device_semiring.cuh) and registered when that unit is loaded */
@@ -134,7 +143,8 @@ int cbgpu_memory_in_use(cbgpu_ctx *ctx, int64_t *live_bytes);
  * "bitmap_min_nnz" smallest task the bitmap path takes, "light_max" products up to which a column stays one task,
  * "shared_acc" / "shared_acc_max" / "shared_acc_small_max" shared-memory accumulator classes, "bitmap_save_mb" /
  * "bitmap_save_min_flop" symbolic -> numeric hand-over, "bitmap_cta_threads", "bitmap_small_threads", "force_path" (tests:
- * 1 hash only, 2 bitmap only), "regsort" (1: tasks with <= 256 products and segments sorted in registers), "merge_engine",
+ * 1 hash only, 2 bitmap only), "regsort" (1: tasks with <= 256 products and segments sorted in registers), "sacc_v2" (bit per CTA shape: second
+ * version of the shared-accumulator kernels), "merge_engine", "merge_tma" (streaming merge with bulk tile copies), "validate_uploads",
  * "summa_fused", "fiber_fused", "fiber_pipeline" */
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value);
 int cbgpu_get_option(cbgpu_ctx *ctx, const char *name, int64_t *value);
@@ -145,6 +155,12 @@ int64_t cbgpu_launch_count(const cbgpu_ctx *ctx);
  * replaces: SpDCCols::CreateImpl / GetArrays (SpDCCols.cpp:735,:827) as the thing BCastMatrix moves,
  * and the tuples->DCSC constructor SpDCCols(const SpTuples&, bool) (SpDCCols.cpp:110-189). */
 int cbgpu_mat_upload(cbgpu_ctx *ctx, const cbgpu_dcsc_view *host, cbgpu_mat **out);
+/* Structural check of a resident block on the device: column pointers ascending from 0 to nnz, listed columns non-empty,
+ * column ids ascending and < n, row ids in [0, m) and strictly ascending inside every column -- what the engine's window
+ * searches and the streaming merge assume, and what reference blocks from the sort=false paths (mtSpGEMM.h:434) or a
+ * hand-built SpDCCols may violate. CBGPU_ERR_INVALID + a message naming what is wrong. Option "validate_uploads" = 1 runs
+ * it inside every cbgpu_mat_upload (the overlay sets it when CBGPU_VALIDATE is in the environment). */
+int cbgpu_mat_validate(cbgpu_ctx *ctx, const cbgpu_mat *M);
 /* adopt DEVICE arrays laid out as plain CSC: colptr int64[n+1], rows int32[nnz] ascending per column,
  * vals dtype[nnz]. Arrays are copied into library-owned storage (the caller keeps its buffers). */
 int cbgpu_mat_from_device_csc(cbgpu_ctx *ctx, int64_t m, int64_t n, int64_t nnz, const int64_t *colptr,

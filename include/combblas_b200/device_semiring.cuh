@@ -9,7 +9,9 @@
 // entry points with libcbgpu.so under a fresh semiring id when the exported symbol is first called.
 //
 // Compile:  nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -shared \
-//                -I<repo>/include my_semiring.cu -L<repo>/combblas_b200 -lcbgpu -o libmy_semiring.so
+//                --cudart shared -I<repo>/include my_semiring.cu -L<repo>/combblas_b200 -lcbgpu -o libmy_semiring.so
+// (--cudart shared: libcbgpu.so uses the shared CUDA runtime; one runtime instance per process keeps kernel handles, streams
+// and events of both libraries in one place)
 // The engine headers are internal to the library: rebuild this unit whenever libcbgpu.so is rebuilt (CBGPU_VERSION is checked).
 #pragma once
 #include "semiring_decl.h"

@@ -49,11 +49,20 @@ template <> struct semiring_id<combblas::PlusTimesSRing<bool, double>> { static 
 template <> struct semiring_id<combblas::SelectMaxSRing<bool, int64_t>> { static constexpr int value = CBGPU_SR_SELECT_MAX_BOOL_I64; };
 template <> struct semiring_id<combblas::SelectMaxSRing<int64_t, int64_t>> { static constexpr int value = CBGPU_SR_SELECT_MAX_I64; };
 template <> struct semiring_id<combblas::MinPlusSRing<double, double>> { static constexpr int value = CBGPU_SR_MIN_PLUS_F64; };
+// the indexing pair of SpParMat::SubsRef_SR (SpParMat.cpp:2515-2566): add must not happen, the device path checks it
+template <> struct semiring_id<combblas::BoolCopy2ndSRing<double>> { static constexpr int value = CBGPU_SR_BOOL_COPY_2ND_F64; };
+template <> struct semiring_id<combblas::BoolCopy1stSRing<double>> { static constexpr int value = CBGPU_SR_BOOL_COPY_1ST_F64; };
+template <> struct semiring_id<combblas::BoolCopy2ndSRing<int64_t>> { static constexpr int value = CBGPU_SR_BOOL_COPY_2ND_I64; };
+template <> struct semiring_id<combblas::BoolCopy1stSRing<int64_t>> { static constexpr int value = CBGPU_SR_BOOL_COPY_1ST_I64; };
+template <> struct semiring_id<combblas::BoolCopy2ndSRing<bool>> { static constexpr int value = CBGPU_SR_BOOL_COPY_2ND_BOOL; };
+template <> struct semiring_id<combblas::BoolCopy1stSRing<bool>> { static constexpr int value = CBGPU_SR_BOOL_COPY_1ST_BOOL; };
 
 constexpr int sr_types[CBGPU_SR_COUNT][3] = {
     {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_F32, CBGPU_F32, CBGPU_F32},  {CBGPU_I64, CBGPU_I64, CBGPU_I64},
     {CBGPU_BOOL, CBGPU_I64, CBGPU_I64}, {CBGPU_F64, CBGPU_F64, CBGPU_F64}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL},
-    {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_I32, CBGPU_I32, CBGPU_I32}, {CBGPU_I64, CBGPU_I64, CBGPU_I64}};
+    {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_I32, CBGPU_I32, CBGPU_I32}, {CBGPU_I64, CBGPU_I64, CBGPU_I64},
+    {CBGPU_BOOL, CBGPU_F64, CBGPU_F64}, {CBGPU_F64, CBGPU_BOOL, CBGPU_F64}, {CBGPU_BOOL, CBGPU_I64, CBGPU_I64},
+    {CBGPU_I64, CBGPU_BOOL, CBGPU_I64}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL}, {CBGPU_BOOL, CBGPU_BOOL, CBGPU_BOOL}};
 
 // value types the device instantiation of SR works on: the library's table, or what CBGPU_DECLARE_SEMIRING stated
 template <class SR, int WHICH>
@@ -99,6 +108,9 @@ inline cbgpu_ctx *context() {
       std::fprintf(stderr, "[cbgpu overlay] no usable GPU (status %d); the device path has no CPU fallback\n", rc);
       MPI_Abort(MPI_COMM_WORLD, INVALIDPARAMS);
     }
+    // CBGPU_VALIDATE: every block handed to the device is checked there first (sorted, in-range rows; cbgpu_mat_validate) --
+    // reference blocks from the sort=false paths are legal on the host and wrong on the device
+    if (std::getenv("CBGPU_VALIDATE")) cbgpu_set_option(ctx, "validate_uploads", 1);
   }
   return ctx;
 }
@@ -292,6 +304,26 @@ SpParMat<IU, NUO, UDERO> Mult_AnXBn_Synch(SpParMat<IU, NU1, UDERA> &A, SpParMat<
   cbgpu_mat_free(ctx, dA);
   cbgpu_mat_free(ctx, dB);
   return SpParMat<IU, NUO, UDERO>(ov::block_of<UDERO>(ctx, dC), GridC);
+}
+
+// ---- Mult_AnXBn_DoubleBuff (ParFriends.h:1238-1440; what SpParMat::SubsRef_SR calls with the BoolCopy semirings,
+// SpParMat.cpp:2515-2566) and Mult_AnXBn_Overlap (:1562-1690, "not stable" in the reference). Both compute the same product
+// as Mult_AnXBn_Synch and differ only in how the host overlaps its broadcasts with its multiplies (split halves / Ibcast).
+// On the device the stages of a SUMMA are one stacked multiply after device-to-device broadcasts that cost 0.5-2 % of a
+// step, so all three names reach the same entry.
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+  requires cbgpu_overlay::dist_supported<SR, NUO, UDERO, NU1, NU2, UDERA, UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_DoubleBuff(SpParMat<IU, NU1, UDERA> &A, SpParMat<IU, NU2, UDERB> &B, bool clearA = false,
+                                               bool clearB = false) {
+  if (cbgpu_overlay::disabled()) return Mult_AnXBn_DoubleBuff<cbgpu_overlay::cpu_only<SR>, NUO, UDERO>(A, B, clearA, clearB);
+  return Mult_AnXBn_Synch<SR, NUO, UDERO>(A, B, clearA, clearB);
+}
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+  requires cbgpu_overlay::dist_supported<SR, NUO, UDERO, NU1, NU2, UDERA, UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_Overlap(SpParMat<IU, NU1, UDERA> &A, SpParMat<IU, NU2, UDERB> &B, bool clearA = false,
+                                            bool clearB = false) {
+  if (cbgpu_overlay::disabled()) return Mult_AnXBn_Overlap<cbgpu_overlay::cpu_only<SR>, NUO, UDERO>(A, B, clearA, clearB);
+  return Mult_AnXBn_Synch<SR, NUO, UDERO>(A, B, clearA, clearB);
 }
 
 // ---- MemEfficientSpGEMM (ParFriends.h:452-777): HipMCL's expansion. Column phases of B, every finished piece of C pruned on the

@@ -43,10 +43,18 @@ SR_DTYPES = {
     6: (np.uint8, np.float64, np.float64),
     7: (np.int32, np.int32, np.int32),
     8: (np.int64, np.int64, np.int64),
+    9: (np.uint8, np.float64, np.float64),
+    10: (np.float64, np.uint8, np.float64),
+    11: (np.uint8, np.int64, np.int64),
+    12: (np.int64, np.uint8, np.int64),
+    13: (np.uint8, np.uint8, np.uint8),
+    14: (np.uint8, np.uint8, np.uint8),
 }
 SR_NAMES = {
     0: "PlusTimes<f64>", 1: "PlusTimes<f32>", 2: "PlusTimes<i64>", 3: "SelectMax<bool,i64>", 4: "MinPlus<f64>",
     5: "OrAnd<bool>", 6: "PlusTimes<bool,f64>", 7: "PlusTimes<i32>", 8: "SelectMax<i64>",
+    9: "BoolCopy2nd<f64>", 10: "BoolCopy1st<f64>", 11: "BoolCopy2nd<i64>", 12: "BoolCopy1st<i64>", 13: "BoolCopy2nd<bool>",
+    14: "BoolCopy1st<bool>",
 }
 
 # reference routines (oracle/ref_oracle.h)

@@ -59,6 +59,18 @@ typedef bool NT1; typedef double NT2; typedef double NTO; typedef PlusTimesSRing
 typedef int32_t NT1; typedef int32_t NT2; typedef int32_t NTO; typedef PlusTimesSRing<int32_t, int32_t> SR;
 #elif CB_SR == 8
 typedef int64_t NT1; typedef int64_t NT2; typedef int64_t NTO; typedef SelectMaxSRing<int64_t, int64_t> SR;
+#elif CB_SR == 9 /* the indexing pair of SpParMat::SubsRef_SR (SpParMat.cpp:2515-2566); their add throws */
+typedef bool NT1; typedef double NT2; typedef double NTO; typedef BoolCopy2ndSRing<double> SR;
+#elif CB_SR == 10
+typedef double NT1; typedef bool NT2; typedef double NTO; typedef BoolCopy1stSRing<double> SR;
+#elif CB_SR == 11
+typedef bool NT1; typedef int64_t NT2; typedef int64_t NTO; typedef BoolCopy2ndSRing<int64_t> SR;
+#elif CB_SR == 12
+typedef int64_t NT1; typedef bool NT2; typedef int64_t NTO; typedef BoolCopy1stSRing<int64_t> SR;
+#elif CB_SR == 13
+typedef bool NT1; typedef bool NT2; typedef bool NTO; typedef BoolCopy2ndSRing<bool> SR;
+#elif CB_SR == 14
+typedef bool NT1; typedef bool NT2; typedef bool NTO; typedef BoolCopy1stSRing<bool> SR;
 #else
 #error "unknown CB_SR"
 #endif
@@ -250,12 +262,15 @@ int cblas_splits = 1; /* every CombBLAS program defines this (CombBLAS.h:76) */
   extern "C" int ref_memeff_prune_sr##i(const ref_csc *, const ref_csc *, int, double, int64_t, int64_t, double, int, int, \
                                         ref_result **);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7) DECL(8)
+DECL(9) DECL(10) DECL(11) DECL(12) DECL(13) DECL(14)
 #define CASE(i, call) case i: return call;
 #define ALL(fn, ...)                                                                                                   \
   switch (semiring) {                                                                                                  \
     case 0: return fn##0(__VA_ARGS__); case 1: return fn##1(__VA_ARGS__); case 2: return fn##2(__VA_ARGS__);           \
     case 3: return fn##3(__VA_ARGS__); case 4: return fn##4(__VA_ARGS__); case 5: return fn##5(__VA_ARGS__);           \
     case 6: return fn##6(__VA_ARGS__); case 7: return fn##7(__VA_ARGS__); case 8: return fn##8(__VA_ARGS__);           \
+    case 9: return fn##9(__VA_ARGS__); case 10: return fn##10(__VA_ARGS__); case 11: return fn##11(__VA_ARGS__);       \
+    case 12: return fn##12(__VA_ARGS__); case 13: return fn##13(__VA_ARGS__); case 14: return fn##14(__VA_ARGS__);     \
     default: return -3;                                                                                                \
   }
 

@@ -117,6 +117,18 @@ static inline double f64_min(double a, double b) { return b < a ? b : a; }      
 static inline uint8_t bool_and(uint8_t a, uint8_t b) { return (uint8_t)(a && b); }
 static inline uint8_t bool_or(uint8_t a, uint8_t b) { return (uint8_t)(a || b); }
 static inline double boolf64_mul(uint8_t a, double b) { return (double)(a != 0) * b; }
+/* BoolCopy2ndSRing<OUT> / BoolCopy1stSRing<OUT> (Semirings.h:51-138): multiply copies the non-boolean operand; add prints
+ * "Add should not happen" and throws. Here add raises a flag and the entry point returns -2 (the reference aborts). */
+static volatile int bool_copy_add_happened = 0;
+static inline double copy2nd_f64(uint8_t a, double b) { (void)a; return b; }
+static inline double copy1st_f64(double a, uint8_t b) { (void)b; return a; }
+static inline int64_t copy2nd_i64(uint8_t a, int64_t b) { (void)a; return b; }
+static inline int64_t copy1st_i64(int64_t a, uint8_t b) { (void)b; return a; }
+static inline uint8_t copy2nd_u8(uint8_t a, uint8_t b) { (void)a; return b; }
+static inline uint8_t copy1st_u8(uint8_t a, uint8_t b) { (void)b; return a; }
+static inline double forbidden_f64(double a, double b) { (void)a; bool_copy_add_happened = 1; return b; }
+static inline int64_t forbidden_i64(int64_t a, int64_t b) { (void)a; bool_copy_add_happened = 1; return b; }
+static inline uint8_t forbidden_u8(uint8_t a, uint8_t b) { (void)a; bool_copy_add_happened = 1; return b; }
 
 typedef struct { int64_t key; int64_t slot; } keyslot;
 static int cmp_keyslot(const void *x, const void *y) {
@@ -223,8 +235,15 @@ DEFINE_SPGEMM(sr5, uint8_t, uint8_t, uint8_t, bool_and, bool_or)
 DEFINE_SPGEMM(sr6, uint8_t, double, double, boolf64_mul, f64_add)
 DEFINE_SPGEMM(sr7, int32_t, int32_t, int32_t, i32_mul, i32_add)
 DEFINE_SPGEMM(sr8, int64_t, int64_t, int64_t, i64_mul, i64_max)
+DEFINE_SPGEMM(sr9, uint8_t, double, double, copy2nd_f64, forbidden_f64)
+DEFINE_SPGEMM(sr10, double, uint8_t, double, copy1st_f64, forbidden_f64)
+DEFINE_SPGEMM(sr11, uint8_t, int64_t, int64_t, copy2nd_i64, forbidden_i64)
+DEFINE_SPGEMM(sr12, int64_t, uint8_t, int64_t, copy1st_i64, forbidden_i64)
+DEFINE_SPGEMM(sr13, uint8_t, uint8_t, uint8_t, copy2nd_u8, forbidden_u8)
+DEFINE_SPGEMM(sr14, uint8_t, uint8_t, uint8_t, copy1st_u8, forbidden_u8)
 
-static const int OUT_BYTES[9] = {8, 4, 8, 8, 8, 1, 8, 4, 8};
+#define PORT_SR_COUNT 15
+static const int OUT_BYTES[PORT_SR_COUNT] = {8, 4, 8, 8, 8, 1, 8, 4, 8, 8, 8, 8, 8, 1, 1};
 
 static port_result *alloc_result(int64_t nnz, int vbytes) {
   port_result *r = (port_result *)calloc(1, sizeof(port_result));
@@ -245,7 +264,8 @@ static int64_t *exclusive_scan(const int64_t *in, int64_t n) {
 }
 
 int port_spgemm(int semiring, const port_csc *A, const port_csc *B, int sort, port_result **out, double *seconds) {
-  if (semiring < 0 || semiring > 8 || A->n != B->m) return -1;
+  if (semiring < 0 || semiring >= PORT_SR_COUNT || A->n != B->m) return -1;
+  bool_copy_add_happened = 0;
   double t0 = now_s();
   int64_t *flop = (int64_t *)malloc((size_t)(B->n + 1) * sizeof(int64_t));
   int64_t *nnz = (int64_t *)malloc((size_t)(B->n + 1) * sizeof(int64_t));
@@ -262,9 +282,16 @@ int port_spgemm(int semiring, const port_csc *A, const port_csc *B, int sort, po
     case 6: spgemm_sr6(A, B, sort, colptrC, r->rows, r->cols, (double *)r->vals); break;
     case 7: spgemm_sr7(A, B, sort, colptrC, r->rows, r->cols, (int32_t *)r->vals); break;
     case 8: spgemm_sr8(A, B, sort, colptrC, r->rows, r->cols, (int64_t *)r->vals); break;
+    case 9: spgemm_sr9(A, B, sort, colptrC, r->rows, r->cols, (double *)r->vals); break;
+    case 10: spgemm_sr10(A, B, sort, colptrC, r->rows, r->cols, (double *)r->vals); break;
+    case 11: spgemm_sr11(A, B, sort, colptrC, r->rows, r->cols, (int64_t *)r->vals); break;
+    case 12: spgemm_sr12(A, B, sort, colptrC, r->rows, r->cols, (int64_t *)r->vals); break;
+    case 13: spgemm_sr13(A, B, sort, colptrC, r->rows, r->cols, (uint8_t *)r->vals); break;
+    case 14: spgemm_sr14(A, B, sort, colptrC, r->rows, r->cols, (uint8_t *)r->vals); break;
   }
   free(flop); free(nnz); free(colptrC);
   if (seconds) *seconds = now_s() - t0;
+  if (bool_copy_add_happened) { port_result_free(r); return -2; } /* "Add should not happen" */
   *out = r;
   return 0;
 }
@@ -285,12 +312,19 @@ static int64_t merge_dispatch(int semiring, int k, const port_csc *lists, int so
     case 6: return MERGE_CALL(sr6, double, count_only, cp, cn, r);
     case 7: return MERGE_CALL(sr7, int32_t, count_only, cp, cn, r);
     case 8: return MERGE_CALL(sr8, int64_t, count_only, cp, cn, r);
+    case 9: return MERGE_CALL(sr9, double, count_only, cp, cn, r);
+    case 10: return MERGE_CALL(sr10, double, count_only, cp, cn, r);
+    case 11: return MERGE_CALL(sr11, int64_t, count_only, cp, cn, r);
+    case 12: return MERGE_CALL(sr12, int64_t, count_only, cp, cn, r);
+    case 13: return MERGE_CALL(sr13, uint8_t, count_only, cp, cn, r);
+    case 14: return MERGE_CALL(sr14, uint8_t, count_only, cp, cn, r);
   }
   return -1;
 }
 
 int port_merge(int semiring, int k, const port_csc *lists, int sort, port_result **out, double *seconds) {
-  if (semiring < 0 || semiring > 8 || k < 1) return -1;
+  if (semiring < 0 || semiring >= PORT_SR_COUNT || k < 1) return -1;
+  bool_copy_add_happened = 0;
   double t0 = now_s();
   int64_t n = lists[0].n;
   int64_t *colnnz = (int64_t *)malloc((size_t)(n + 1) * sizeof(int64_t));
@@ -300,6 +334,7 @@ int port_merge(int semiring, int k, const port_csc *lists, int sort, port_result
   merge_dispatch(semiring, k, lists, sort, 0, cp, NULL, r);
   free(colnnz); free(cp);
   if (seconds) *seconds = now_s() - t0;
+  if (bool_copy_add_happened) { port_result_free(r); return -2; } /* "Add should not happen" */
   *out = r;
   return 0;
 }

@@ -121,3 +121,44 @@ def test_empty_and_degenerate_inputs(port_oracle):
     y = Csc.from_coo(2, 1, [0, 1], [0, 0], np.array([1.0, 1.0]))
     c = port_oracle.spgemm(x, y, 0)
     assert c.nnz == 1 and c.vals[0] == 0.0
+
+
+@pytest.mark.parametrize("pair", [(9, 10, np.float64), (11, 12, np.int64), (13, 14, np.uint8)])
+def test_bool_copy_semirings_subsref(port_oracle, pair):
+    """BoolCopy2ndSRing / BoolCopy1stSRing (Semirings.h:51-138), the pair SpParMat::SubsRef_SR multiplies with: S*A*T with
+    boolean selectors equals A[ri][:, ci] entry for entry (explicit zeros and signs kept); the restatement equals the compiled
+    reference where that is present; a product in which an output would receive two values fails, as the reference's add throws"""
+    from tests.util import subsref_operands
+    from oracle.oracle import RefOracle
+
+    sr2, sr1, dt = pair
+    A, S, T, ri, ci = subsref_operands(300, 260, 180, 140, 5 + sr2, dt)
+    a, s_, t_ = to_csc(A, dt), to_csc(S, np.uint8), to_csc(T, np.uint8)
+    sa = port_oracle.spgemm(s_, a, sr2)
+    sat = port_oracle.spgemm(sa, t_, sr1)
+    dense = A.toarray()[ri][:, ci]
+    got = np.zeros(dense.shape)
+    got[sat.rows, sat.cols_expanded()] = sat.vals
+    assert np.array_equal(got, dense)
+    if RefOracle.available():
+        ref = RefOracle()
+        rsa = ref.spgemm(s_, a, sr2)
+        rsat = ref.spgemm(rsa, t_, sr1)
+        assert same_pattern(sa, rsa) and np.array_equal(sa.vals, rsa.vals)
+        assert same_pattern(sat, rsat) and np.array_equal(sat.vals, rsat.vals)
+    # a selector row with two entries on rows of A that share a column: the output needs add -> "Add should not happen"
+    X = sp_two_hits(A, 300)
+    with pytest.raises(RuntimeError):
+        port_oracle.spgemm(to_csc(X, np.uint8), a, sr2)
+
+
+def sp_two_hits(A, m):
+    """a 1 x m boolean row with two entries on rows of A that share a column: S*A then needs an add"""
+    import scipy.sparse as sp
+
+    Ac = A.tocsc()
+    col = int(np.argmax(np.diff(Ac.indptr)))
+    r0, r1 = Ac.indices[Ac.indptr[col]], Ac.indices[Ac.indptr[col] + 1]
+    X = sp.coo_matrix((np.ones(2), (np.zeros(2, int), np.array([r0, r1]))), shape=(1, m)).tocsc()
+    X.sort_indices()
+    return X

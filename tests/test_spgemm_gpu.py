@@ -125,6 +125,89 @@ def test_shared_accumulator_classes_every_semiring(ctx, oracle, sr):
         ctx.set_option("shared_acc_small_max", -1)
 
 
+@pytest.mark.parametrize("pair", [(9, 10, np.float64), (11, 12, np.int64), (13, 14, np.uint8)])
+def test_bool_copy_semirings_subsref(ctx, oracle, port_oracle, pair):
+    """BoolCopy2ndSRing / BoolCopy1stSRing (Semirings.h:51-138; SpParMat::SubsRef_SR, SpParMat.cpp:2515-2566): S*A and (S*A)*T
+    with boolean selectors against the oracle, bit for bit (explicit zeros and negative values are copied, not added to an
+    identity), through the hash / register-sort classes and through the bitmap classes; the stage merge of two disjoint row
+    halves; and the reference's "Add should not happen": a product or merge that would need add fails with CBGPU_ERR_INVALID"""
+    from tests.util import subsref_operands
+
+    sr2, sr1, dt = pair
+    A, S, T, ri, ci = subsref_operands(3000, 2600, 2200, 1900, 50 + sr2, dt)
+    a, s_, t_ = to_csc(A, dt), to_csc(S, np.uint8), to_csc(T, np.uint8)
+    want_sa = oracle.spgemm(s_, a, sr2)
+    want_sat = oracle.spgemm(want_sa, t_, sr1)
+    for force in (0, 2):
+        ctx.set_option("force_path", force)
+        try:
+            sa = cb.LocalHybridSpGEMM(ctx, sr2, to_dcsc(S, np.uint8), to_dcsc(A, dt))
+            assert_same(sa, want_sa, sr2)
+            sat = cb.LocalHybridSpGEMM(ctx, sr1, dcsc_of(want_sa), to_dcsc(T, np.uint8))
+            assert_same(sat, want_sat, sr1)
+        finally:
+            ctx.set_option("force_path", 0)
+    # SUMMA-stage style merge: the selector split by columns gives partial products with disjoint rows... of the same columns
+    half = S.shape[1] // 2
+    S0, S1 = S.tocsc()[:, :half], S.tocsc()[:, half:]
+    A0, A1 = A.tocsr()[:half].tocsc(), A.tocsr()[half:].tocsc()
+    for M in (S0, S1, A0, A1):
+        M.sort_indices()
+    p0 = port_oracle.spgemm(to_csc(S0, np.uint8), to_csc(A0, dt), sr2)
+    p1 = port_oracle.spgemm(to_csc(S1, np.uint8), to_csc(A1, dt), sr2)
+    for tma in (1, 0):
+        ctx.set_option("merge_tma", tma)
+        try:
+            assert_same(cb.MultiwayMerge(ctx, sr2, [dcsc_of(p0), dcsc_of(p1)]), want_sa, sr2)
+            if p0.nnz > 0:
+                with pytest.raises(cb.CbgpuError, match="Add should not happen"):
+                    cb.MultiwayMerge(ctx, sr2, [dcsc_of(p0), dcsc_of(p0)])
+        finally:
+            ctx.set_option("merge_tma", 1)
+    # a selector row with two entries on rows of A that share a column
+    Ac = A.tocsc()
+    col = int(np.argmax(np.diff(Ac.indptr)))
+    r0, r1 = Ac.indices[Ac.indptr[col]], Ac.indices[Ac.indptr[col] + 1]
+    X = sp.coo_matrix((np.ones(2), (np.zeros(2, int), np.array([r0, r1]))), shape=(1, A.shape[0])).tocsc()
+    X.sort_indices()
+    with pytest.raises(cb.CbgpuError, match="Add should not happen"):
+        cb.LocalHybridSpGEMM(ctx, sr2, to_dcsc(X, np.uint8), to_dcsc(A, dt))
+
+
+@pytest.mark.parametrize("v2", [7, 15, 23])
+@pytest.mark.parametrize("sr", range(9))
+def test_shared_accumulators_second_version(ctx, oracle, sr, v2):
+    """num_sacc2_kernel (option sacc_v2: 16-bit ranks, rows stored by the accumulate walk, vector scan, presence words fetched
+    by a bulk copy): all three CTA shapes, with and without the row array (bits 3 and 4), every semiring; one window and
+    several; hand-over forced for small tasks so that the bulk-copy branch runs"""
+    A = rmat(12, 16, seed=20 + sr)
+    ta, tb, _ = SR_DTYPES[sr]
+    want = oracle.spgemm(to_csc(typed(A, ta), ta), to_csc(typed(A, tb), tb), sr)
+    ctx.set_option("sacc_v2", v2)
+    ctx.set_option("force_path", 2)
+    try:
+        dA, dB = ctx.upload(to_dcsc(typed(A, ta), ta)), ctx.upload(to_dcsc(typed(A, tb), tb))
+        for (wlog2, cap, small, save_min) in ((17, 500, 120, 8192), (17, 0, -1, 64), (10, 400, 100, 64), (11, 0, -1, 8192)):
+            ctx.set_option("bitmap_window_log2", wlog2)
+            ctx.set_option("shared_acc_max", cap)
+            ctx.set_option("shared_acc_small_max", small)
+            ctx.set_option("bitmap_save_min_flop", save_min)
+            D, st = ctx.spgemm(sr, dA, dB, want_stats=True)
+            rows, cols, vals = ctx.download_coo(D)
+            assert_same(cb.SpTuples(A.shape[0], A.shape[1], rows, cols, vals), want, sr)
+            assert st.tasks_bitmap_smem > 0
+            D.free()
+        for x in (dA, dB):
+            x.free()
+    finally:
+        ctx.set_option("sacc_v2", 0)
+        ctx.set_option("force_path", 0)
+        ctx.set_option("bitmap_window_log2", 17)
+        ctx.set_option("shared_acc_max", 0)
+        ctx.set_option("shared_acc_small_max", -1)
+        ctx.set_option("bitmap_save_min_flop", 8192)
+
+
 @pytest.mark.parametrize("sr", [0, 2, 3, 4, 5, 7])
 def test_register_sort_runs_across_lanes(ctx, oracle, sr):
     """register-sort classes (engine.cuh regsort_kernel): r dense rows of A times a column of B with k entries gives r runs of k
@@ -278,6 +361,53 @@ def test_merge_large_columns_and_windows(ctx, port_oracle):
         got = cb.MultiwayMerge(ctx, 0, [dcsc_of(p) for p in parts])
         assert_same(got, want, 0)
     ctx.set_option("bitmap_window_log2", 17)
+
+
+@pytest.mark.parametrize("sr", [0, 1, 2, 5, 7])
+def test_streaming_merge_bulk_copies_every_value_width(ctx, port_oracle, sr):
+    """merge2_tma_kernel (persistent CTAs, double-buffered bulk copies in, bulk stores out) against the oracle and against the
+    one-tile-per-CTA kernel: value widths of 1, 4 and 8 bytes (the 16-byte phase of every part differs), columns of several
+    tiles next to empty and one-entry columns, duplicate pairs on tile and thread boundaries (dense columns in both lists)"""
+    ta, tb, _ = SR_DTYPES[sr]
+    A = rmat(13, 16, seed=81)
+    a = to_csc(typed(A, ta), ta)
+    parts = [port_oracle.spgemm(a, to_csc(typed(rmat(13, 6, seed=90 + i), tb), tb), sr) for i in range(3)]
+    want = port_oracle.merge(parts, sr)
+    got = {}
+    for tma in (1, 0):
+        ctx.set_option("merge_tma", tma)
+        try:
+            got[tma] = cb.MultiwayMerge(ctx, sr, [dcsc_of(p) for p in parts])
+        finally:
+            ctx.set_option("merge_tma", 1)
+        assert_same(got[tma], want, sr)
+    assert np.array_equal(got[0].rows, got[1].rows) and np.array_equal(got[0].cols, got[1].cols)
+
+
+def test_validate_rejects_blocks_the_engine_cannot_take(ctx):
+    """cbgpu_mat_validate / option validate_uploads: sorted, in-range blocks pass; unsorted rows (legal after the reference's
+    sort=false paths), rows >= m, broken column pointers and unordered column ids are named in the error"""
+    A = rmat(10, 8, seed=3)
+    good = to_dcsc(A, np.float64)
+    D = ctx.upload(good)
+    ctx.validate(D)
+    D.free()
+    ctx.set_option("validate_uploads", 1)
+    try:
+        ctx.upload(good).free()
+        col = int(np.argmax(np.diff(good.cp)))
+        b = int(good.cp[col])
+        for what, mutate in (("row ids not strictly ascending", lambda d: d.ir.__setitem__(slice(b, b + 2), d.ir[b:b + 2][::-1].copy())),
+                             ("row ids out of range", lambda d: d.ir.__setitem__(int(d.cp[col + 1]) - 1, d.m + 5)),
+                             ("column pointers", lambda d: d.cp.__setitem__(1, d.cp[2] + 1)),
+                             ("column ids", lambda d: d.jc.__setitem__(slice(0, 2), d.jc[0:2][::-1].copy()))):
+            bad = to_dcsc(A.copy(), np.float64)
+            bad.ir, bad.cp, bad.jc = bad.ir.copy(), bad.cp.copy(), bad.jc.copy()
+            mutate(bad)
+            with pytest.raises(cb.CbgpuError, match=what):
+                ctx.upload(bad)
+    finally:
+        ctx.set_option("validate_uploads", 0)
 
 
 def test_colsplit_concat_and_checksum(ctx):

@@ -69,3 +69,21 @@ def assert_same(got, want, sr, rtol=None):
         assert np.all(err <= tol * np.maximum(np.abs(got.vals), np.abs(want.vals)))
     else:
         assert np.array_equal(got.vals, want.vals), "values differ (bit-exact semiring)"
+
+
+def subsref_operands(m, n, nri, nci, seed, dt):
+    """Operands of SpParMat::SubsRef_SR (SpParMat.cpp:2515-2566): A (m x n, values of type dt), the boolean row selector
+    S (nri x m, S[i, ri[i]] = 1) and the boolean column selector T (n x nci, T[ci[j], j] = 1). ri / ci may repeat indices;
+    every entry of S*A and of (S*A)*T still receives exactly one product, which is what BoolCopy2nd/1stSRing rely on."""
+    rng = np.random.default_rng(seed)
+    A = sp.random(m, n, density=0.03, random_state=rng, format="csc")
+    A.data = np.floor(A.data * 1000) - 300.0  # negative values and zeros included: the product must copy them bit for bit
+    if np.dtype(dt) == np.uint8:
+        A.data = (A.data > 0).astype(np.float64)
+    ri = rng.integers(0, m, nri)
+    ci = rng.integers(0, n, nci)
+    S = sp.coo_matrix((np.ones(nri), (np.arange(nri), ri)), shape=(nri, m)).tocsc()
+    T = sp.coo_matrix((np.ones(nci), (ci, np.arange(nci))), shape=(n, nci)).tocsc()
+    for M in (A, S, T):
+        M.sort_indices()
+    return A, S, T, ri, ci

@@ -12,10 +12,12 @@ n = 1 << a.scale
 A0, A1 = ctx.submatrix(G, 0, n, 0, n // 2), ctx.submatrix(G, 0, n, n // 2, n)
 B0, B1 = ctx.submatrix(G, 0, n // 2, 0, n), ctx.submatrix(G, n // 2, n, 0, n)
 P0, P1 = ctx.spgemm(0, A0, B0), ctx.spgemm(0, A1, B1)
-for i in range(a.reps):
+for i in range(2 * a.reps):
+    tma = 1 if i < a.reps else 0
+    ctx.set_option("merge_tma", tma)
     M, st = ctx.merge(0, [P0, P1], want_stats=True)
     nin, nout = P0.nnz + P1.nnz, M.nnz
     bytes_alg = nin * 12 + nout * 12
-    print(f"merge2: in {nin} out {nout} ms {st.ms_total:.3f} (setup {st.ms_setup:.3f} count {st.ms_symbolic:.3f} write {st.ms_numeric:.3f}) "
+    print(f"merge2 tma={tma}: in {nin} out {nout} ms {st.ms_total:.3f} (setup {st.ms_setup:.3f} count {st.ms_symbolic:.3f} write {st.ms_numeric:.3f}) "
           f"algorithmic {bytes_alg/1e9:.2f} GB -> {bytes_alg/st.ms_total/1e6:.1f} GB/s", flush=True)
     M.free()
