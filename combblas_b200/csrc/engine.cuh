@@ -959,13 +959,17 @@ __device__ __forceinline__ T rs_shfl_up(unsigned mask, T v, int d, int width) {
   }
 }
 
-template <class SR, bool MERGE, int G, bool NUMERIC>
+// PACKED (numeric pass, blocks of fewer than 2^(32 - log2 CAP) rows): the network sorts row << log2(CAP) | staging position
+// -- one register per element instead of key + value -- and the values are fetched from the staging area afterwards.
+template <class SR, bool MERGE, int G, bool NUMERIC, bool PACKED = false>
 __global__ void __launch_bounds__(256, NUMERIC ? 4 : 6)
 regsort_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t *tasknnz, int32_t *Cir, typename SR::out_t *Cval) {
   typedef typename SR::acc_t acc_t;
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   typedef typename SR::b_t mult_t;
   constexpr int E = kRsItems, CAP = G * E, GROUPS = 256 / G;
+  constexpr int LOG2CAP = G == 8 ? 6 : (G == 16 ? 7 : 8);
+  constexpr bool SORT_VALS = NUMERIC && !PACKED; // values travel through the network
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned *skey_all = reinterpret_cast<unsigned *>(smem_raw);             // [GROUPS * CAP] = 2048 rows
   acc_t *sval_all = reinterpret_cast<acc_t *>(skey_all + GROUPS * CAP);    // [GROUPS * CAP] (numeric only)
@@ -1021,8 +1025,8 @@ regsort_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t 
 #pragma unroll
   for (int q = 0; q < E; ++q) {
     const int e = gl * E + q;
-    key[q] = e < P ? skey[e] : kRsPad;
-    if (NUMERIC) val[q] = e < P ? sval[e] : SR::identity();
+    key[q] = e < P ? (PACKED ? ((skey[e] << LOG2CAP) | (unsigned)e) : skey[e]) : kRsPad;
+    if (SORT_VALS) val[q] = e < P ? sval[e] : SR::identity();
   }
 #pragma unroll
   for (int kk = 2; kk <= CAP; kk <<= 1) {
@@ -1036,11 +1040,11 @@ regsort_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t 
         for (int q = 0; q < E; ++q) {
           const unsigned ok = __shfl_xor_sync(gmask, key[q], lj, G);
           acc_t ov;
-          if (NUMERIC) ov = rs_shfl_xor<acc_t>(gmask, val[q], lj, G);
+          if (SORT_VALS) ov = rs_shfl_xor<acc_t>(gmask, val[q], lj, G);
           const bool take = keep_min ? (ok < key[q]) : (ok > key[q]);
           if (take) {
             key[q] = ok;
-            if (NUMERIC) val[q] = ov;
+            if (SORT_VALS) val[q] = ov;
           }
         }
       } else { // partner in the same lane
@@ -1053,7 +1057,7 @@ regsort_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t 
               const unsigned tk = key[q];
               key[q] = key[p];
               key[p] = tk;
-              if (NUMERIC) {
+              if (SORT_VALS) {
                 const acc_t tv = val[q];
                 val[q] = val[p];
                 val[p] = tv;
@@ -1062,6 +1066,14 @@ regsort_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64_t 
           }
         }
       }
+    }
+  }
+  if (PACKED) { // rows back in place, values from the staging area by position
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const unsigned kq = key[q];
+      if (NUMERIC) val[q] = kq != kRsPad ? sval[kq & (unsigned)(CAP - 1)] : SR::identity();
+      key[q] = kq != kRsPad ? (kq >> LOG2CAP) : kRsPad;
     }
   }
   // ---- fold equal rows
@@ -1197,6 +1209,19 @@ __device__ __forceinline__ void bitmap_mark(const Source<SR, MERGE> &s, const Ta
 // warp_sums has 33 entries.
 template <bool RANKS>
 __device__ __forceinline__ int bitmap_scan(const unsigned *bits, unsigned *rank, int nword, int *warp_sums) {
+  if (!RANKS) { // count only: 16-byte loads, thread t takes vectors t, t + blockDim.x, ... (the array is padded to whole vectors)
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(bits);
+    const int nvec = (nword + 3) >> 2;
+    int mine = 0;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint4 w = b4[v];
+      mine += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+    }
+    block_exclusive_scan(mine, warp_sums, warp_sums + 32);
+    const int total = warp_sums[32];
+    __syncthreads();
+    return total;
+  }
   // every thread owns a contiguous run of words; an ODD run length keeps the lanes of a warp on different banks
   const int wpt = ((nword + blockDim.x - 1) / blockDim.x) | 1;
   const int c0 = min(nword, (int)threadIdx.x * wpt), c1 = min(nword, c0 + wpt);
@@ -1405,8 +1430,10 @@ num_sacc_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wor
 // -- although six words in seven are empty. This version
 //  * keeps the rank prefixes as 16-bit numbers (a task of these classes has < 65536 outputs): 8 KB less shared memory per task
 //    at 2^17-row windows, which pays for
-//  * a row array next to the accumulators: every product stores its row id at its slot (all products of a slot store the same
-//    value), so the sorted rows fall out of the accumulate walk and the unpack pass over the words disappears (ROWS_BY_WALK);
+//  * a 16-bit row array next to the accumulators: every product stores its row offset at its slot (all products of a slot store
+//    the same value), so the sorted rows fall out of the accumulate walk and the unpack pass over the words disappears
+//    (ROWS_BY_WALK); in the medium shape that pass was 22 % of all instructions executed (divergent: a warp iterates as often as
+//    its fullest word has bits; profiles/r2_ncu_sacc2_s22.txt);
 //  * scans the words with 16-byte loads, thread t taking vectors t, t + THREADS, ...: the up to four per-thread counts travel
 //    through ONE block scan as 16-bit fields of a 64-bit word, and the four ranks of a vector leave as one 8-byte store;
 //  * fetches handed-over presence words with one bulk copy of the TMA unit instead of a load/store loop of the whole CTA.
@@ -1414,12 +1441,13 @@ template <int THREADS>
 __device__ __forceinline__ void bitmap_scan16(const unsigned *bits, unsigned short *rank, int nword, unsigned long long *wtot /*[32]*/) {
   constexpr int nwarp = THREADS >> 5;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int nvec = (nword + 3) >> 2; // <= 4 * THREADS (checked by the host)
+  constexpr int J = (1024 + THREADS - 1) / THREADS; // vectors per thread: windows of at most 4096 words (checked by the host)
+  const int nvec = (nword + 3) >> 2;
   const uint4 *b4 = reinterpret_cast<const uint4 *>(bits);
-  uint4 w[4];
+  uint4 w[J];
   unsigned long long x = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < J; ++j) {
     const int v = j * THREADS + (int)threadIdx.x;
     w[j] = make_uint4(0u, 0u, 0u, 0u);
     if (v < nvec) w[j] = b4[v];
@@ -1444,7 +1472,7 @@ __device__ __forceinline__ void bitmap_scan16(const unsigned *bits, unsigned sho
   unsigned base = 0; // outputs of the vector blocks before block j
   uint2 *r2 = reinterpret_cast<uint2 *>(rank);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < J; ++j) {
     const int v = j * THREADS + (int)threadIdx.x;
     if (v < nvec) {
       const unsigned r0 = base + (unsigned)((excl >> (16 * j)) & 0xFFFFull);
@@ -1464,11 +1492,13 @@ num_sacc2_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wo
   typedef typename SR::out_t out_t;
   typedef typename Source<SR, MERGE>::aval_t aval_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: bits[max_words] u32 | acc[cap] acc_t | rows[cap] i32 (ROWS_BY_WALK) | rank[max_words] u16; cap is a multiple of 4
+  // layout: bits[max_words] u32 | acc[cap] acc_t | rows[cap] u16 (ROWS_BY_WALK) | rank[max_words] u16; cap is a multiple of 4.
+  // A row is kept as the low 16 bits of its offset in the window (at most 2^17 rows, checked by the host): outputs are sorted by
+  // row, so the 17th bit of output i is simply i >= (number of outputs in the lower 2^16 rows) = rank[2048].
   unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
   acc_t *acc = reinterpret_cast<acc_t *>(bits + max_words);
-  int32_t *srow = reinterpret_cast<int32_t *>(acc + cap);
-  unsigned short *rank = reinterpret_cast<unsigned short *>(ROWS_BY_WALK ? (void *)(srow + cap) : (void *)srow);
+  unsigned short *srow = reinterpret_cast<unsigned short *>(acc + cap);
+  unsigned short *rank = ROWS_BY_WALK ? srow + cap : srow;
   __shared__ FlatQueueT<THREADS> queue;
   __shared__ unsigned long long wtot[32];
   __shared__ __align__(8) unsigned long long bar;
@@ -1479,6 +1509,7 @@ num_sacc2_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wo
   const int64_t obase = r.obase;
   const int nnz = r.nnz;
   const bool restage = !MERGE && r.slot < 0 && r.nseg <= THREADS;
+  const int first = min(nnz, cap); // outputs of the first (usually only) pass
   if (r.slot >= 0) { // uniform per CTA: the presence words of the symbolic pass arrive as one bulk copy
     const unsigned bytes = (unsigned)((w.nword + 3) >> 2) * 16u;
     if (threadIdx.x == 0) {
@@ -1487,12 +1518,12 @@ num_sacc2_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wo
       mbar_arrive_expect_tx(&bar, bytes);
       bulk_load(bits, saved + (int64_t)r.slot * save_stride, bytes, &bar);
     }
-    for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity(); // while the words are in flight
+    for (int i = threadIdx.x; i < first; i += THREADS) acc[i] = SR::identity(); // while the words are in flight
     __syncthreads(); // the barrier is initialised for everybody
     mbar_wait(&bar, 0);
   } else {
     bitmap_mark(s, k, &queue, bits, w.nword, w.rbase, restage);
-    for (int i = threadIdx.x; i < nnz; i += THREADS) acc[i] = SR::identity();
+    for (int i = threadIdx.x; i < first; i += THREADS) acc[i] = SR::identity();
   }
   bitmap_scan16<THREADS>(bits, rank, w.nword, wtot); // ends with __syncthreads: ranks and identities in place
   if (!ROWS_BY_WALK) {
@@ -1507,20 +1538,35 @@ num_sacc2_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wo
       }
     }
   }
-  auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
-    const unsigned rr = (unsigned)(row - rbase);
-    const unsigned wd = rr >> 5;
-    const unsigned slot = (unsigned)rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (rr & 31u)) - 1u));
-    if (ROWS_BY_WALK) srow[slot] = row;
-    acc_t v;
-    if (MERGE) v = SR::from_out((out_t)aval);
-    else v = SR::mul((typename SR::a_t)aval, mu);
-    SR::template accumulate_shared<FIRST>(&acc[slot], v);
-  };
-  bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
-  if (ROWS_BY_WALK)
-    for (int i = threadIdx.x; i < nnz; i += THREADS) Cir[obase + i] = srow[i];
-  for (int i = threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(acc[i]);
+  const int upper = w.nword > 2048 ? (int)rank[2048] : nnz; // first output of the upper 2^16 rows
+  // STRIPES: a task with up to twice (... kSaccStripes times) the outputs the accumulators hold is done in passes over all of its
+  // products, pass p accumulating the outputs [p * cap, (p + 1) * cap) only. A pass costs the loads and the rank lookup of every
+  // product again (0.6 cycles per product and SM) but keeps the accumulation in shared memory: 0.4 cycles against the 1.5 of
+  // one L2 reduction per product in num_bitmap_kernel, the only other home of such a task.
+  for (int lo = 0; lo < nnz; lo += cap) { // uniform per CTA; one pass unless the host sent a larger task (large shape only)
+    const int cnt = min(cap, nnz - lo);
+    if (lo > 0) {
+      for (int i = threadIdx.x; i < cnt; i += THREADS) acc[i] = SR::identity();
+      __syncthreads();
+    }
+    auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
+      const unsigned rr = (unsigned)(row - rbase);
+      const unsigned wd = rr >> 5;
+      const unsigned slot = (unsigned)rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (rr & 31u)) - 1u)) - (unsigned)lo;
+      if (slot < (unsigned)cnt) {
+        if (ROWS_BY_WALK) srow[slot] = (unsigned short)rr;
+        acc_t v;
+        if (MERGE) v = SR::from_out((out_t)aval);
+        else v = SR::mul((typename SR::a_t)aval, mu);
+        SR::template accumulate_shared<FIRST>(&acc[slot], v);
+      }
+    };
+    bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
+    if (ROWS_BY_WALK)
+      for (int i = threadIdx.x; i < cnt; i += THREADS) Cir[obase + lo + i] = rbase + (int)srow[i] + (lo + i >= upper ? 65536 : 0);
+    for (int i = threadIdx.x; i < cnt; i += THREADS) Cval[obase + lo + i] = SR::to_out(acc[i]);
+    if (lo + cap < nnz) __syncthreads(); // the accumulators are reused by the next pass
+  }
 }
 
 } // namespace cbgpu

@@ -473,19 +473,25 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     const int64_t dyn_l = sacc_dynamic_smem(ctx, kSaccThreadsL, kSaccBlocksL, sizeof(FlatQueueT<kSaccThreadsL>));
     // second version of the kernel (option sacc_v2, bit per shape): 16-bit ranks, and for the small and medium shape (bit 3: the
     // large one too, bit 4: not the medium one) a row array beside the accumulators; needs max_words <= 16 * THREADS (vector scan)
-    const bool v2_s = (opt.sacc_v2 & 1) && max_words <= 16 * kSaccThreadsS, v2_m = (opt.sacc_v2 & 2) && max_words <= 16 * kSaccThreadsM,
-               v2_l = (opt.sacc_v2 & 4) && max_words <= 16 * kSaccThreadsL;
+    const bool v2_ok = max_words <= 4096; // 16-bit row offsets + the window's half bit: windows of at most 2^17 rows
+    const bool v2_s = (opt.sacc_v2 & 1) && v2_ok && max_words <= 16 * kSaccThreadsS, v2_m = (opt.sacc_v2 & 2) && v2_ok,
+               v2_l = (opt.sacc_v2 & 4) && v2_ok;
     const bool rbw_s = true, rbw_m = !(opt.sacc_v2 & 16), rbw_l = (opt.sacc_v2 & 8) != 0;
     auto cap_of = [&](int64_t dyn, bool v2, bool rbw) -> int64_t {
       int64_t c = (dyn - (int64_t)bm_bytes) / (int64_t)sizeof(acc_t);
       if (v2) // 256 bytes of the budget go to the static workspace the second version adds (64-bit warp totals, the mbarrier)
-        c = std::min<int64_t>(((dyn - 256 - (int64_t)max_words * 6) / (int64_t)(sizeof(acc_t) + (rbw ? 4 : 0))) & ~(int64_t)3, 65532);
+        c = std::min<int64_t>(((dyn - 256 - (int64_t)max_words * 6) / (int64_t)(sizeof(acc_t) + (rbw ? 2 : 0))) & ~(int64_t)3, 65532);
       return (opt.shared_acc && c >= 64) ? c : 0;
     };
     const int64_t lay_s = cap_of(dyn_s, v2_s, rbw_s), lay_m = cap_of(dyn_m, v2_m, rbw_m), lay_l = cap_of(dyn_l, v2_l, rbw_l);
     int64_t cap_s = lay_s, cap_m = lay_m, cap_l = lay_l;
-    if (opt.shared_acc_max > 0) // tests and tuning: shrink the three capacities together so that small inputs reach every shape
+    int64_t pass_l = lay_l; // outputs per pass of the large shape (the accumulator array of the second version)
+    if (opt.shared_acc_max > 0) { // tests and tuning: shrink the three capacities together so that small inputs reach every shape
       cap_l = std::min(cap_l, opt.shared_acc_max), cap_m = std::min(cap_m, opt.shared_acc_max / 2), cap_s = std::min(cap_s, opt.shared_acc_max / 4);
+      pass_l = std::max<int64_t>(std::min(lay_l, opt.shared_acc_max) & ~(int64_t)3, 4);
+    }
+    // the large shape of the second version takes tasks of up to sacc_stripes times its capacity, in as many passes
+    if (v2_l && lay_l > 0 && opt.sacc_stripes > 1) cap_l = std::min<int64_t>(pass_l * std::min<int64_t>(opt.sacc_stripes, 4), 65532);
     if (opt.shared_acc_small_max >= 0) cap_s = std::min(cap_s, opt.shared_acc_small_max);
     if (ntask > 0) {
       // below this many outputs a task is cheaper in the per-warp hash classes than with a window-sized bitmap
@@ -536,9 +542,9 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
     if (nc.count[NUM_SA_L] > 0) {
       CB_KBEGIN(CBGPU_K_NUM_BITMAP_SMEM);
       if (v2_l && rbw_l) {
-        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false, true>, NUM_SA_L, kSaccThreadsL, dyn_l, lay_l));
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false, true>, NUM_SA_L, kSaccThreadsL, dyn_l, pass_l));
       } else if (v2_l) {
-        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false, false>, NUM_SA_L, kSaccThreadsL, dyn_l, lay_l));
+        CB_TRY(launch_v2(num_sacc2_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false, false>, NUM_SA_L, kSaccThreadsL, dyn_l, pass_l));
       } else {
         auto kern = num_sacc_kernel<SR, MERGE, kSaccThreadsL, kSaccBlocksL, false>;
         CB_TRY(optin_smem(ctx, kern, (size_t)dyn_l));
@@ -679,9 +685,16 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       };
       if (nc.count[NUM_RS_8] + nc.count[NUM_RS_16] + nc.count[NUM_RS_32] > 0) {
         CB_KBEGIN(CBGPU_K_NUM_REGSORT);
-        CB_TRY(launch(regsort_kernel<SR, MERGE, 8, true>, NUM_RS_8, 8));
-        CB_TRY(launch(regsort_kernel<SR, MERGE, 16, true>, NUM_RS_16, 16));
-        CB_TRY(launch(regsort_kernel<SR, MERGE, 32, true>, NUM_RS_32, 32));
+        // row << log2(capacity) | position must fit 32 bits below the pad key: blocks of fewer than 2^24 rows sort packed keys
+        if (io.m < ((int64_t)1 << 24) - 1 && opt.regsort_packed) {
+          CB_TRY(launch(regsort_kernel<SR, MERGE, 8, true, true>, NUM_RS_8, 8));
+          CB_TRY(launch(regsort_kernel<SR, MERGE, 16, true, true>, NUM_RS_16, 16));
+          CB_TRY(launch(regsort_kernel<SR, MERGE, 32, true, true>, NUM_RS_32, 32));
+        } else {
+          CB_TRY(launch(regsort_kernel<SR, MERGE, 8, true>, NUM_RS_8, 8));
+          CB_TRY(launch(regsort_kernel<SR, MERGE, 16, true>, NUM_RS_16, 16));
+          CB_TRY(launch(regsort_kernel<SR, MERGE, 32, true>, NUM_RS_32, 32));
+        }
         CB_KEND(CBGPU_K_NUM_REGSORT);
         for (int c = NUM_RS_8; c <= NUM_RS_32; ++c) {
           note_class(CBGPU_K_NUM_REGSORT, nc.count[c], class_weight(nb, num_class, c, false), class_weight(nb, num_class, c, true));

@@ -23,6 +23,10 @@ struct MyPlusTimes {
 typedef SpDCCols<int64_t, double> DCD;
 typedef PlusTimesSRing<double, double> PTDD;
 
+// the indexing semirings under names the overlay does not know -> SubsRef_SR stays on the reference path with them
+struct MyCopy1st : BoolCopy1stSRing<double> {};
+struct MyCopy2nd : BoolCopy2ndSRing<double> {};
+
 static DCD *random_block(int64_t m, int64_t n, int64_t nnz, unsigned seed) {
   std::mt19937_64 g(seed);
   std::tuple<int64_t, int64_t, double> *t = new std::tuple<int64_t, int64_t, double>[nnz];
@@ -159,6 +163,23 @@ int main(int argc, char **argv) {
     ok = same_matrix(Pg, Pc) && Pg.getnnz() > 0;
     std::printf("%s MemEfficientSpGEMM3D overlay vs reference: nnz %lld\n", ok ? "PASS" : "FAIL", (long long)Pg.getnnz());
     if (!ok) diff_report(Pg, Pc);
+    fails += !ok;
+  }
+  {
+    // indexing, unchanged: A(ri, ci) -> SubsRef_SR<BoolCopy1stSRing, BoolCopy2ndSRing> -> two Mult_AnXBn_DoubleBuff calls with
+    // boolean selection matrices (SpParMat.cpp:2515-2566): the overlay's DoubleBuff overload + the BoolCopy device semirings
+    std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+    SpParMat<int64_t, double, DCD> A(random_block(3000, 3000, 70000, 11), grid);
+    FullyDistVec<int64_t, int64_t> ri(grid, 700, 0), ci(grid, 600, 0);
+    std::mt19937_64 g(12);
+    for (int64_t i = 0; i < 700; ++i) ri.SetElement(i, (int64_t)(g() % 3000)); // repeated indices allowed
+    for (int64_t i = 0; i < 600; ++i) ci.SetElement(i, (int64_t)(g() % 3000));
+    SpParMat<int64_t, double, DCD> Bg = A(ri, ci);                                           // -> libcbgpu.so
+    SpParMat<int64_t, double, DCD> Bc = A.SubsRef_SR<MyCopy1st, MyCopy2nd>(ri, ci, false);   // -> reference
+    bool ok = same_matrix(Bg, Bc) && Bg.getnnz() > 0 && Bg.getnrow() == 700 && Bg.getncol() == 600;
+    std::printf("%s SpParMat::operator()(ri, ci) (SubsRef_SR, BoolCopy semirings through Mult_AnXBn_DoubleBuff) overlay vs reference: nnz %lld\n",
+                ok ? "PASS" : "FAIL", (long long)Bg.getnnz());
+    if (!ok) diff_report(Bg, Bc);
     fails += !ok;
   }
   MPI_Finalize();

@@ -21,7 +21,7 @@ def test_unchanged_reference_driver_runs_on_the_device_library():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0, r.stdout + r.stderr[-2000:]
-    assert r.stdout.count("PASS") == 6 and "FAIL" not in r.stdout
+    assert r.stdout.count("PASS") == 7 and "FAIL" not in r.stdout
 
 
 @pytest.mark.gpu
@@ -37,7 +37,7 @@ def test_driver_with_its_own_semiring_structs_runs_on_the_device_library():
     assert r.stdout.count("PASS") == 2 and "FAIL" not in r.stdout
 
 
-@pytest.mark.parametrize("exe,count", [("overlay_driver", 6), ("user_semiring_driver", 2)])
+@pytest.mark.parametrize("exe,count", [("overlay_driver", 7), ("user_semiring_driver", 2)])
 def test_run_time_switch_hands_every_call_back_to_the_reference(exe, count):
     """CBGPU_DISABLE=1: the overloads forward to the reference's own templates (through a semiring type the overlay does not
     know), no context is created and no GPU is needed -- the same binaries pass on the CPU-only build container"""

@@ -187,7 +187,10 @@ def test_shared_accumulators_second_version(ctx, oracle, sr, v2):
     ctx.set_option("force_path", 2)
     try:
         dA, dB = ctx.upload(to_dcsc(typed(A, ta), ta)), ctx.upload(to_dcsc(typed(A, tb), tb))
-        for (wlog2, cap, small, save_min) in ((17, 500, 120, 8192), (17, 0, -1, 64), (10, 400, 100, 64), (11, 0, -1, 8192)):
+        # stripes: the large shape takes tasks of up to `stripes` times its capacity in as many passes over the products
+        for (wlog2, cap, small, save_min, stripes) in ((17, 500, 120, 8192, 2), (17, 0, -1, 64, 2), (10, 400, 100, 64, 3), (11, 0, -1, 8192, 1),
+                                                       (17, 300, 80, 64, 4)):
+            ctx.set_option("sacc_stripes", stripes)
             ctx.set_option("bitmap_window_log2", wlog2)
             ctx.set_option("shared_acc_max", cap)
             ctx.set_option("shared_acc_small_max", small)
@@ -200,12 +203,37 @@ def test_shared_accumulators_second_version(ctx, oracle, sr, v2):
         for x in (dA, dB):
             x.free()
     finally:
-        ctx.set_option("sacc_v2", 0)
+        ctx.set_option("sacc_v2", 15)
+        ctx.set_option("sacc_stripes", 1)
         ctx.set_option("force_path", 0)
         ctx.set_option("bitmap_window_log2", 17)
         ctx.set_option("shared_acc_max", 0)
         ctx.set_option("shared_acc_small_max", -1)
         ctx.set_option("bitmap_save_min_flop", 8192)
+
+
+@pytest.mark.parametrize("v2", [15, 31])
+def test_shared_accumulators_second_version_full_window(ctx, oracle, v2):
+    """windows of 2^17 rows: the 16-bit row offsets of num_sacc2_kernel need the half bit of the window (outputs at or behind
+    rank[2048] lie in the upper 2^16 rows); R-MAT scale 17 squared with the bitmap classes forced, hand-over on and off"""
+    A = rmat(17, 4, seed=77)
+    want = oracle.spgemm(to_csc(A, np.float64), to_csc(A, np.float64), 0)
+    dA = ctx.upload(to_dcsc(A, np.float64))
+    ctx.set_option("sacc_v2", v2)
+    ctx.set_option("force_path", 2)
+    try:
+        for save_min in (8192, 1 << 40):
+            ctx.set_option("bitmap_save_min_flop", save_min)
+            D, st = ctx.spgemm(0, dA, dA, want_stats=True)
+            rows, cols, vals = ctx.download_coo(D)
+            assert_same(cb.SpTuples(A.shape[0], A.shape[1], rows, cols, vals), want, 0)
+            assert st.tasks_bitmap_smem > 0
+            D.free()
+    finally:
+        ctx.set_option("sacc_v2", 15)
+        ctx.set_option("force_path", 0)
+        ctx.set_option("bitmap_save_min_flop", 8192)
+        dA.free()
 
 
 @pytest.mark.parametrize("sr", [0, 2, 3, 4, 5, 7])
@@ -227,12 +255,16 @@ def test_register_sort_runs_across_lanes(ctx, oracle, sr):
             # even columns: the k columns of A that hold the dense rows (long runs); odd ones: some of them plus empty columns of A
             pick = cols if j % 2 == 0 else np.concatenate([cols[: max(1, k // 3)], rng.choice(inner, size=5, replace=False)])
             B[np.unique(pick), j] = rng.integers(1, 4, size=len(np.unique(pick)))
-        for mode in (1, 2):  # 1: numeric pass (default), 2: the symbolic pass counts with the same network
+        # regsort 1: numeric pass (default), 2: the symbolic pass counts with the same network; packed 1: the network sorts
+        # row << log2(capacity) | position and the values are fetched afterwards (default), 0: key + value through the network
+        for mode, packed in ((1, 1), (2, 1), (1, 0)):
             ctx.set_option("regsort", mode)
+            ctx.set_option("regsort_packed", packed)
             try:
                 check_pair(ctx, oracle, sr, typed(A.tocsc(), ta), typed(B.tocsc(), tb))
             finally:
                 ctx.set_option("regsort", 1)
+                ctx.set_option("regsort_packed", 1)
 
 
 @pytest.mark.parametrize("sr", range(9))
