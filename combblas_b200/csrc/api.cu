@@ -548,7 +548,6 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "fiber_fused")) return &o.fiber_fused;
   if (!strcmp(name, "fiber_pipeline")) return &o.fiber_pipeline;
-  if (!strcmp(name, "hash_rank_sort")) return &o.hash_rank_sort;
   return nullptr;
 }
 int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_process, int idx_bytes, int in_val_bytes,
@@ -567,10 +566,6 @@ int cbgpu_calculate_phases(int64_t max_local_nnz_a, int64_t nnz_product_per_proc
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value) {
   int64_t *s = option_slot(ctx, name);
   if (!s) return set_error(ctx, CBGPU_ERR_INVALID, "unknown option %s", name);
-#ifndef CBGPU_EXPERIMENTAL_RANK_SORT
-  if (!strcmp(name, "hash_rank_sort") && value != 0)
-    return set_error(ctx, CBGPU_ERR_UNSUPPORTED, "hash_rank_sort is not compiled in (make EXTRA=-DCBGPU_EXPERIMENTAL_RANK_SORT)");
-#endif
   if (!strcmp(name, "bitmap_cta_threads") && value != 256 && value != 512)
     return set_error(ctx, CBGPU_ERR_INVALID, "bitmap_cta_threads must be 256 or 512");
   if (!strcmp(name, "bitmap_small_threads") && value != 128 && value != 256)

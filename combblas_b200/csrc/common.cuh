@@ -39,7 +39,6 @@ struct Options {
   int64_t regsort_packed = 1;      // numeric register sort on row << log2(capacity) | position where the block has fewer than 2^24 rows (values fetched after the sort); 0 = key + value through the network
   int64_t force_path = 0;          // debugging: 1 = hash only (where it fits), 2 = bitmap only
   int64_t summa_fused = 1;         // 1 = all SUMMA stages as one stacked local multiply, 0 = stage loop + merge
-  int64_t hash_rank_sort = 0;      // per-warp hash classes: rank the hits by counting instead of sorting them (to be validated)
   int64_t fiber_fused = 1;         // 3D: replicate the inputs along the fiber instead of reducing partial results (see dist.cu); 0 = the reference's fiber reduction
   int64_t fiber_pipeline = 0;      // fiber_fused == 0 only: second host thread + stream overlaps the fiber reduction of slab p with the multiply of slab p+1
   int64_t merge_engine = 0;        // 1 = k-way merges through the accumulation engine instead of streaming 2-way rounds

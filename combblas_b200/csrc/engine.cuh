@@ -56,9 +56,6 @@ struct Source {
   // tasks (null task_col: task t is column t over all windows)
   const int32_t *task_col;
   const uint32_t *task_win;
-#ifdef CBGPU_EXPERIMENTAL_RANK_SORT
-  int rank_sort; // per-warp hash classes: order the hits by counting smaller keys instead of a bitonic sort (option hash_rank_sort)
-#endif
 };
 
 struct Task {
@@ -883,23 +880,6 @@ num_hash_kernel(Source<SR, MERGE> s, const int32_t *order, int64_t count, const 
   group_sync<GROUP_WARPS>();
   const int n = *cnt;
   const int64_t obase = taskptr[t];
-#ifdef CBGPU_EXPERIMENTAL_RANK_SORT // build with `make EXTRA=-DCBGPU_EXPERIMENTAL_RANK_SORT`: written when no GPU time was left to run it
-  if (GROUP_WARPS == 1 && s.rank_sort) {
-    // The keys of a task are distinct, so the sorted position of a hit is the number of smaller keys: every lane counts
-    // them for its hits against broadcast reads of the whole list (n <= 256) -- no barriers, no dependent shared-memory
-    // round trips, where the bitonic network needs log^2(n)/2 of them.
-    const unsigned *keyhi = reinterpret_cast<const unsigned *>(sortbuf) + 1; // high word of entry j at keyhi[2 * j]
-    for (int i = gtid; i < n; i += GT) {
-      const unsigned long long e = sortbuf[i];
-      const unsigned key = (unsigned)(e >> 32);
-      int r = 0;
-      for (int j = 0; j < n; ++j) r += keyhi[2 * j] < key ? 1 : 0;
-      Cir[obase + r] = (int32_t)key;
-      Cval[obase + r] = SR::to_out(acc[(unsigned)e]);
-    }
-    return;
-  }
-#endif
   int P = 2;
   while (P < n) P <<= 1;
   for (int i = n + gtid; i < P; i += GT) sortbuf[i] = ~0ull;

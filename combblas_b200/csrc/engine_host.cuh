@@ -194,9 +194,6 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
   src.N = io.ncolA;
   src.task_col = nullptr;
   src.task_win = nullptr;
-#ifdef CBGPU_EXPERIMENTAL_RANK_SORT
-  src.rank_sort = (int)opt.hash_rank_sort;
-#endif
 
   // ---- K1: products per column, then tasks
   int64_t *colflop = nullptr;

@@ -143,9 +143,11 @@ int cbgpu_memory_in_use(cbgpu_ctx *ctx, int64_t *live_bytes);
  * "bitmap_min_nnz" smallest task the bitmap path takes, "light_max" products up to which a column stays one task,
  * "shared_acc" / "shared_acc_max" / "shared_acc_small_max" shared-memory accumulator classes, "bitmap_save_mb" /
  * "bitmap_save_min_flop" symbolic -> numeric hand-over, "bitmap_cta_threads", "bitmap_small_threads", "force_path" (tests:
- * 1 hash only, 2 bitmap only), "regsort" (1: tasks with <= 256 products and segments sorted in registers), "sacc_v2" (bit per CTA shape: second
- * version of the shared-accumulator kernels), "merge_engine", "merge_tma" (streaming merge with bulk tile copies), "validate_uploads",
- * "summa_fused", "fiber_fused", "fiber_pipeline" */
+ * 1 hash only, 2 bitmap only), "regsort" (1: tasks with <= 256 products and segments sorted in registers) / "regsort_packed"
+ * (row and staging position sorted as one 32-bit key), "sacc_v2" (bit per CTA shape: second version of the shared-accumulator
+ * kernels) / "sacc_stripes" (passes of the large shape over tasks above its capacity), "bitmap_small_minblocks",
+ * "merge_engine", "merge_tma" (streaming merge with bulk tile copies), "validate_uploads", "summa_fused", "fiber_fused",
+ * "fiber_pipeline" */
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value);
 int cbgpu_get_option(cbgpu_ctx *ctx, const char *name, int64_t *value);
 /* kernels launched by this context so far (bench.py's gpu_launches) */

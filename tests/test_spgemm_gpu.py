@@ -532,25 +532,6 @@ def test_large_scale_properties(ctx):
     C.free()
 
 
-@pytest.mark.skipif(os.environ.get("CBGPU_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="options written without GPU time to validate them; run with CBGPU_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("sr", [0, 3, 5])
-def test_experimental_hash_rank_sort(ctx, oracle, sr):
-    """option hash_rank_sort (library built with EXTRA=-DCBGPU_EXPERIMENTAL_RANK_SORT): the per-warp hash classes order
-    their hits by counting smaller keys (no bitonic sort)"""
-    ctx.set_option("hash_rank_sort", 1)
-    ctx.set_option("force_path", 1)  # hash wherever it fits
-    try:
-        A = rmat(12, 8, seed=6)
-        B = rmat(12, 4, seed=7)
-        check_pair(ctx, oracle, sr, typed(A, SR_DTYPES[sr][0]), typed(B, SR_DTYPES[sr][1]))
-        ctx.set_option("force_path", 0)
-        check_pair(ctx, oracle, sr, typed(A, SR_DTYPES[sr][0]), typed(A, SR_DTYPES[sr][1]))
-    finally:
-        ctx.set_option("hash_rank_sort", 0)
-        ctx.set_option("force_path", 0)
-
-
 def test_failed_allocation_leaks_nothing(ctx):
     """a product whose result cannot be allocated (R-MAT scale 21 squared: about 350 GB) fails with NOMEM after the symbolic
     pass and gives every temporary back: the memory the library holds is the same before and after, and the phased multiply
