@@ -1235,14 +1235,16 @@ sym_bitmap_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t count, int64
   const Window w = task_window(s, k, m);
   bitmap_mark(s, k, &queue, bits, w.nword, w.rbase);
   const int nnz = bitmap_scan<false>(bits, nullptr, w.nword, warp_sums);
-  if (r.slot >= 0) { // uniform per CTA
-    const uint4 *src = reinterpret_cast<const uint4 *>(bits);
-    uint4 *dst = reinterpret_cast<uint4 *>(saved + (int64_t)r.slot * save_stride);
-    const int nvec = (w.nword + 3) >> 2;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x == 0) slot_of_task[t] = r.slot;
+  if (threadIdx.x == 0) {
+    tasknnz[t] = nnz;
+    if (r.slot >= 0) { // the words leave as one bulk store of the TMA unit (the scan ended with a barrier: they are final)
+      fence_proxy_async();
+      bulk_store(saved + (int64_t)r.slot * save_stride, bits, (unsigned)((w.nword + 3) >> 2) * 16u);
+      bulk_commit();
+      slot_of_task[t] = r.slot;
+      bulk_wait_read(); // shared memory must outlive the read; the write completes before the kernel does
+    }
   }
-  if (threadIdx.x == 0) tasknnz[t] = nnz;
 }
 
 // ranked words of a task in shared memory: taken from the symbolic pass if it stored them, marked again otherwise
