@@ -544,7 +544,7 @@ static int64_t *option_slot(cbgpu_ctx *ctx, const char *name) {
   if (!strcmp(name, "merge_tma")) return &o.merge_tma;
   if (!strcmp(name, "validate_uploads")) return &o.validate_uploads;
   if (!strcmp(name, "sacc_v2")) return &o.sacc_v2;
-  if (!strcmp(name, "sacc_stripes")) return &o.sacc_stripes;
+  if (!strcmp(name, "sacc_overflow")) return &o.sacc_overflow;
   if (!strcmp(name, "summa_fused")) return &o.summa_fused;
   if (!strcmp(name, "fiber_fused")) return &o.fiber_fused;
   if (!strcmp(name, "fiber_pipeline")) return &o.fiber_pipeline;

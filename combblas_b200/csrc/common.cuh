@@ -32,7 +32,7 @@ struct Options {
   int64_t bitmap_cta_threads = 512; // CTA size of the large-task bitmap kernels (512 or 256)
   int64_t bitmap_small_threads = 128; // CTA size of the small-task bitmap kernels (128 or 256)
   int64_t bitmap_save_mb = 8192;   // HBM budget (MiB) for the presence words the symbolic pass hands to the numeric pass; 0 = off
-  int64_t bitmap_save_min_flop = 8192; // tasks with at least this many products are handed over (4 bytes per 32 rows of the window)
+  int64_t bitmap_save_min_flop = 2048; // tasks with at least this many products are handed over (4 bytes per 32 rows of the window; bulk copies both ways: 8192 -> 2048 is 20 ms per step at R-MAT scale 22)
   int64_t light_max = 256;         // with several row windows, columns up to this many products stay one task (<= 2048)
   int64_t bitmap_small_minblocks = 8; // resident CTAs per SM the 128-thread numeric bitmap kernel is compiled for (8 or 12)
   int64_t regsort = 1;             // tasks with <= 256 products and segments sorted in registers (regsort_kernel): 1 = numeric pass, 2 = symbolic pass too, 0 = per-warp hash classes
@@ -42,7 +42,7 @@ struct Options {
   int64_t fiber_fused = 1;         // 3D: replicate the inputs along the fiber instead of reducing partial results (see dist.cu); 0 = the reference's fiber reduction
   int64_t fiber_pipeline = 0;      // fiber_fused == 0 only: second host thread + stream overlaps the fiber reduction of slab p with the multiply of slab p+1
   int64_t merge_engine = 0;        // 1 = k-way merges through the accumulation engine instead of streaming 2-way rounds
-  int64_t sacc_stripes = 1;        // > 1: the large shared-accumulator shape takes tasks of up to this many times its capacity, one pass over the products per capacity's worth of outputs (2..4; measured slower than the L2-reduction class at R-MAT scale 22: +115 ms per step)
+  int64_t sacc_overflow = 4;       // > 1: the large shared-accumulator shape takes tasks of up to this many times its capacity (at most 65532 outputs); the outputs beyond the capacity accumulate in C with L2 reductions. 1 = such tasks go to num_bitmap_kernel whole
   int64_t validate_uploads = 0;    // 1 = every cbgpu_mat_upload checks the block on the device (cbgpu_mat_validate) before handing it out
   int64_t merge_tma = 1;           // streaming 2-way merge: 1 = persistent CTAs with double-buffered bulk (TMA) tile copies, 0 = one tile per CTA with load/store loops
   int64_t sacc_v2 = 15;            // shared-accumulator numeric classes, second version (16-bit ranks, vector scan, bulk hand-over): bit 0 small, 1 medium, 2 large shape; bit 3: the large shape keeps a row array too, bit 4: the medium shape does not (measured best at R-MAT scale 22: 31)

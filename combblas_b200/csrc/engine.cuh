@@ -1521,34 +1521,46 @@ num_sacc2_kernel(Source<SR, MERGE> s, const TaskRec *recs, int64_t m, int max_wo
     }
   }
   const int upper = w.nword > 2048 ? (int)rank[2048] : nnz; // first output of the upper 2^16 rows
-  // STRIPES: a task with up to twice (... kSaccStripes times) the outputs the accumulators hold is done in passes over all of its
-  // products, pass p accumulating the outputs [p * cap, (p + 1) * cap) only. A pass costs the loads and the rank lookup of every
-  // product again (0.6 cycles per product and SM) but keeps the accumulation in shared memory: 0.4 cycles against the 1.5 of
-  // one L2 reduction per product in num_bitmap_kernel, the only other home of such a task.
-  for (int lo = 0; lo < nnz; lo += cap) { // uniform per CTA; one pass unless the host sent a larger task (large shape only)
-    const int cnt = min(cap, nnz - lo);
-    if (lo > 0) {
-      for (int i = threadIdx.x; i < cnt; i += THREADS) acc[i] = SR::identity();
-      __syncthreads();
-    }
-    auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
-      const unsigned rr = (unsigned)(row - rbase);
-      const unsigned wd = rr >> 5;
-      const unsigned slot = (unsigned)rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (rr & 31u)) - 1u)) - (unsigned)lo;
-      if (slot < (unsigned)cnt) {
-        if (ROWS_BY_WALK) srow[slot] = (unsigned short)rr;
-        acc_t v;
-        if (MERGE) v = SR::from_out((out_t)aval);
-        else v = SR::mul((typename SR::a_t)aval, mu);
-        SR::template accumulate_shared<FIRST>(&acc[slot], v);
+  // OVERFLOW (large shape only; the host sends it tasks of up to 65532 outputs): the first `cap` outputs accumulate in shared
+  // memory as always, the rest go straight into C with one L2 reduction per product, as in num_bitmap_kernel -- which used to
+  // take such a task whole. A task of 30 k outputs with room for 17.8 k keeps 59 % of its products out of the L2 reductions
+  // (1.5 cycles per lane and SM against 0.4 for an exchange). Rows and identities of the overflowing outputs are written first.
+  constexpr bool OVERFLOW = true; // only the large shape is ever sent such a task; compiling the branch out of the other shapes was measured 30 ms per step SLOWER (code generation at the 64-register limit: profiles/r2_sacc_v2_sweep.txt)
+  if (OVERFLOW && nnz > cap) { // uniform per CTA
+    for (int i = cap + (int)threadIdx.x; i < nnz; i += THREADS) Cval[obase + i] = SR::to_out(SR::identity());
+    if (ROWS_BY_WALK) { // (without the row array the unpack above has already written all rows)
+      for (int c = threadIdx.x; c < w.nword; c += THREADS) {
+        unsigned b = bits[c];
+        int o = (int)rank[c];
+        if (o + __popc(b) <= cap) continue;
+        const int rowbase = rbase + (c << 5);
+        while (b) {
+          if (o >= cap) Cir[obase + o] = rowbase + __ffs(b) - 1;
+          ++o;
+          b &= b - 1;
+        }
       }
-    };
-    bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
-    if (ROWS_BY_WALK)
-      for (int i = threadIdx.x; i < cnt; i += THREADS) Cir[obase + lo + i] = rbase + (int)srow[i] + (lo + i >= upper ? 65536 : 0);
-    for (int i = threadIdx.x; i < cnt; i += THREADS) Cval[obase + lo + i] = SR::to_out(acc[i]);
-    if (lo + cap < nnz) __syncthreads(); // the accumulators are reused by the next pass
+    }
+    __syncthreads(); // the identities are in place before any thread of the CTA reduces into them
   }
+  auto use = [&](int row, aval_t aval, typename SR::b_t mu) {
+    const unsigned rr = (unsigned)(row - rbase);
+    const unsigned wd = rr >> 5;
+    const unsigned slot = (unsigned)rank[wd] + (unsigned)__popc(bits[wd] & ((1u << (rr & 31u)) - 1u));
+    acc_t v;
+    if (MERGE) v = SR::from_out((out_t)aval);
+    else v = SR::mul((typename SR::a_t)aval, mu);
+    if (!OVERFLOW || slot < (unsigned)cap) {
+      if (ROWS_BY_WALK) srow[slot] = (unsigned short)rr;
+      SR::template accumulate_shared<FIRST>(&acc[slot], v);
+    } else {
+      SR::accumulate_out(&Cval[obase + slot], v);
+    }
+  };
+  bitmap_walk<SR, MERGE, true>(s, k, &queue, use, false, restage); // ends with __syncthreads
+  if (ROWS_BY_WALK)
+    for (int i = threadIdx.x; i < first; i += THREADS) Cir[obase + i] = rbase + (int)srow[i] + (i >= upper ? 65536 : 0);
+  for (int i = threadIdx.x; i < first; i += THREADS) Cval[obase + i] = SR::to_out(acc[i]);
 }
 
 } // namespace cbgpu

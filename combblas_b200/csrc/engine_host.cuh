@@ -487,8 +487,9 @@ int run_engine(cbgpu_ctx_impl *ctx, Source<SR, MERGE> src, const EngineIO &io) {
       cap_l = std::min(cap_l, opt.shared_acc_max), cap_m = std::min(cap_m, opt.shared_acc_max / 2), cap_s = std::min(cap_s, opt.shared_acc_max / 4);
       pass_l = std::max<int64_t>(std::min(lay_l, opt.shared_acc_max) & ~(int64_t)3, 4);
     }
-    // the large shape of the second version takes tasks of up to sacc_stripes times its capacity, in as many passes
-    if (v2_l && lay_l > 0 && opt.sacc_stripes > 1) cap_l = std::min<int64_t>(pass_l * std::min<int64_t>(opt.sacc_stripes, 4), 65532);
+    // the large shape of the second version also takes tasks above its capacity (16-bit ranks: up to 65532 outputs, or
+    // sacc_overflow times the capacity): what does not fit the accumulators goes to C with L2 reductions
+    if (v2_l && lay_l > 0 && opt.sacc_overflow > 1) cap_l = std::min<int64_t>(pass_l * opt.sacc_overflow, 65532);
     if (opt.shared_acc_small_max >= 0) cap_s = std::min(cap_s, opt.shared_acc_small_max);
     if (ntask > 0) {
       // below this many outputs a task is cheaper in the per-warp hash classes than with a window-sized bitmap

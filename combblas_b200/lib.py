@@ -443,7 +443,7 @@ class Context:
 
 OPTION_NAMES = ["bitmap_window_log2", "bitmap_min_nnz", "shared_acc", "shared_acc_max", "shared_acc_small_max", "bitmap_cta_threads", "bitmap_small_threads",
                 "bitmap_small_minblocks", "bitmap_save_mb", "bitmap_save_min_flop", "light_max", "force_path", "merge_engine", "summa_fused", "fiber_fused", "fiber_pipeline", "regsort", "regsort_packed",
-                "sacc_v2", "sacc_stripes", "merge_tma", "validate_uploads"]
+                "sacc_v2", "sacc_overflow", "merge_tma", "validate_uploads"]
 
 
 class SlabPipeline:

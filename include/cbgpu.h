@@ -145,7 +145,7 @@ int cbgpu_memory_in_use(cbgpu_ctx *ctx, int64_t *live_bytes);
  * "bitmap_save_min_flop" symbolic -> numeric hand-over, "bitmap_cta_threads", "bitmap_small_threads", "force_path" (tests:
  * 1 hash only, 2 bitmap only), "regsort" (1: tasks with <= 256 products and segments sorted in registers) / "regsort_packed"
  * (row and staging position sorted as one 32-bit key), "sacc_v2" (bit per CTA shape: second version of the shared-accumulator
- * kernels) / "sacc_stripes" (passes of the large shape over tasks above its capacity), "bitmap_small_minblocks",
+ * kernels) / "sacc_overflow" (the large shape takes tasks of up to this many times its capacity, the rest of their outputs accumulate in C), "bitmap_small_minblocks",
  * "merge_engine", "merge_tma" (streaming merge with bulk tile copies), "validate_uploads", "summa_fused", "fiber_fused",
  * "fiber_pipeline" */
 int cbgpu_set_option(cbgpu_ctx *ctx, const char *name, int64_t value);

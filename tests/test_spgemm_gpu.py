@@ -187,10 +187,11 @@ def test_shared_accumulators_second_version(ctx, oracle, sr, v2):
     ctx.set_option("force_path", 2)
     try:
         dA, dB = ctx.upload(to_dcsc(typed(A, ta), ta)), ctx.upload(to_dcsc(typed(A, tb), tb))
-        # stripes: the large shape takes tasks of up to `stripes` times its capacity in as many passes over the products
+        # sacc_overflow: the large shape takes tasks of up to that many times its capacity; the outputs beyond the capacity
+        # accumulate in C with L2 reductions (1: such tasks go to num_bitmap_kernel whole)
         for (wlog2, cap, small, save_min, stripes) in ((17, 500, 120, 8192, 2), (17, 0, -1, 64, 2), (10, 400, 100, 64, 3), (11, 0, -1, 8192, 1),
                                                        (17, 300, 80, 64, 4)):
-            ctx.set_option("sacc_stripes", stripes)
+            ctx.set_option("sacc_overflow", stripes)
             ctx.set_option("bitmap_window_log2", wlog2)
             ctx.set_option("shared_acc_max", cap)
             ctx.set_option("shared_acc_small_max", small)
@@ -204,12 +205,12 @@ def test_shared_accumulators_second_version(ctx, oracle, sr, v2):
             x.free()
     finally:
         ctx.set_option("sacc_v2", 15)
-        ctx.set_option("sacc_stripes", 1)
+        ctx.set_option("sacc_overflow", 4)
         ctx.set_option("force_path", 0)
         ctx.set_option("bitmap_window_log2", 17)
         ctx.set_option("shared_acc_max", 0)
         ctx.set_option("shared_acc_small_max", -1)
-        ctx.set_option("bitmap_save_min_flop", 8192)
+        ctx.set_option("bitmap_save_min_flop", 2048)
 
 
 @pytest.mark.parametrize("v2", [15, 31])
@@ -232,7 +233,7 @@ def test_shared_accumulators_second_version_full_window(ctx, oracle, v2):
     finally:
         ctx.set_option("sacc_v2", 15)
         ctx.set_option("force_path", 0)
-        ctx.set_option("bitmap_save_min_flop", 8192)
+        ctx.set_option("bitmap_save_min_flop", 2048)
         dA.free()
 
 
