@@ -417,6 +417,33 @@ def test_streaming_merge_bulk_copies_every_value_width(ctx, port_oracle, sr):
     assert np.array_equal(got[0].rows, got[1].rows) and np.array_equal(got[0].cols, got[1].cols)
 
 
+@pytest.mark.parametrize("v2", [15, 0])
+@pytest.mark.parametrize("sr", [0, 3, 5])
+def test_merge_through_the_engine_large_columns(ctx, port_oracle, sr, v2):
+    """the k-way merge through the accumulation engine (option merge_engine = 1; always taken for k = 1): columns of thousands of
+    entries reach the bitmap classes with MERGE = true -- shared accumulators (second and first version), the overflow into C
+    (capacity lowered), the register-sort classes for the short columns"""
+    ta, tb, _ = SR_DTYPES[sr]
+    A = rmat(13, 16, seed=61)
+    a = to_csc(typed(A, ta), ta)
+    parts = [port_oracle.spgemm(a, to_csc(typed(rmat(13, 6, seed=70 + i), tb), tb), sr) for i in range(3)]
+    want3 = port_oracle.merge(parts, sr)
+    want1 = port_oracle.merge(parts[:1], sr)
+    ctx.set_option("merge_engine", 1)
+    ctx.set_option("sacc_v2", v2)
+    try:
+        for cap in (0, 600):
+            ctx.set_option("shared_acc_max", cap)
+            ctx.set_option("shared_acc_small_max", 150 if cap else -1)
+            assert_same(cb.MultiwayMerge(ctx, sr, [dcsc_of(p) for p in parts]), want3, sr)
+            assert_same(cb.MultiwayMerge(ctx, sr, [dcsc_of(parts[0])]), want1, sr)
+    finally:
+        ctx.set_option("merge_engine", 0)
+        ctx.set_option("sacc_v2", 15)
+        ctx.set_option("shared_acc_max", 0)
+        ctx.set_option("shared_acc_small_max", -1)
+
+
 def test_validate_rejects_blocks_the_engine_cannot_take(ctx):
     """cbgpu_mat_validate / option validate_uploads: sorted, in-range blocks pass; unsorted rows (legal after the reference's
     sort=false paths), rows >= m, broken column pointers and unordered column ids are named in the error"""
