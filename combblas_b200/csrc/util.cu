@@ -49,7 +49,9 @@ static void flush_big_cache(cbgpu_ctx_impl *ctx) {
 
 int dev_alloc(cbgpu_ctx_impl *ctx, void **p, size_t bytes) {
   *p = nullptr;
-  if (bytes == 0) bytes = 16;
+  // whole 16-byte granules: the bulk (TMA) copies of the streaming merge and of the hand-over read the granule that holds the
+  // last element of an array to its end
+  bytes = bytes == 0 ? 16 : ((bytes + 15) & ~(size_t)15);
   BigCache &bc = big_cache(ctx->device);
   if (bytes >= kBigBlock) {
     std::lock_guard<std::mutex> lock(bc.mu);
