@@ -162,3 +162,16 @@ def sp_two_hits(A, m):
     X = sp.coo_matrix((np.ones(2), (np.zeros(2, int), np.array([r0, r1]))), shape=(1, m)).tocsc()
     X.sort_indices()
     return X
+
+
+@pytest.mark.parametrize("name,sr2,sr1", [("f64", 9, 10), ("i64", 11, 12), ("bool", 13, 14)])
+def test_port_matches_committed_subsref_outputs(port_oracle, name, sr2, sr1):
+    """the C restatement against the committed outputs of the unmodified reference for the indexing semirings
+    (tests/golden/ref_subsref.npz, written by tests/golden/make_golden_subsref.py): bit for bit"""
+    f = "ref_subsref.npz"
+    A, S, T = load(f, name + "_A"), load(f, name + "_S"), load(f, name + "_T")
+    SA, SAT = load(f, name + "_SA"), load(f, name + "_SAT")
+    sa = port_oracle.spgemm(S, A, sr2)
+    assert same_pattern(sa, SA) and np.array_equal(sa.vals, SA.vals)
+    sat = port_oracle.spgemm(sa, T, sr1)
+    assert same_pattern(sat, SAT) and np.array_equal(sat.vals, SAT.vals)
