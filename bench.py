@@ -8,7 +8,9 @@ A "step" is one pass of the hot path: C = A (x) A over PlusTimesSRing<double,dou
                ascending), timed with CUDA events on the launching stream, max over ranks.
   e2e        : same metric through the host-buffer entry points: pinned-host DCSC operands are copied H2D inside the timed
                region, result essentials read back (the product itself, 864 GB at scale 22, stays on the device and is
-               consumed slab by slab, as MemEfficientSpGEMM's caller consumes it).
+               consumed slab by slab, as MemEfficientSpGEMM's caller consumes it). With several ranks every rank uploads ITS
+               blocks of A and B from pinned host memory inside the timed region and runs the same phased SUMMA (wall clock
+               between barriers, max over ranks).
   roofline   : algorithmic bytes (SURVEY.md section 8d formula with the device layout sI=4, colptr 8) / time, against the
                measured HBM copy bandwidth in MEASURED_PEAKS.json; per-kernel-class breakdown from events inside the library.
   parity     : after the timed steps one more step of the SAME code path runs with checksums: order-independent 64-bit sums
